@@ -1,0 +1,91 @@
+"""ctypes binding of `libegtr_b200.so` (declared in `include/egtr_b200.h`).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C egtr_b200/csrc`.  There is
+no CPU or PyTorch fallback: if the shared object is missing, importing the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libegtr_b200.so")
+
+
+class EgtrError(RuntimeError):
+    pass
+
+
+class ASrc(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("a2", C.c_void_p), ("mode", C.c_int), ("lda", C.c_int),
+                ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
+                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int),
+                ("ldr", C.c_int), ("relu", C.c_int), ("rows_per_b", C.c_int), ("bstride", C.c_int),
+                ("off", C.c_int)]
+
+
+_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes (every function returns int status unless listed in _RESTYPES)
+SIGNATURES = {
+    "egtr_last_error": [],
+    "egtr_abi_version": [],
+    "egtr_launch_count": [],
+    "egtr_launch_count_reset": [],
+    "egtr_split_weight_bf16": [_p, _i, _i, _i, _p, _p],
+    "egtr_gemm_sbf16": [C.POINTER(ASrc), _p, _i, _i, _i, _i, C.POINTER(Epilogue), _p],
+    "egtr_gemm_f32": [C.POINTER(ASrc), _p, _i, _i, _i, C.POINTER(Epilogue), _p],
+    "egtr_msda_fwd_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "egtr_msda_fused_fwd_f32": [_p, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "egtr_add_layernorm_f32": [_p, _p, _p, _p, _i, _i, _p, _p],
+    "egtr_mask_rows_f32": [_p, _i, _i, _p, _i, _p],
+    "egtr_maxpool3x3s2_nhwc_f32": [_p, _i, _i, _i, _i, _p, _p],
+    "egtr_groupnorm_f32": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "egtr_groupnorm_scratch_doubles": [_i, _i],
+    "egtr_levels_geometry_f32": [_p, _i, _i, _i, C.POINTER(_i), _i, _p, _i, _p, _p, _p, _p, _p],
+    "egtr_mha_core_f32": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "egtr_small_linear_f32": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p],
+    "egtr_relation_pair_hidden_f32": [_p, _p, _i, _p, _i, _i, _i, _p, _p],
+    "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+}
+_RESTYPES = {
+    "egtr_last_error": C.c_char_p,
+    "egtr_launch_count": _ll,
+    "egtr_launch_count_reset": None,
+    "egtr_groupnorm_scratch_doubles": _ll,
+}
+_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version"}
+
+_lib = None
+
+
+def load():
+    """Load the shared object (once).  Raises EgtrError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise EgtrError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(no CPU fallback exists for the EGTR hot path)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library drift
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an entry point and raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name not in _NO_STATUS and rc != 0:
+        raise EgtrError(f"{name} failed (status {rc}): {lib.egtr_last_error().decode()}")
+    return rc

@@ -1,0 +1,138 @@
+// Shared device/host helpers for the EGTR B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/egtr_b200.h"
+
+namespace egtr {
+
+// ----------------------------------------------------------------------------- host errors
+void set_last_error(const char* fmt, ...);
+
+#define EGTR_CHECK(cond, code, ...)                                  \
+  do {                                                               \
+    if (!(cond)) {                                                   \
+      ::egtr::set_last_error(__VA_ARGS__);                           \
+      return (code);                                                 \
+    }                                                                \
+  } while (0)
+
+#define EGTR_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::egtr::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                         \
+      return EGTR_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+int num_sms();
+
+// ----------------------------------------------------------------------------- A-operand source
+// Where the rows of a GEMM's left operand come from.  One description serves the tcgen05 kernel's
+// software producer and the SIMT kernel: rows are 64-float (256 B) contiguous runs in global memory.
+//   mode 0  plain   : row m = a + m*lda                 (+ a2 + m*lda if a2 != nullptr, e.g. x + pos)
+//   mode 1  conv    : implicit im2col over an NHWC tensor; k = (ky*KW + kx)*C + c, zero padding.
+using ASrc = egtr_asrc_t;
+
+struct RowInfo {  // per tile row, decoded once per tile
+  long long base;  // plain: m*lda ; conv: b*H*W (pixel index of the image origin)
+  int iy0, ix0;    // conv: top-left input coordinate of the receptive field (may be negative)
+  int valid;       // 0 -> row beyond M: reads as zeros
+};
+
+__device__ __forceinline__ RowInfo decode_row(const ASrc& s, long long m, long long M) {
+  RowInfo r;
+  r.valid = m < M;
+  if (s.mode == 0) {
+    r.base = m * (long long)s.lda;
+    r.iy0 = r.ix0 = 0;
+  } else if (s.mode == 2) {
+    long long ohw = (long long)s.OH * s.OW;
+    long long b = m / ohw;
+    int rem = (int)(m - b * ohw);
+    int oy = rem / s.OW, ox = rem - oy * s.OW;
+    r.base = b;  // image index; elements are gathered one by one from the NCHW planes
+    r.iy0 = oy * s.stride - s.pad;
+    r.ix0 = ox * s.stride - s.pad;
+  } else {
+    long long ohw = (long long)s.OH * s.OW;
+    long long b = m / ohw;
+    int rem = (int)(m - b * ohw);
+    int oy = rem / s.OW, ox = rem - oy * s.OW;
+    r.base = b * (long long)s.H * s.W;
+    r.iy0 = oy * s.stride - s.pad;
+    r.ix0 = ox * s.stride - s.pad;
+  }
+  return r;
+}
+
+// Offset (in floats) of the 16B-aligned run starting at column k0 of this row, or -1 for zeros.
+// For conv mode k0..k0+63 must not straddle a filter tap (C % 64 == 0 or the run is < C).
+__device__ __forceinline__ long long row_offset(const ASrc& s, const RowInfo& r, int k0) {
+  if (!r.valid) return -1;
+  if (s.mode == 0) return r.base + k0;
+  int tap = k0 / s.C;
+  int c0 = k0 - tap * s.C;
+  int ky = tap / s.KW, kx = tap - ky * s.KW;
+  int iy = r.iy0 + ky, ix = r.ix0 + kx;
+  if ((unsigned)iy >= (unsigned)s.H || (unsigned)ix >= (unsigned)s.W) return -1;
+  return (r.base + (long long)iy * s.W + ix) * s.C + c0;
+}
+
+// mode 2 (NCHW stem gather): four consecutive k of one row, k = (ky*KW + kx)*C + c, zero beyond KH*KW*C.
+__device__ __forceinline__ float4 gather4_nchw(const ASrc& s, long long img, int iy0, int ix0, int k) {
+  float v[4];
+  const int kmax = s.KH * s.KW * s.C;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kk = k + j;
+    float x = 0.f;
+    if (kk < kmax) {
+      const int tap = kk / s.C, c = kk - tap * s.C;
+      const int ky = tap / s.KW, kx = tap - ky * s.KW;
+      const int iy = iy0 + ky, ix = ix0 + kx;
+      if ((unsigned)iy < (unsigned)s.H && (unsigned)ix < (unsigned)s.W)
+        x = __ldg(s.a + ((img * s.C + c) * s.H + iy) * (long long)s.W + ix);
+    }
+    v[j] = x;
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ----------------------------------------------------------------------------- epilogue
+// out[orow(m)*ldo + n] = act(acc + bias[n] + res[orow(m)*ldr + n])
+//   orow(m) = (m / rows_per_b) * bstride + off + m % rows_per_b   (level slices of [B,S,C] buffers)
+using Epilogue = egtr_epilogue_t;
+
+__device__ __forceinline__ long long out_row(const Epilogue& e, long long m) {
+  if (e.rows_per_b <= 0) return m;
+  long long b = m / e.rows_per_b;
+  return b * e.bstride + e.off + (m - b * e.rows_per_b);
+}
+
+// ----------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo == x to ~2^-17 relative.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+}  // namespace egtr

@@ -1,0 +1,95 @@
+// fp32 CUDA-core GEMM with the same operand-source / epilogue contract as the tcgen05 kernel.
+// Used where tensor-core tiles do not fit (K % 64 != 0, a few hundred rows with N < 64) and as the
+// independent cross-check of the tensor-core path in tests.  64x64 tile, BK = 16, 4x4 per thread.
+#include "common.cuh"
+
+namespace egtr {
+void count_launch();
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Ws[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const long long m0 = (long long)blockIdx.y * TM;
+  const int n0 = blockIdx.x * TN;
+  const int lrow = tid >> 2, lq = tid & 3;  // loader mapping: one float4 per thread per tile
+  const RowInfo ri = decode_row(src, m0 + lrow, M);
+  const int wn = n0 + lrow;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = av;
+    const long long off = src.mode == 2 ? -1 : row_offset(src, ri, k0);
+    if (src.mode == 2) {
+      if (ri.valid) av = gather4_nchw(src, ri.base, ri.iy0, ri.ix0, k0 + lq * 4);
+    } else if (off >= 0) {
+      av = __ldg((const float4*)(src.a + off) + lq);
+      if (src.a2) {
+        const float4 p = __ldg((const float4*)(src.a2 + off) + lq);
+        av.x += p.x; av.y += p.y; av.z += p.z; av.w += p.w;
+      }
+    }
+    if (wn < N) wv = __ldg((const float4*)(w + (long long)wn * K + k0) + lq);
+    __syncthreads();
+    As[lq * 4 + 0][lrow] = av.x; As[lq * 4 + 1][lrow] = av.y; As[lq * 4 + 2][lrow] = av.z; As[lq * 4 + 3][lrow] = av.w;
+    Ws[lq * 4 + 0][lrow] = wv.x; Ws[lq * 4 + 1][lrow] = wv.y; Ws[lq * 4 + 2][lrow] = wv.z; Ws[lq * 4 + 3][lrow] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a = *(const float4*)&As[k][ty * 4];
+      const float4 b = *(const float4*)&Ws[k][tx * 4];
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const long long orow = out_row(ep, m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float o = acc[i][j];
+      if (ep.bias) o += __ldg(ep.bias + n);
+      if (ep.res) o += ep.res[orow * ep.ldr + n];
+      if (ep.relu) o = fmaxf(o, 0.f);
+      ep.out[orow * ep.ldo + n] = o;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace egtr
+
+using namespace egtr;
+
+extern "C" int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N, int K, const egtr_epilogue_t* ep,
+                             egtr_stream_t s) {
+  EGTR_CHECK(a && w && ep && a->a && ep->out, EGTR_ERR_ARG, "egtr_gemm_f32: null argument");
+  EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 16 == 0, EGTR_ERR_ARG, "egtr_gemm_f32: need K %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  EGTR_CHECK(a->mode == 0 || (a->mode == 1 && a->C % 16 == 0 && K == a->KH * a->KW * a->C) ||
+                 (a->mode == 2 && K >= a->KH * a->KW * a->C), EGTR_ERR_ARG,
+             "egtr_gemm_f32: conv source needs C %% 16 == 0 and K == KH*KW*C");
+  EGTR_CHECK(a->mode != 0 || a->lda % 4 == 0, EGTR_ERR_ARG, "egtr_gemm_f32: lda %% 4 != 0");
+  dim3 grid(cdiv(N, TN), cdiv(M, TM));
+  EGTR_CHECK(grid.y <= 65535, EGTR_ERR_ARG, "egtr_gemm_f32: M too large for this path (%d)", M);
+  gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*a, w, M, N, K, *ep);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}

@@ -1,0 +1,417 @@
+// D[M,N] = A[M,K] * W[N,K]^T (+bias, +residual, ReLU) on Blackwell tensor cores.
+//
+// Precision: the reference path is fp32 end to end and parity is 1e-3 on the final outputs.  A single
+// bf16 or tf32 product per term measurably fails that (tools/precision_probe.py: 9e-1 / 3e-3 on
+// pred_rel); three bf16 products per term  a*w ~= ah*wh + ah*wl + al*wh  (a = ah + al, w = wh + wl)
+// reproduce fp32 to ~5e-5.  So every k-step issues three tcgen05.mma (kind::f16, BF16 inputs, FP32
+// accumulate in TMEM) — which costs nothing extra against a TF32 kernel because at 128x256 tiles both
+// are bound by operand delivery from L2, not by the tensor pipe.
+//
+// Structure: persistent, warp-specialised, one CTA per SM.
+//   warps 0-3  epilogue : tcgen05.ld accumulator rows -> bias/residual/ReLU -> global fp32
+//   warp  4    TMA      : weight tiles (hi and lo planes, pre-split once at load) -> 128B-swizzled smem
+//   warp  5    MMA      : one lane issues tcgen05.mma; owns the TMEM allocation
+//   warps 6-9  A-producer: LDG fp32 activation rows (plain rows, x+pos, or an implicit-im2col gather
+//                          for convolutions), split to bf16 hi/lo in registers, st.shared into the same
+//                          swizzled K-major layout TMA would have produced — activations stay fp32 in
+//                          HBM and there is never an im2col buffer.
+// Pipelines: smem stage full/empty mbarriers (producers+TMA -> MMA), two TMEM accumulator stages
+// with full/empty mbarriers (MMA -> epilogue) so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace egtr {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 320;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // one bf16 plane
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4096 /*barriers, row info*/;
+};
+
+struct RowSlot {  // RowInfo packed for shared memory
+  long long base;
+  int iy0, ix0;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
+                  int Npad, int K, int* __restrict__ err) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* ctrl = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = (uint64_t*)ctrl;           // [STAGES]
+  uint64_t* empty_bar = full_bar + C::STAGES;     // [STAGES]
+  uint64_t* tmem_full = empty_bar + C::STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_holder = (uint32_t*)(tmem_empty + 2);
+  RowSlot* rows = (RowSlot*)(ctrl + 256);         // [128] x 16 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = Npad / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / BLOCK_K;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_w);
+    for (int i = 0; i < C::STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 128 + 1);  // 128 producer threads + the TMA thread's expect_tx arrive
+      ptx::mbar_init(&empty_bar[i], 1);       // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) ptx::tmem_alloc<C::TMEM_COLS>(tmem_holder);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA: weight tiles
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 101);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_TILE_BYTES);
+          ptx::tma_load_2d(st + 2 * A_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
+          ptx::tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, Npad + n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, err, 102);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase, err, 103);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 2;  // bytes along K inside the swizzle row
+            const uint64_t dah = ptx::umma_desc_sw128(a_hi + koff), dal = ptx::umma_desc_sw128(a_lo + koff);
+            const uint64_t dbh = ptx::umma_desc_sw128(b_hi + koff), dbl = ptx::umma_desc_sw128(b_lo + koff);
+            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb | ks) != 0);  // small terms first
+            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ A producer (4 warps)
+    const int p = warp - 6;
+    const int ptid = p * 32 + lane;
+    const int kc = lane & 15;   // which float4 of the 64-float run
+    const int rsub = lane >> 4; // 0/1: two rows per warp-wide load
+    int stage = 0, phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const long long m0 = (long long)(t / n_tiles) * BLOCK_M;
+      ptx::named_bar_sync(1, 128);  // previous tile's readers are done with `rows`
+      {
+        RowInfo ri = decode_row(src, m0 + ptid, M);
+        RowSlot rs;
+        rs.base = ri.valid ? ri.base : -1;
+        rs.iy0 = ri.iy0;
+        rs.ix0 = ri.ix0;
+        rows[ptid] = rs;
+      }
+      ptx::named_bar_sync(1, 128);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int k0 = kb * BLOCK_K;
+        int ky = 0, kx = 0, c0 = k0;
+        if (src.mode == 1) {
+          const int tap = k0 / src.C;
+          c0 = k0 - tap * src.C;
+          ky = tap / src.KW;
+          kx = tap - ky * src.KW;
+        }
+        float4 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = p * 32 + 2 * i + rsub;
+          const RowSlot rs = rows[r];
+          long long off = -1;
+          if (src.mode == 2) {
+            v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+          }
+          if (rs.base >= 0) {
+            if (src.mode == 0) {
+              off = rs.base + k0;
+            } else {
+              const int iy = rs.iy0 + ky, ix = rs.ix0 + kx;
+              if ((unsigned)iy < (unsigned)src.H && (unsigned)ix < (unsigned)src.W)
+                off = (rs.base + (long long)iy * src.W + ix) * src.C + c0;
+            }
+          }
+          if (off >= 0) {
+            v[i] = __ldg((const float4*)(src.a + off) + kc);
+            if (src.a2 != nullptr) {
+              const float4 w = __ldg((const float4*)(src.a2 + off) + kc);
+              v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
+            }
+          } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+        uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = p * 32 + 2 * i + rsub;
+          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+          split_bf16(v[i].x, h0, l0);
+          split_bf16(v[i].y, h1, l1);
+          split_bf16(v[i].z, h2, l2);
+          split_bf16(v[i].w, h3, l3);
+          const uint32_t o = ptx::sw128_offset(r, kc >> 1) + (kc & 1) * 8;
+          uint2 ph, pl;
+          ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+          pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+          *(uint2*)(a_hi + o) = ph;
+          *(uint2*)(a_lo + o) = pl;
+        }
+        ptx::fence_proxy_async_smem();  // make the st.shared visible to the tensor core's async proxy
+        ptx::mbar_arrive(&full_bar[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quadrants)
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      const long long m = (long long)(t / n_tiles) * BLOCK_M + warp * 32 + lane;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
+      ptx::tc_fence_after();
+      const long long orow = out_row(ep, m);
+      float* __restrict__ optr = ep.out + orow * ep.ldo;
+      const float* __restrict__ rptr = ep.res ? ep.res + orow * ep.ldr : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
+        ptx::tmem_ld_wait();
+        if (m < M) {
+          const int nb = n0 + c0;
+          if (nb + 32 <= N && (ep.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
+              o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
+              if (ep.bias) {
+                const float4 b = __ldg((const float4*)(ep.bias + nb + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (rptr) {
+                const float4 q = *(const float4*)(rptr + nb + j);
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+              }
+              if (ep.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *(float4*)(optr + nb + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              if (n < N) {
+                float o = __uint_as_float(r[j]);
+                if (ep.bias) o += __ldg(ep.bias + n);
+                if (rptr) o += rptr[n];
+                if (ep.relu) o = fmaxf(o, 0.f);
+                optr[n] = o;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int npad, k, block_n;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && npad == o.npad && k == o.k && block_n == o.block_n; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)k.npad * 1315423911u ^ (size_t)k.k * 2654435761u ^ (size_t)k.block_n;
+  }
+};
+
+// Weight tensor maps are immutable per (pointer, shape): encode once, reuse for every launch.
+int weight_tensor_map(const void* planes, int Npad, int K, int block_n, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  MapKey key{planes, Npad, K, block_n};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EGTR_OK;
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  EGTR_CHECK(enc != nullptr, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)2 * Npad};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(planes), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  cache.emplace(key, m);
+  *out = m;
+  return EGTR_OK;
+}
+
+int* device_error_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+template <int BLOCK_N>
+int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap tmap;
+  int rc = weight_tensor_map(planes, Npad, K, BLOCK_N, &tmap);
+  if (rc != EGTR_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, device_error_flag());
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+// fp32 [N,K] -> bf16 hi/lo planes [2][Npad][K]
+__global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, int Npad, __nv_bfloat16* __restrict__ planes) {
+  const long long total = (long long)Npad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K);
+    __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
+    if (n < N) split_bf16(w[i], h, l);
+    planes[i] = h;
+    planes[total + i] = l;
+  }
+}
+
+}  // namespace
+
+void count_launch();
+
+}  // namespace egtr
+
+using namespace egtr;
+
+extern "C" int egtr_split_weight_bf16(const float* w, int N, int K, int Npad, void* planes, egtr_stream_t s) {
+  EGTR_CHECK(w && planes && N > 0 && K > 0 && Npad >= N && Npad % 64 == 0, EGTR_ERR_ARG,
+             "egtr_split_weight_bf16: bad arguments (N=%d K=%d Npad=%d)", N, K, Npad);
+  const long long total = (long long)Npad * K;
+  int grid = cdiv(total, 256);
+  if (grid > 4 * 148) grid = 4 * 148;
+  split_weight_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(w, N, K, Npad, (__nv_bfloat16*)planes);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M, int N, int Npad, int K,
+                               const egtr_epilogue_t* ep, egtr_stream_t s) {
+  EGTR_CHECK(a && w_planes && ep && a->a && ep->out, EGTR_ERR_ARG, "egtr_gemm_sbf16: null argument");
+  EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0 && Npad % 64 == 0 && Npad >= N, EGTR_ERR_ARG,
+             "egtr_gemm_sbf16: need K %% 64 == 0 and Npad %% 64 == 0 (M=%d N=%d Npad=%d K=%d)", M, N, Npad, K);
+  EGTR_CHECK(a->mode == 0 || (a->mode == 1 && a->C % 64 == 0 && K == a->KH * a->KW * a->C) ||
+                 (a->mode == 2 && K >= a->KH * a->KW * a->C), EGTR_ERR_ARG,
+             "egtr_gemm_sbf16: conv source needs C %% 64 == 0 and K == KH*KW*C (mode=%d C=%d K=%d)", a->mode, a->C, K);
+  EGTR_CHECK(a->mode != 0 || (a->lda % 4 == 0 && a->lda >= K), EGTR_ERR_ARG, "egtr_gemm_sbf16: lda=%d", a->lda);
+  EGTR_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)w_planes & 127) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16: alignment");
+  count_launch();
+  cudaStream_t st = (cudaStream_t)s;
+  if (Npad % 256 == 0) return launch<256>(*a, w_planes, M, N, Npad, K, *ep, st);
+  if (Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
+  return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);
+}

@@ -1,0 +1,260 @@
+// Multi-scale deformable attention forward (K1 of SURVEY.md §2.3), rewritten for B200.
+//
+// Reference semantics: model/custom_kernel/cuda/ms_deform_im2col_cuda.cuh:237-299 (+ bilinear 33-84):
+//   out[b,q,m,:] = sum_{l,p} w[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]),
+//   pixel coords x = loc_x*W - 0.5, a sample counts only if -1 < y < H and -1 < x < W, corners outside
+//   the map read as zero.
+//
+// The kernel is bound by the SM's L1/L2 gather path (each (q,m) pulls 16 samples x 4 corners x 128 B),
+// not by compulsory HBM traffic, so the design goals are (1) every gather is a full 128-byte line read
+// by 8 lanes x float4, (2) sample arithmetic is done once per sample, not once per channel lane, and
+// (3) queries that share cache lines run in the same CTA: a CTA owns ONE head and a 8x4 pixel patch of
+// encoder queries (neighbouring pixels sample neighbouring tokens), or 32 consecutive decoder queries.
+//   phase 1: 256 threads = 16 (query) x 16 (sample) lanes: read the raw offsets/logits (fused form) or
+//            the precomputed locations/weights (drop-in form), softmax over the 16 samples with
+//            16-lane shuffles, turn each sample into 4 corner token indices + 4 combined weights in smem;
+//   phase 2: 32 groups of 8 lanes: stream the 16 samples of one query, 4 predicated LDG.128 each.
+#include "common.cuh"
+
+namespace egtr {
+void count_launch();
+namespace {
+
+constexpr int QPB = 32;      // queries per CTA
+constexpr int MAX_L = 8;
+constexpr int SLOT_WORDS = 8;                      // 4 token indices + 4 weights
+constexpr int Q_STRIDE = 16 * SLOT_WORDS + 8;      // words per query, padded against bank conflicts
+
+struct Levels {
+  int L;
+  int H[MAX_L], W[MAX_L], start[MAX_L];
+  int patch_start[MAX_L + 1];  // encoder patch enumeration (8x4 pixel patches per level)
+  int patches_x[MAX_L];
+};
+
+struct MsdaArgs {
+  const float* value; int ld_value;       // [B,S,...] row stride in floats; head m at column m*32
+  const float* offaw; int ld_offaw;       // fused: per query [M*L*P*2 offsets | M*L*P logits]
+  const float* ref_points;                // fused decoder: [Lq,2], scaled by valid_ratios[b,l] in-kernel
+  const float* valid_ratios;              // fused encoder: [B,L,2]
+  const float* loc;                       // drop-in: [B,Lq,M,L,P,2]
+  const float* attw;                      // drop-in: [B,Lq,M,L,P]
+  const int64_t* dev_shapes;              // drop-in: [L,2] int64 on device
+  const int64_t* dev_start;               // drop-in: [L] int64 on device
+  float* out;                             // [B,Lq,M*32]
+  int B, S, M, Lq;
+  int enc_patches;                        // 1: queries are the S tokens, enumerated in 8x4 patches
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+msda_kernel(const MsdaArgs a, const Levels lv_in) {
+  __shared__ float slots[QPB * Q_STRIDE];
+  __shared__ int q_of[QPB];
+  __shared__ int lvH[MAX_L], lvW[MAX_L], lvS[MAX_L];
+
+  const int tid = threadIdx.x;
+  const int m = blockIdx.y;
+  const int b = blockIdx.z;
+  const int L = lv_in.L;
+
+  if (tid < L) {
+    if (FUSED) {
+      lvH[tid] = lv_in.H[tid]; lvW[tid] = lv_in.W[tid]; lvS[tid] = lv_in.start[tid];
+    } else {  // the reference op takes its shape tensors on the device (ms_deform_attn.h:20-39)
+      lvH[tid] = (int)a.dev_shapes[2 * tid]; lvW[tid] = (int)a.dev_shapes[2 * tid + 1]; lvS[tid] = (int)a.dev_start[tid];
+    }
+  }
+  // ---- which queries does this CTA own?
+  if (tid < QPB) {
+    int q = -1;
+    if (a.enc_patches) {
+      int l = 0;
+      while (l + 1 < L && (int)blockIdx.x >= lv_in.patch_start[l + 1]) ++l;
+      const int pid = blockIdx.x - lv_in.patch_start[l];
+      const int py = pid / lv_in.patches_x[l], px = pid - py * lv_in.patches_x[l];
+      const int y = py * 4 + (tid >> 3), x = px * 8 + (tid & 7);
+      if (y < lv_in.H[l] && x < lv_in.W[l]) q = lv_in.start[l] + y * lv_in.W[l] + x;
+    } else {
+      q = blockIdx.x * QPB + tid;
+      if (q >= a.Lq) q = -1;
+    }
+    q_of[tid] = q;
+  }
+  __syncthreads();
+
+  // ---- phase 1: one thread per (query, sample); two passes cover the 32 queries
+  const int s = tid & 15;          // sample index = l*P + p   (L*P == 16)
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int qi = (tid >> 4) + pass * 16;
+    const int q = q_of[qi];
+    float* slot = &slots[qi * Q_STRIDE + s * SLOT_WORDS];
+    int idx[4] = {-1, -1, -1, -1};
+    float cw[4] = {0.f, 0.f, 0.f, 0.f};
+    // L*P == 16 with P == 4 is asserted on the host.
+    const int l = s >> 2;
+    float2 off = make_float2(0.f, 0.f);
+    float wgt = 0.f;
+    if (FUSED) {
+      // softmax over the 16 samples of this (query, head): 16-lane butterflies, executed by every
+      // lane (absent queries feed zeros) so the full-mask shuffles stay convergent.
+      float logit = 0.f;
+      if (q >= 0) {
+        const float* row = a.offaw + ((long long)b * a.Lq + q) * a.ld_offaw;
+        off = *(const float2*)(row + (m * 16 + s) * 2);
+        logit = row[a.M * 32 + m * 16 + s];
+      }
+      float mx = logit;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = expf(logit - mx);
+      float sum = e;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      wgt = e / sum;
+    }
+    if (q >= 0) {
+      const int H = lvH[l], W = lvW[l];
+      float lx, ly;
+      if (FUSED) {
+        float rx, ry;
+        if (a.enc_patches) {
+          // deformable_detr.py:1616-1648: pixel centre / (valid_ratio * size), then * valid_ratio of level l
+          int lq = 0;
+          while (lq + 1 < L && q >= lvS[lq + 1]) ++lq;
+          const int pix = q - lvS[lq];
+          const int py = pix / lvW[lq], px = pix - py * lvW[lq];
+          const float* vr = a.valid_ratios + (long long)b * L * 2;
+          rx = ((float)px + 0.5f) / (vr[lq * 2 + 0] * (float)lvW[lq]) * vr[l * 2 + 0];
+          ry = ((float)py + 0.5f) / (vr[lq * 2 + 1] * (float)lvH[lq]) * vr[l * 2 + 1];
+        } else {
+          // decoder: reference_points[:, :, None] * valid_ratios[:, None] (deformable_detr.py:1865-1867);
+          // the sigmoid'ed points are shared by the batch ([Lq,2]) because there is no box refinement.
+          const float2 r = *(const float2*)(a.ref_points + (long long)q * 2);
+          const float* vr = a.valid_ratios + (long long)b * L * 2;
+          rx = r.x * vr[l * 2 + 0]; ry = r.y * vr[l * 2 + 1];
+        }
+        lx = rx + off.x / (float)W;  // deformable_detr.py:1066-1073
+        ly = ry + off.y / (float)H;
+      } else {
+        const long long base = (((long long)b * a.Lq + q) * a.M + m) * 16 + s;
+        const float2 lc = *(const float2*)(a.loc + base * 2);
+        lx = lc.x; ly = lc.y;
+        wgt = a.attw[base];
+      }
+      const float him = ly * (float)H - 0.5f, wim = lx * (float)W - 0.5f;  // cuh:285-286
+      if (him > -1.f && wim > -1.f && him < (float)H && wim < (float)W) {   // cuh:288
+        const int hl = (int)floorf(him), wl = (int)floorf(wim);
+        const float lh = him - (float)hl, lw = wim - (float)wl;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int base_tok = lvS[l] + hl * W + wl;
+        const bool y0 = hl >= 0, y1 = hl + 1 <= H - 1, x0 = wl >= 0, x1 = wl + 1 <= W - 1;
+        if (y0 && x0) { idx[0] = base_tok;         cw[0] = hh * hw * wgt; }
+        if (y0 && x1) { idx[1] = base_tok + 1;     cw[1] = hh * lw * wgt; }
+        if (y1 && x0) { idx[2] = base_tok + W;     cw[2] = lh * hw * wgt; }
+        if (y1 && x1) { idx[3] = base_tok + W + 1; cw[3] = lh * lw * wgt; }
+      }
+    }
+    *(int4*)slot = make_int4(idx[0], idx[1], idx[2], idx[3]);
+    *(float4*)(slot + 4) = make_float4(cw[0], cw[1], cw[2], cw[3]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: 8 lanes x float4 per query, 16 samples x 4 corners
+  const int g = tid >> 3, c4 = (tid & 7) * 4;
+  const int q = q_of[g];
+  if (q < 0) return;
+  const float* vbase = a.value + (long long)b * a.S * a.ld_value + m * 32 + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* myslots = &slots[g * Q_STRIDE];
+#pragma unroll 4
+  for (int ss = 0; ss < 16; ++ss) {
+    const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
+    const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
+    if (id.x >= 0) v0 = __ldg((const float4*)(vbase + (long long)id.x * a.ld_value));
+    if (id.y >= 0) v1 = __ldg((const float4*)(vbase + (long long)id.y * a.ld_value));
+    if (id.z >= 0) v2 = __ldg((const float4*)(vbase + (long long)id.z * a.ld_value));
+    if (id.w >= 0) v3 = __ldg((const float4*)(vbase + (long long)id.w * a.ld_value));
+    acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y); acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
+    acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y); acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
+    acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
+    acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y); acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+  }
+  *(float4*)(a.out + ((long long)b * a.Lq + q) * (a.M * 32) + m * 32 + c4) = acc;
+}
+
+int fill_levels(const int* shapes_hw, int L, Levels* lv, int* S_out) {
+  lv->L = L;
+  int start = 0, pstart = 0;
+  for (int l = 0; l < L; ++l) {
+    lv->H[l] = shapes_hw[2 * l];
+    lv->W[l] = shapes_hw[2 * l + 1];
+    lv->start[l] = start;
+    start += lv->H[l] * lv->W[l];
+    lv->patch_start[l] = pstart;
+    lv->patches_x[l] = (lv->W[l] + 7) / 8;
+    pstart += lv->patches_x[l] * ((lv->H[l] + 3) / 4);
+  }
+  lv->patch_start[L] = pstart;
+  *S_out = start;
+  return pstart;
+}
+
+}  // namespace
+}  // namespace egtr
+
+using namespace egtr;
+
+extern "C" int egtr_msda_fwd_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                 const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int L,
+                                 int Lq, int P, float* out, egtr_stream_t s) {
+  EGTR_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, EGTR_ERR_ARG,
+             "egtr_msda_fwd_f32: null pointer");
+  EGTR_CHECK(B > 0 && S > 0 && M > 0 && Lq > 0, EGTR_ERR_ARG, "egtr_msda_fwd_f32: empty shape");
+  EGTR_CHECK(D == 32 && L * P == 16 && P == 4 && L <= MAX_L, EGTR_ERR_UNSUPPORTED,
+             "egtr_msda_fwd_f32: built for head_dim 32 and L*P = 4*4 (got D=%d L=%d P=%d)", D, L, P);
+  EGTR_CHECK((long long)B * S * M * D < (1LL << 31), EGTR_ERR_ARG, "egtr_msda_fwd_f32: B*S*M*D must be < 2^31");
+  EGTR_CHECK(B <= 65535 && M <= 65535, EGTR_ERR_ARG, "egtr_msda_fwd_f32: grid limits");
+  MsdaArgs a = {};
+  a.value = value; a.ld_value = M * D;
+  a.loc = sampling_loc; a.attw = attn_weight;
+  a.dev_shapes = spatial_shapes; a.dev_start = level_start_index;
+  a.out = out; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = 0;
+  Levels lv = {};
+  lv.L = L;
+  dim3 grid(cdiv(Lq, QPB), M, B);
+  msda_kernel<false><<<grid, 256, 0, (cudaStream_t)s>>>(a, lv);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
+                                       int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                                       int B, int S, int M, int D, int L, int Lq, int P, float* out, egtr_stream_t s) {
+  EGTR_CHECK(value && shapes_hw && offaw && out, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: null pointer");
+  EGTR_CHECK(valid_ratios != nullptr && (enc_ref || ref_points != nullptr), EGTR_ERR_ARG,
+             "egtr_msda_fused_fwd_f32: reference points missing");
+  EGTR_CHECK(D == 32 && L * P == 16 && P == 4 && L <= MAX_L, EGTR_ERR_UNSUPPORTED,
+             "egtr_msda_fused_fwd_f32: built for head_dim 32 and L*P = 4*4 (got D=%d L=%d P=%d)", D, L, P);
+  EGTR_CHECK(ld_value % 4 == 0 && ld_value >= M * D && ld_offaw >= M * L * P * 3 && ld_offaw % 2 == 0, EGTR_ERR_ARG,
+             "egtr_msda_fused_fwd_f32: bad leading dimensions");
+  EGTR_CHECK(B <= 65535 && M <= 65535, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: grid limits");
+  Levels lv = {};
+  int S_chk = 0;
+  const int patches = fill_levels(shapes_hw, L, &lv, &S_chk);
+  EGTR_CHECK(S_chk == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: sum(H*W)=%d != S=%d", S_chk, S);
+  EGTR_CHECK(!enc_ref || Lq == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: encoder form needs Lq == S");
+  MsdaArgs a = {};
+  a.value = value; a.ld_value = ld_value;
+  a.offaw = offaw; a.ld_offaw = ld_offaw;
+  a.ref_points = ref_points; a.valid_ratios = valid_ratios;
+  a.out = out; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
+  dim3 grid(enc_ref ? patches : cdiv(Lq, QPB), M, B);
+  msda_kernel<true><<<grid, 256, 0, (cudaStream_t)s>>>(a, lv);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}

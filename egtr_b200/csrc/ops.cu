@@ -1,0 +1,381 @@
+// Row-wise and image-geometry kernels of the EGTR path (everything that is not a GEMM, the
+// deformable gather or the relation head).  All fp32, all HBM-bound: coalesced float4 traffic,
+// one pass over the data wherever the reduction structure allows it.
+#include "common.cuh"
+
+namespace egtr {
+void count_launch();
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm(x + res), C == 256
+__global__ void __launch_bounds__(256)
+add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, int rows, float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xp = (const float4*)(x + (long long)row * 256);
+  float4 a = xp[lane], b = xp[lane + 32];
+  if (res) {
+    const float4* rp = (const float4*)(res + (long long)row * 256);
+    const float4 c = rp[lane], d = rp[lane + 32];
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+  const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / 256.f);
+  a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+  b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+  const float var = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w) * (1.f / 256.f);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  const float4 g0 = ((const float4*)gamma)[lane], g1 = ((const float4*)gamma)[lane + 32];
+  const float4 b0 = ((const float4*)beta)[lane], b1 = ((const float4*)beta)[lane + 32];
+  float4 o0, o1;
+  o0.x = a.x * rstd * g0.x + b0.x; o0.y = a.y * rstd * g0.y + b0.y; o0.z = a.z * rstd * g0.z + b0.z; o0.w = a.w * rstd * g0.w + b0.w;
+  o1.x = b.x * rstd * g1.x + b1.x; o1.y = b.y * rstd * g1.y + b1.y; o1.z = b.z * rstd * g1.z + b1.z; o1.w = b.w * rstd * g1.w + b1.w;
+  float4* op = (float4*)(out + (long long)row * 256);
+  op[lane] = o0;
+  op[lane + 32] = o1;
+}
+
+// ------------------------------------------------------------------ zero masked rows
+__global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const uint8_t* __restrict__ keep, long long rows) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = i / C4;
+  if (row >= rows) return;
+  if (!keep[row]) ((float4*)(x + row * ld))[i - row * C4] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------ 3x3/2 pad 1 max-pool, NHWC
+__global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int OH, int OW, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * OH * OW * C4;
+  if (i >= total) return;
+  const int c = (int)(i % C4);
+  long long t = i / C4;
+  const int ox = (int)(t % OW); t /= OW;
+  const int oy = (int)(t % OH);
+  const int b = (int)(t / OH);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = oy * 2 - 1 + dy;
+    if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox * 2 - 1 + dx;
+      if ((unsigned)ix >= (unsigned)W) continue;
+      const float4 v = __ldg((const float4*)x + (((long long)b * H + iy) * W + ix) * C4 + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  ((float4*)out)[i] = m;
+}
+
+// ------------------------------------------------------------------ GroupNorm (C == 256, 32 groups of 8)
+// pass 1: per (b, row chunk) partial sums per group in double; pass 2: normalise in place.
+constexpr int GN_ROWS = 256;  // rows per CTA
+__global__ void __launch_bounds__(256)
+groupnorm_partial_kernel(const float* __restrict__ x, int rows_per_b, int bstride, int off, double* __restrict__ part) {
+  // thread = (row lane r8 in 0..7, float4 column c in 0..63 -> group c/2)
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int c = threadIdx.x & 63, r8 = threadIdx.x >> 6;  // 4 row lanes x 64 float4 columns
+  const int row0 = chunk * GN_ROWS;
+  float s = 0.f, ss = 0.f;
+  for (int r = row0 + r8; r < min(row0 + GN_ROWS, rows_per_b); r += 4) {
+    const float4 v = ((const float4*)(x + ((long long)b * bstride + off + r) * 256))[c];
+    s += v.x + v.y + v.z + v.w;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ double sh[256][2];
+  sh[threadIdx.x][0] = (double)s;
+  sh[threadIdx.x][1] = (double)ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    double a = 0.0, q = 0.0;
+    for (int rr = 0; rr < 4; ++rr)
+      for (int cc = 0; cc < 2; ++cc) {
+        a += sh[rr * 64 + g * 2 + cc][0];
+        q += sh[rr * 64 + g * 2 + cc][1];
+      }
+    double* p = part + (((long long)b * gridDim.x + chunk) * 32 + g) * 2;
+    p[0] = a;
+    p[1] = q;
+  }
+}
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int off, const double* __restrict__ part,
+                       const float* __restrict__ gamma, const float* __restrict__ beta) {
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  __shared__ float mean_s[32], rstd_s[32];
+  if (threadIdx.x < 32) {
+    double a = 0.0, q = 0.0;
+    for (int k = 0; k < nchunks; ++k) {
+      const double* p = part + (((long long)b * nchunks + k) * 32 + threadIdx.x) * 2;
+      a += p[0];
+      q += p[1];
+    }
+    const double n = (double)rows_per_b * 8.0;
+    const double mean = a / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_s[threadIdx.x] = (float)mean;
+    rstd_s[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63, r8 = threadIdx.x >> 6;
+  const float mean = mean_s[c >> 1], rstd = rstd_s[c >> 1];
+  const float4 g = ((const float4*)gamma)[c], be = ((const float4*)beta)[c];
+  const int row0 = chunk * GN_ROWS;
+  for (int r = row0 + r8; r < min(row0 + GN_ROWS, rows_per_b); r += 4) {
+    float4* p = (float4*)(x + ((long long)b * bstride + off + r) * 256) + c;
+    float4 v = *p;
+    v.x = (v.x - mean) * rstd * g.x + be.x; v.y = (v.y - mean) * rstd * g.y + be.y;
+    v.z = (v.z - mean) * rstd * g.z + be.z; v.w = (v.w - mean) * rstd * g.w + be.w;
+    *p = v;
+  }
+}
+
+// ------------------------------------------------------------------ masks, cumulative sums, valid ratios
+struct GeoLevels {
+  int L;
+  int h[8], w[8], start[8];
+};
+// one CTA per (level, image): nearest-neighbour mask, then column/row inclusive scans.
+__global__ void __launch_bounds__(256)
+level_masks_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLevels lv, int S, uint8_t* __restrict__ mask_flat,
+                   float* __restrict__ ycum, float* __restrict__ xcum, float* __restrict__ valid_ratios) {
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int h = lv.h[l], w = lv.w[l];
+  uint8_t* mk = mask_flat + (long long)b * S + lv.start[l];
+  float* yc = ycum + (long long)b * S + lv.start[l];
+  float* xc = xcum + (long long)b * S + lv.start[l];
+  const int64_t* pm = pixel_mask + (long long)b * H * W;
+  const float sy = (float)H / (float)h, sx = (float)W / (float)w;  // legacy 'nearest': src = floor(dst * in/out)
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    const int yy = min((int)floorf((float)y * sy), H - 1), xx = min((int)floorf((float)x * sx), W - 1);
+    mk[i] = pm[(long long)yy * W + xx] != 0;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {  // y_embed = cumsum over rows (deformable_detr.py:853)
+    float c = 0.f;
+    for (int y = 0; y < h; ++y) { c += (float)mk[y * w + x]; yc[y * w + x] = c; }
+  }
+  for (int y = threadIdx.x; y < h; y += blockDim.x) {  // x_embed = cumsum over columns (854)
+    float c = 0.f;
+    for (int x = 0; x < w; ++x) { c += (float)mk[y * w + x]; xc[y * w + x] = c; }
+  }
+  if (threadIdx.x == 0) {  // get_valid_ratio (2064-2073): first column / first row
+    int vh = 0, vw = 0;
+    for (int y = 0; y < h; ++y) vh += mk[y * w];
+    for (int x = 0; x < w; ++x) vw += mk[x];
+    valid_ratios[((long long)b * lv.L + l) * 2 + 0] = (float)vw / (float)w;
+    valid_ratios[((long long)b * lv.L + l) * 2 + 1] = (float)vh / (float)h;
+  }
+}
+// sine embedding (850-876; normalize=True, scale=2*pi, T=10000) + level_embed (2262); C == 256
+__global__ void __launch_bounds__(256)
+pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum, GeoLevels lv, int S, const float* __restrict__ level_embed,
+                 float* __restrict__ pos) {
+  const int tok = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+  int l = 0;
+  while (l + 1 < lv.L && tok >= lv.start[l + 1]) ++l;
+  const int w = lv.w[l], h = lv.h[l];
+  const int pix = tok - lv.start[l];
+  const int y = pix / w, x = pix - y * w;
+  const long long base = (long long)b * S + lv.start[l];
+  const bool is_y = c < 128;
+  const int i = is_y ? c : c - 128;
+  float e, last;
+  if (is_y) { e = ycum[base + pix]; last = ycum[base + (h - 1) * w + x]; }
+  else      { e = xcum[base + pix]; last = xcum[base + y * w + (w - 1)]; }
+  const float v = (e - 0.5f) / (last + 1e-6f) * 6.283185307179586f;
+  const float dim_t = powf(10000.f, (float)(2 * (i / 2)) / 128.f);
+  const float a = v / dim_t;
+  pos[((long long)b * S + tok) * 256 + c] = ((i & 1) ? cosf(a) : sinf(a)) + level_embed[l * 256 + c];
+}
+
+// ------------------------------------------------------------------ decoder self-attention core
+// grid (heads, B, ceil(N/8)); 8 warps, one query per warp; K,V of the head staged in smem.
+__global__ void __launch_bounds__(256)
+mha_core_kernel(const float* __restrict__ qkv, int ld, int N, int C, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* ks = sm;                   // [N][33]
+  float* vs = sm + (size_t)N * 33;  // [N][32]
+  const int hd = blockIdx.x, b = blockIdx.y;
+  const float* base = qkv + (long long)b * N * ld + hd * 32;
+  for (int i = threadIdx.x; i < N * 32; i += blockDim.x) {
+    const int j = i >> 5, d = i & 31;
+    ks[j * 33 + d] = base[(long long)j * ld + C + d];
+    vs[j * 32 + d] = base[(long long)j * ld + 2 * C + d];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.z * 8 + warp;
+  if (qi >= N) return;
+  const float qd = base[(long long)qi * ld + lane];  // lane d holds q[d] (already scaled)
+  float sc[10];  // N <= 320
+  float mx = -INFINITY;
+  const int nj = (N + 31) >> 5;
+  for (int t = 0; t < nj; ++t) {
+    const int j = t * 32 + lane;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      const float q = __shfl_sync(0xffffffffu, qd, d);
+      if (j < N) s = fmaf(q, ks[j * 33 + d], s);
+    }
+    sc[t] = (j < N) ? s : -INFINITY;
+    mx = fmaxf(mx, sc[t]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int t = 0; t < nj; ++t) {
+    sc[t] = (t * 32 + lane < N) ? expf(sc[t] - mx) : 0.f;
+    sum += sc[t];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  float acc = 0.f;
+  for (int t = 0; t < nj; ++t) {
+    const float p = sc[t] * inv;
+    const int jmax = min(32, N - t * 32);
+    for (int jj = 0; jj < jmax; ++jj) acc = fmaf(__shfl_sync(0xffffffffu, p, jj), vs[(t * 32 + jj) * 32 + lane], acc);
+  }
+  out[((long long)b * N + qi) * C + hd * 32 + lane] = acc;
+}
+
+// ------------------------------------------------------------------ tiny-N linear (N <= 8), one warp per row
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bvec, int rows, int K,
+                    int N, int act, const float* __restrict__ ref, int ld_ref, int ref_rows, float* __restrict__ y, int ldy) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float xv = x[(long long)row * ldx + k];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) acc[n] = fmaf(xv, __ldg(w + (long long)n * K + k), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n == lane) v = acc[n];
+    if (bvec) v += bvec[lane];
+    if (act == 2 && lane < 2) {  // bbox head: += inverse_sigmoid(reference point) (egtr.py:291-298, deformable_detr.py:658-662)
+      float r = fminf(fmaxf(ref[(long long)(row % ref_rows) * ld_ref + lane], 0.f), 1.f);
+      v += logf(fmaxf(r, 1e-5f) / fmaxf(1.f - r, 1e-5f));
+    }
+    if (act >= 1) v = sigmoidf_(v);
+    y[(long long)row * ldy + lane] = v;
+  }
+}
+
+}  // namespace
+}  // namespace egtr
+
+using namespace egtr;
+
+extern "C" int egtr_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, int rows,
+                                      int C, float* out, egtr_stream_t s) {
+  EGTR_CHECK(x && gamma && beta && out && rows > 0, EGTR_ERR_ARG, "egtr_add_layernorm_f32: bad arguments");
+  EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_f32: built for d_model 256 (got %d)", C);
+  add_layernorm256_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, res, gamma, beta, rows, out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s) {
+  EGTR_CHECK(x && keep && rows > 0 && C % 4 == 0 && ld % 4 == 0, EGTR_ERR_ARG, "egtr_mask_rows_f32: bad arguments");
+  const long long total = (long long)rows * (C / 4);
+  mask_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, ld, C / 4, keep, rows);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_maxpool3x3s2_nhwc_f32(const float* x, int B, int H, int W, int C, float* out, egtr_stream_t s) {
+  EGTR_CHECK(x && out && B > 0 && H > 0 && W > 0 && C % 4 == 0, EGTR_ERR_ARG, "egtr_maxpool3x3s2_nhwc_f32: bad arguments");
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)B * OH * OW * (C / 4);
+  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, B, H, W, C / 4, OH, OW, out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups,
+                                  const float* gamma, const float* beta, double* scratch, egtr_stream_t s) {
+  EGTR_CHECK(x && gamma && beta && scratch && B > 0 && rows_per_b > 0, EGTR_ERR_ARG, "egtr_groupnorm_f32: bad arguments");
+  EGTR_CHECK(C == 256 && groups == 32, EGTR_ERR_UNSUPPORTED, "egtr_groupnorm_f32: built for GroupNorm(32, 256)");
+  dim3 grid(cdiv(rows_per_b, GN_ROWS), B);
+  groupnorm_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, scratch);
+  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, scratch, gamma, beta);
+  count_launch();
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b) {
+  return (long long)B * cdiv(rows_per_b, GN_ROWS) * 32 * 2;
+}
+
+extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H, int W, const int* shapes_hw, int L,
+                                        const float* level_embed, int C, uint8_t* mask_flat, float* pos_flat,
+                                        float* valid_ratios, float* scratch, egtr_stream_t s) {
+  EGTR_CHECK(pixel_mask && shapes_hw && level_embed && mask_flat && pos_flat && valid_ratios && scratch, EGTR_ERR_ARG,
+             "egtr_levels_geometry_f32: null pointer");
+  EGTR_CHECK(C == 256 && L >= 1 && L <= 8 && B > 0 && B <= 65535, EGTR_ERR_UNSUPPORTED, "egtr_levels_geometry_f32: C=%d L=%d", C, L);
+  GeoLevels lv;
+  lv.L = L;
+  int S = 0;
+  for (int l = 0; l < L; ++l) {
+    lv.h[l] = shapes_hw[2 * l];
+    lv.w[l] = shapes_hw[2 * l + 1];
+    lv.start[l] = S;
+    S += lv.h[l] * lv.w[l];
+  }
+  float* ycum = scratch;
+  float* xcum = scratch + (long long)B * S;
+  level_masks_kernel<<<dim3(L, B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat, ycum, xcum, valid_ratios);
+  pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, pos_flat);
+  count_launch();
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_mha_core_f32(const float* qkv, int ld, int B, int N, int heads, int D, float* out, egtr_stream_t s) {
+  EGTR_CHECK(qkv && out && B > 0 && N > 0, EGTR_ERR_ARG, "egtr_mha_core_f32: bad arguments");
+  EGTR_CHECK(D == 32 && N <= 320 && ld >= 3 * heads * D, EGTR_ERR_UNSUPPORTED, "egtr_mha_core_f32: head_dim 32, N <= 320 (D=%d N=%d)", D, N);
+  const size_t smem = (size_t)N * (33 + 32) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    EGTR_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 320 * 65 * 4));
+    attr = true;
+  }
+  mha_core_kernel<<<dim3(heads, B, cdiv(N, 8)), 256, smem, (cudaStream_t)s>>>(qkv, ld, N, heads * D, out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_small_linear_f32(const float* x, int ldx, const float* w, const float* b, int rows, int K, int N,
+                                     int act, const float* ref, int ld_ref, int ref_rows, float* y, int ldy, egtr_stream_t s) {
+  EGTR_CHECK(x && w && y && rows > 0 && K > 0 && N >= 1 && N <= 8, EGTR_ERR_ARG, "egtr_small_linear_f32: bad arguments (N=%d)", N);
+  EGTR_CHECK(act != 2 || ref != nullptr, EGTR_ERR_ARG, "egtr_small_linear_f32: act 2 needs reference points");
+  small_linear_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, ldx, w, b, rows, K, N, act, ref, ld_ref, ref_rows > 0 ? ref_rows : rows, y, ldy);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}

@@ -1,0 +1,37 @@
+// Library-wide state: per-thread error string, launch counter, device properties.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace egtr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace egtr
+
+extern "C" const char* egtr_last_error(void) { return egtr::g_err; }
+extern "C" int egtr_abi_version(void) { return 1; }
+extern "C" long long egtr_launch_count(void) { return egtr::g_launches.load(); }
+extern "C" void egtr_launch_count_reset(void) { egtr::g_launches.store(0); }

@@ -1,0 +1,469 @@
+"""Host-side driver of the EGTR forward: weight preparation and the launch sequence.
+
+PyTorch is used for device memory, streams and the tensors handed back to the caller; every
+arithmetic step of the path is a kernel of `libegtr_b200.so` reached through the C ABI
+(`include/egtr_b200.h`).  The sequence mirrors `DeformableDetrModel.forward`
+(`/root/reference/model/deformable_detr.py:2161-2390`) and the inference part of
+`DetrForSceneGraphGeneration.forward` (`/root/reference/model/egtr.py:241-418, 507-540`).
+
+Layouts: images are consumed NCHW as given; every activation after the stem is NHWC, i.e. a
+row-major [rows, C] matrix — which is also the `[B, S, 256]` token layout of the transformer, so
+`flatten(2).transpose(1, 2)` (deformable_detr.py:2259) costs nothing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ASrc, Epilogue, call
+
+RESNET_BLOCKS = (3, 4, 6, 3)
+
+
+def _ptr(t: Optional[torch.Tensor], col: int = 0) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr() + col * t.element_size()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gemm_backend() -> str:
+    """`tc` (tcgen05, the product path) or `simt` — the fp32 CUDA-core kernel, a bring-up/debug knob
+    used by tests to cross-check the tensor-core path.  Both are kernels of this library."""
+    return os.environ.get("EGTR_B200_GEMM", "tc")
+
+
+class Lin:
+    """A prepared weight: fp32 [N,K] plus bf16 hi/lo planes [2,Npad,K] for the tensor-core GEMM."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], device):
+        w = w.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.N, self.K = w.shape
+        self.Npad = ((self.N + 63) // 64) * 64
+        self.w = w
+        self.b = None if b is None else b.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.planes = torch.empty(2 * self.Npad * self.K, dtype=torch.bfloat16, device=device)
+        call("egtr_split_weight_bf16", _ptr(w), self.N, self.K, self.Npad, _ptr(self.planes), _stream())
+
+
+def _conv_mat(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """[Cout,Cin,KH,KW] -> [Cout, KH*KW*Cin] (k = (ky*KW + kx)*Cin + c), optionally zero-padded in K."""
+    cout = w.shape[0]
+    m = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    if k_pad is not None and k_pad > m.shape[1]:
+        m = torch.cat([m, m.new_zeros(cout, k_pad - m.shape[1])], 1)
+    return m.contiguous()
+
+
+def _fold_bn(sd, conv: str, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """FrozenBN folded into the conv: scale = w*rsqrt(var+1e-5) (deformable_detr.py:704-714)."""
+    scale = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
+    shift = sd[bn + ".bias"] - sd[bn + ".running_mean"] * scale
+    return sd[conv + ".weight"] * scale.view(-1, 1, 1, 1), shift
+
+
+def conv_out(n: int, k: int, s: int, p: int) -> int:
+    return (n + 2 * p - k) // s + 1
+
+
+def level_shapes(H: int, W: int, num_levels: int = 4) -> List[Tuple[int, int]]:
+    """Feature-map sizes of C3, C4, C5 and the extra stride-2 levels for an H x W input."""
+    h, w = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+    h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)  # max-pool -> C2 resolution
+    shapes = []
+    for _ in range(3):
+        h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        shapes.append((h, w))
+    for _ in range(num_levels - 3):
+        h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        shapes.append((h, w))
+    return shapes[:num_levels]
+
+
+class Engine:
+    def __init__(self, config, state_dict: Dict[str, torch.Tensor], device):
+        _lib.load()
+        self.cfg = config
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.EgtrError("the EGTR hot path runs on CUDA devices only (no CPU fallback)")
+        c = config
+        if c.two_stage or c.with_box_refine:
+            raise _lib.EgtrError("two_stage / with_box_refine are outside the EGTR inference path (SURVEY.md §2.1)")
+        if not (c.d_model == 256 and c.encoder_attention_heads == 8 and c.decoder_attention_heads == 8
+                and c.num_feature_levels == 4 and c.encoder_n_points == 4 and c.decoder_n_points == 4
+                and c.backbone == "resnet50" and not c.dilation and c.position_embedding_type == "sine"
+                and c.activation_function == "relu"):
+            raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
+        self._ws: Dict[tuple, dict] = {}
+        with torch.cuda.device(self.device):
+            self._prepare(state_dict)
+
+    # ------------------------------------------------------------------ weights
+    def _prepare(self, sd_in):
+        dev = self.device
+        sd = {k: v.detach().to(dev, torch.float32) if v.is_floating_point() else v for k, v in sd_in.items()}
+        cfg = self.cfg
+        d = cfg.d_model
+        L = lambda w, b=None: Lin(w, b, dev)  # noqa: E731
+        bb = "model.backbone.conv_encoder.model."
+        w, b = _fold_bn(sd, bb + "conv1", bb + "bn1")
+        self.stem = L(_conv_mat(w, 192), b)
+        self.blocks = []
+        for li, nblk in enumerate(RESNET_BLOCKS, start=1):
+            for bi in range(nblk):
+                p = f"{bb}layer{li}.{bi}."
+                blk = {"stride": 2 if (bi == 0 and li > 1) else 1, "last": bi == nblk - 1}
+                for j in (1, 2, 3):
+                    w, b = _fold_bn(sd, p + f"conv{j}", p + f"bn{j}")
+                    blk[f"c{j}"] = L(_conv_mat(w), b)
+                if (p + "downsample.0.weight") in sd:
+                    w, b = _fold_bn(sd, p + "downsample.0", p + "downsample.1")
+                    blk["ds"] = L(_conv_mat(w), b)
+                self.blocks.append((li, blk))
+        self.input_proj = []
+        for l in range(cfg.num_feature_levels):
+            p = f"model.input_proj.{l}."
+            self.input_proj.append((L(_conv_mat(sd[p + "0.weight"]), sd[p + "0.bias"]), sd[p + "1.weight"].contiguous(), sd[p + "1.bias"].contiguous()))
+        self.level_embed = sd["model.level_embed"].contiguous()
+
+        def msda(p):
+            return dict(
+                offaw=L(torch.cat([sd[p + "sampling_offsets.weight"], sd[p + "attention_weights.weight"]], 0),
+                        torch.cat([sd[p + "sampling_offsets.bias"], sd[p + "attention_weights.bias"]], 0)),
+                out=L(sd[p + "output_proj.weight"], sd[p + "output_proj.bias"]),
+            )
+
+        def ln(p):
+            return sd[p + ".weight"].contiguous(), sd[p + ".bias"].contiguous()
+
+        self.enc = []
+        for i in range(cfg.encoder_layers):
+            p = f"model.encoder.layers.{i}."
+            lay = msda(p + "self_attn.")
+            lay["value"] = L(sd[p + "self_attn.value_proj.weight"], sd[p + "self_attn.value_proj.bias"])
+            lay["ln1"], lay["ln2"] = ln(p + "self_attn_layer_norm"), ln(p + "final_layer_norm")
+            lay["fc1"], lay["fc2"] = L(sd[p + "fc1.weight"], sd[p + "fc1.bias"]), L(sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+            self.enc.append(lay)
+
+        heads = cfg.decoder_attention_heads
+        scaling = (d // heads) ** -0.5
+        self.dec = []
+        vals_w, vals_b = [], []
+        for i in range(cfg.decoder_layers):
+            p = f"model.decoder.layers.{i}."
+            lay = msda(p + "encoder_attn.")
+            # q is scaled after the projection in the reference (deformable_detr.py:1166): fold it in.
+            lay["qk"] = L(torch.cat([sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.k_proj.weight"]], 0),
+                          torch.cat([sd[p + "self_attn.q_proj.bias"] * scaling, sd[p + "self_attn.k_proj.bias"]], 0))
+            lay["v"] = L(sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"])
+            lay["o"] = L(sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+            lay["ln1"], lay["ln2"], lay["ln3"] = ln(p + "self_attn_layer_norm"), ln(p + "encoder_attn_layer_norm"), ln(p + "final_layer_norm")
+            lay["fc1"], lay["fc2"] = L(sd[p + "fc1.weight"], sd[p + "fc1.bias"]), L(sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+            vals_w.append(sd[p + "encoder_attn.value_proj.weight"])
+            vals_b.append(sd[p + "encoder_attn.value_proj.bias"])
+            self.dec.append(lay)
+        # the six cross-attention value projections read the same encoder output: one [S,256]x[256,1536] GEMM
+        self.dec_value = L(torch.cat(vals_w, 0), torch.cat(vals_b, 0))
+
+        qpe = sd["model.query_position_embeddings.weight"]
+        self.query_pos = qpe[:, :d].contiguous()
+        self.query_tgt = qpe[:, d:].contiguous()
+        self.refpt_w = sd["model.reference_points.weight"].contiguous()
+        self.refpt_b = sd["model.reference_points.bias"].contiguous()
+
+        last = cfg.decoder_layers - 1
+        self.cls = L(sd[f"class_embed.{last}.weight"], sd[f"class_embed.{last}.bias"])
+        self.box0 = L(sd[f"bbox_embed.{last}.layers.0.weight"], sd[f"bbox_embed.{last}.layers.0.bias"])
+        self.box1 = L(sd[f"bbox_embed.{last}.layers.1.weight"], sd[f"bbox_embed.{last}.layers.1.bias"])
+        self.box2_w = sd[f"bbox_embed.{last}.layers.2.weight"].contiguous()
+        self.box2_b = sd[f"bbox_embed.{last}.layers.2.bias"].contiguous()
+
+        # relation head (egtr.py:322-418): un-scaling of the captured q folded into proj_q
+        unscale = (d // heads) ** 0.5
+        self.rel_sub = [L(sd[f"proj_q.{l}.weight"] * unscale, sd[f"proj_q.{l}.bias"]) for l in range(cfg.decoder_layers)]
+        self.rel_obj = [L(sd[f"proj_k.{l}.weight"], sd[f"proj_k.{l}.bias"]) for l in range(cfg.decoder_layers)]
+        self.rel_sub.append(L(sd["final_sub_proj.weight"], sd["final_sub_proj.bias"]))
+        self.rel_obj.append(L(sd["final_obj_proj.weight"], sd["final_obj_proj.bias"]))
+        r1, c1, g = sd["rel_predictor.layers.0.weight"], sd["connectivity_layer.layers.0.weight"], sd["rel_predictor_gate.weight"]
+        zeros512 = torch.zeros(2 * d, device=dev)
+        self.rel_u = L(torch.cat([r1[:, :d], c1[:, :d], g[:, :d]], 0), None)
+        self.rel_v = L(torch.cat([r1[:, d:], c1[:, d:], g[:, d:]], 0), torch.cat([zeros512, sd["rel_predictor_gate.bias"]], 0))
+        self.rel_b1 = torch.cat([sd["rel_predictor.layers.0.bias"], sd["connectivity_layer.layers.0.bias"]], 0).contiguous()
+        self.rel_w2 = L(sd["rel_predictor.layers.1.weight"], sd["rel_predictor.layers.1.bias"])
+        self.con_w2 = L(sd["connectivity_layer.layers.1.weight"], sd["connectivity_layer.layers.1.bias"])
+        self.rel_w3 = L(sd["rel_predictor.layers.2.weight"], sd["rel_predictor.layers.2.bias"])
+        self.con_w3_w = sd["connectivity_layer.layers.2.weight"].contiguous()
+        self.con_w3_b = sd["connectivity_layer.layers.2.bias"].contiguous()
+        self.triplet = sd["triplet_dist"].contiguous()
+        self.rel_dist = sd["rel_dist"].contiguous()
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ launch helpers
+    def gemm(self, lin: Lin, M: int, out: torch.Tensor, *, a: Optional[torch.Tensor] = None, lda: Optional[int] = None,
+             a_col: int = 0, a2: Optional[torch.Tensor] = None, conv: Optional[dict] = None, relu: bool = False,
+             res: Optional[torch.Tensor] = None, ldr: int = 0, ldo: Optional[int] = None, out_col: int = 0,
+             remap: Optional[Tuple[int, int, int]] = None):
+        src = ASrc()
+        if conv is None:
+            src.a, src.a2, src.mode = _ptr(a, a_col), _ptr(a2, a_col), 0
+            src.lda = lda if lda is not None else lin.K
+        else:
+            src.a, src.a2, src.mode, src.lda = _ptr(conv["x"]), None, conv.get("mode", 1), 0
+            for k in ("H", "W", "C", "OH", "OW", "KH", "KW", "stride", "pad"):
+                setattr(src, k, conv[k])
+        ep = Epilogue()
+        ep.bias, ep.res, ep.out = _ptr(lin.b), _ptr(res), _ptr(out, out_col)
+        ep.ldo = ldo if ldo is not None else lin.N
+        ep.ldr = ldr if ldr else ep.ldo
+        ep.relu = int(relu)
+        ep.rows_per_b, ep.bstride, ep.off = remap if remap else (0, 0, 0)
+        if gemm_backend() == "simt":
+            call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
+        else:
+            call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+
+    def layernorm(self, x, res, ln, rows, out):
+        call("egtr_add_layernorm_f32", _ptr(x), _ptr(res), _ptr(ln[0]), _ptr(ln[1]), rows, 256, _ptr(out), _stream())
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, B: int, H: int, W: int) -> dict:
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, cfg = self.device, self.cfg
+        f32 = dict(dtype=torch.float32, device=dev)
+        shapes = level_shapes(H, W, cfg.num_feature_levels)
+        S = sum(h * w for h, w in shapes)
+        N = cfg.num_queries
+        h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+        h2, w2 = conv_out(h1, 3, 2, 1), conv_out(w1, 3, 2, 1)
+        ws = dict(shapes=shapes, S=S, stem_hw=(h1, w1), c2_hw=(h2, w2))
+        ws["shapes_c"] = (C.c_int * (2 * len(shapes)))(*[v for hw in shapes for v in hw])
+        ws["starts"] = [sum(h * w for h, w in shapes[:l]) for l in range(len(shapes))]
+        ws["stem"] = torch.empty(B * h1 * w1, 64, **f32)
+        # backbone ping-pong buffers sized for the largest stage output (layer1: h2*w2 x 256)
+        big = B * h2 * w2 * 256
+        ws["bb"] = [torch.empty(big, **f32) for _ in range(4)]
+        ws["c5"] = None
+        ws["mask_flat"] = torch.empty(B, S, dtype=torch.uint8, device=dev)
+        ws["pos"] = torch.empty(B * S, 256, **f32)
+        ws["valid_ratios"] = torch.empty(B, len(shapes), 2, **f32)
+        ws["geo_scratch"] = torch.empty(2 * B * S, **f32)
+        gn = max(call("egtr_groupnorm_scratch_doubles", B, h * w) for h, w in shapes)
+        ws["gn_scratch"] = torch.empty(int(gn), dtype=torch.float64, device=dev)
+        ws["x"] = [torch.empty(B * S, 256, **f32) for _ in range(3)]
+        ws["offaw"] = torch.empty(B * S, 384, **f32)
+        ws["value"] = torch.empty(B * S, 256, **f32)
+        ws["attn"] = torch.empty(B * S, 256, **f32)
+        ws["ffn"] = torch.empty(B * S, 1024, **f32)
+        ws["dec_value"] = torch.empty(B * S, 256 * cfg.decoder_layers, **f32)
+        ws["qpos"] = self.query_pos.unsqueeze(0).expand(B, -1, -1).reshape(B * N, 256).contiguous()
+        ws["tgt"] = self.query_tgt.unsqueeze(0).expand(B, -1, -1).reshape(B * N, 256).contiguous()
+        ws["ref"] = torch.empty(N, 2, **f32)
+        ws["dh"] = [torch.empty(B * N, 256, **f32) for _ in range(4)]
+        ws["dattn"] = torch.empty(B * N, 256, **f32)
+        ws["doffaw"] = torch.empty(B * N, 384, **f32)
+        ws["dffn"] = torch.empty(B * N, 1024, **f32)
+        ws["box_h"] = [torch.empty(B * N, 256, **f32) for _ in range(2)]
+        Lr = cfg.decoder_layers + 1
+        ws["sub"] = torch.empty(B * N * Lr, 256, **f32)
+        ws["obj"] = torch.empty(B * N * Lr, 256, **f32)
+        ws["U"] = torch.empty(B * N * Lr, 516, **f32)
+        ws["V"] = torch.empty(B * N * Lr, 516, **f32)
+        ws["H1"] = torch.empty(B * N * N, 512, **f32)
+        ws["H2r"] = torch.empty(B * N * N, 256, **f32)
+        ws["H2c"] = torch.empty(B * N * N, 256, **f32)
+        ws["rel_logits"] = torch.empty(B * N * N, cfg.num_rel_labels, **f32)
+        ws["con_logits"] = torch.empty(B * N * N, 1, **f32)
+        ws["cls_idx"] = torch.empty(B * N, dtype=torch.int32, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        cfg, dev = self.cfg, self.device
+        if pixel_values.device != dev:
+            raise _lib.EgtrError(f"pixel_values on {pixel_values.device}, model on {dev}")
+        with torch.cuda.device(dev):
+            return self._forward(pixel_values, pixel_mask, taps)
+
+    def _forward(self, pixel_values, pixel_mask, taps):
+        cfg, dev = self.cfg, self.device
+        st = _stream()
+        px = pixel_values.to(torch.float32).contiguous()
+        B, Cin, H, W = px.shape
+        if Cin != 3:
+            raise ValueError(f"pixel_values must have 3 channels, got {Cin}")
+        if pixel_mask is None:
+            pixel_mask = torch.ones(B, H, W, dtype=torch.long, device=dev)
+        pm = pixel_mask.to(torch.long).contiguous()
+        ws = self._workspace(B, H, W)
+        shapes, S, starts = ws["shapes"], ws["S"], ws["starts"]
+        N, d, Lv = cfg.num_queries, cfg.d_model, len(shapes)
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- geometry: masks, position embeddings, valid ratios (deformable_detr.py:783-785, 850-876, 2064-2073)
+        call("egtr_levels_geometry_f32", _ptr(pm), B, H, W, ws["shapes_c"], Lv, _ptr(self.level_embed), d,
+             _ptr(ws["mask_flat"]), _ptr(ws["pos"]), _ptr(ws["valid_ratios"]), _ptr(ws["geo_scratch"]), st)
+
+        # ---- backbone (deformable_detr.py:778): stem 7x7/2 as a gather-GEMM over the NCHW image, max-pool, bottlenecks
+        h1, w1 = ws["stem_hw"]
+        self.gemm(self.stem, B * h1 * w1, ws["stem"], relu=True,
+                  conv=dict(x=px, mode=2, H=H, W=W, C=3, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=3))
+        h, w = ws["c2_hw"]
+        bufs = ws["bb"]
+        x = bufs[0]
+        call("egtr_maxpool3x3s2_nhwc_f32", _ptr(ws["stem"]), B, h1, w1, 64, _ptr(x), st)
+        cur, cin = 0, 64
+        for li, blk in self.blocks:
+            s = blk["stride"]
+            oh, ow = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if s == 2 else (h, w)
+            planes = blk["c1"].N
+            free = [i for i in range(4) if i != cur]
+            y1, y2, idt = bufs[free[0]], bufs[free[1]], bufs[free[2]]
+            self.gemm(blk["c1"], B * h * w, y1, a=x, lda=cin, relu=True)
+            self.gemm(blk["c2"], B * oh * ow, y2, relu=True,
+                      conv=dict(x=y1, H=h, W=w, C=planes, OH=oh, OW=ow, KH=3, KW=3, stride=s, pad=1))
+            if "ds" in blk:
+                self.gemm(blk["ds"], B * oh * ow, idt,
+                          conv=dict(x=x, H=h, W=w, C=cin, OH=oh, OW=ow, KH=1, KW=1, stride=s, pad=0))
+                res = idt
+            else:
+                res = x
+            # conv3 + bn3 + identity + ReLU in one epilogue; output reuses y1's buffer
+            self.gemm(blk["c3"], B * oh * ow, y1, a=y2, lda=planes, relu=True, res=res, ldr=planes * 4)
+            x, cur, cin, h, w = y1, free[0], planes * 4, oh, ow
+            if blk.get("last") and li >= 2:
+                # C3/C4/C5 feed input_proj straight away: 1x1 conv + GroupNorm written into the level's
+                # slice of source_flatten [B,S,256] (deformable_detr.py:2221-2241, 2259-2266)
+                lvl = li - 2
+                lin, gw, gb = self.input_proj[lvl]
+                hw = h * w
+                self.gemm(lin, B * hw, ws["x"][0], a=x, lda=cin, ldo=256, remap=(hw, S, starts[lvl]))
+                call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, hw, S, starts[lvl], 256, 32, _ptr(gw), _ptr(gb), _ptr(ws["gn_scratch"]), st)
+                if li == 4:  # extra level: 3x3/2 conv on C5
+                    if Lv > 4:
+                        raise _lib.EgtrError("more than 4 feature levels are not built")
+                    lin2, gw2, gb2 = self.input_proj[3]
+                    oh2, ow2 = shapes[3]
+                    self.gemm(lin2, B * oh2 * ow2, ws["x"][0], ldo=256, remap=(oh2 * ow2, S, starts[3]),
+                              conv=dict(x=x, H=h, W=w, C=cin, OH=oh2, OW=ow2, KH=3, KW=3, stride=2, pad=1))
+                    call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, oh2 * ow2, S, starts[3], 256, 32, _ptr(gw2), _ptr(gb2), _ptr(ws["gn_scratch"]), st)
+                if taps is not None:
+                    taps[f"c{li + 1}"] = x[: B * hw * cin].view(B, h, w, cin).permute(0, 3, 1, 2).clone()
+        if taps is not None:
+            taps["source_flatten"] = ws["x"][0].view(B, S, 256).clone()
+            taps["lvl_pos_embed_flatten"] = ws["pos"].view(B, S, 256).clone()
+            taps["mask_flatten"] = ws["mask_flat"].bool().clone()
+            taps["valid_ratios"] = ws["valid_ratios"].clone()
+
+        # ---- encoder (deformable_detr.py:1283-1358)
+        M = B * S
+        xa, xb, xc = ws["x"]
+        pos, offaw, value, attn, ffn = ws["pos"], ws["offaw"], ws["value"], ws["attn"], ws["ffn"]
+        vr = ws["valid_ratios"]
+        for i, lay in enumerate(self.enc):
+            self.gemm(lay["offaw"], M, offaw, a=xa, a2=pos, lda=256)
+            self.gemm(lay["value"], M, value, a=xa, lda=256)
+            call("egtr_mask_rows_f32", _ptr(value), 256, 256, _ptr(ws["mask_flat"]), M, st)
+            call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
+                 B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
+            self.gemm(lay["out"], M, xb, a=attn, lda=256, res=xa, ldr=256)
+            self.layernorm(xb, None, lay["ln1"], M, xc)
+            self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, relu=True)
+            self.gemm(lay["fc2"], M, xb, a=ffn, lda=1024, res=xc, ldr=256)
+            self.layernorm(xb, None, lay["ln2"], M, xa)
+            if taps is not None and i == 0:
+                taps["enc0_out"] = xa.view(B, S, 256).clone()
+        enc = xa
+        enc_out = enc.view(B, S, 256).clone()
+
+        # ---- decoder (deformable_detr.py:1390-1489, 1774-1968)
+        nl = cfg.decoder_layers
+        dv = ws["dec_value"]
+        self.gemm(self.dec_value, M, dv, a=enc, lda=256)
+        call("egtr_mask_rows_f32", _ptr(dv), 256 * nl, 256 * nl, _ptr(ws["mask_flat"]), M, st)
+        call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
+             None, 0, 0, _ptr(ws["ref"]), 2, st)
+        Md = B * N
+        qpos = ws["qpos"]
+        hbuf = ws["dh"]
+        hcur = ws["tgt"]
+        qkvs = []
+        inter = torch.empty(B, nl, N, 256, **f32)
+        for i, lay in enumerate(self.dec):
+            qkv = torch.empty(Md, 768, **f32)  # captured per layer: q (scaled) | k | v
+            qkvs.append(qkv)
+            t0, t1, t2 = [b for b in hbuf if b is not hcur][:3]
+            self.gemm(lay["qk"], Md, qkv, a=hcur, a2=qpos, lda=256, ldo=768)
+            self.gemm(lay["v"], Md, qkv, a=hcur, lda=256, ldo=768, out_col=512)
+            call("egtr_mha_core_f32", _ptr(qkv), 768, B, N, 8, 32, _ptr(ws["dattn"]), st)
+            self.gemm(lay["o"], Md, t0, a=ws["dattn"], lda=256, res=hcur, ldr=256)
+            self.layernorm(t0, None, lay["ln1"], Md, t1)
+            self.gemm(lay["offaw"], Md, ws["doffaw"], a=t1, a2=qpos, lda=256)
+            call("egtr_msda_fused_fwd_f32", _ptr(dv, i * 256), 256 * nl, ws["shapes_c"], _ptr(ws["doffaw"]), 384,
+                 _ptr(ws["ref"]), _ptr(vr), 0, B, S, 8, 32, Lv, N, 4, _ptr(ws["dattn"]), st)
+            self.gemm(lay["out"], Md, t0, a=ws["dattn"], lda=256, res=t1, ldr=256)
+            self.layernorm(t0, None, lay["ln2"], Md, t2)
+            self.gemm(lay["fc1"], Md, ws["dffn"], a=t2, lda=256, relu=True)
+            self.gemm(lay["fc2"], Md, t0, a=ws["dffn"], lda=1024, res=t2, ldr=256)
+            out_h = inter[:, i]  # strided view [B,N,256] of the stacked intermediates: write through a contiguous temp
+            self.layernorm(t0, None, lay["ln3"], Md, t1)
+            out_h.copy_(t1.view(B, N, 256))
+            hcur = t1
+        h_last = hcur
+
+        # ---- detection heads (egtr.py:283-314; only the last level is returned at inference)
+        K = cfg.num_labels
+        logits = torch.empty(B, N, K, **f32)
+        boxes = torch.empty(B, N, 4, **f32)
+        self.gemm(self.cls, Md, logits, a=h_last, lda=256)
+        self.gemm(self.box0, Md, ws["box_h"][0], a=h_last, lda=256, relu=True)
+        self.gemm(self.box1, Md, ws["box_h"][1], a=ws["box_h"][0], lda=256, relu=True)
+        call("egtr_small_linear_f32", _ptr(ws["box_h"][1]), 256, _ptr(self.box2_w), _ptr(self.box2_b), Md, 256, 4, 2,
+             _ptr(ws["ref"]), 2, N, _ptr(boxes), 4, st)
+
+        # ---- relation head (egtr.py:322-418, 507-516)
+        Lr = nl + 1
+        P = cfg.num_rel_labels
+        sub, obj = ws["sub"], ws["obj"]
+        for l in range(nl):
+            self.gemm(self.rel_sub[l], Md, sub, a=qkvs[l], lda=768, a_col=0, ldo=Lr * 256, out_col=l * 256)
+            self.gemm(self.rel_obj[l], Md, obj, a=qkvs[l], lda=768, a_col=256, ldo=Lr * 256, out_col=l * 256)
+        self.gemm(self.rel_sub[nl], Md, sub, a=h_last, lda=256, ldo=Lr * 256, out_col=nl * 256)
+        self.gemm(self.rel_obj[nl], Md, obj, a=h_last, lda=256, ldo=Lr * 256, out_col=nl * 256)
+        self.gemm(self.rel_u, Md * Lr, ws["U"], a=sub, lda=256, ldo=516)
+        self.gemm(self.rel_v, Md * Lr, ws["V"], a=obj, lda=256, ldo=516)
+        pairs = B * N * N
+        call("egtr_relation_pair_hidden_f32", _ptr(ws["U"]), _ptr(ws["V"]), 516, _ptr(self.rel_b1), B, N, Lr, _ptr(ws["H1"]), st)
+        self.gemm(self.rel_w2, pairs, ws["H2r"], a=ws["H1"], lda=512, a_col=0, relu=True)
+        self.gemm(self.con_w2, pairs, ws["H2c"], a=ws["H1"], lda=512, a_col=256, relu=True)
+        self.gemm(self.rel_w3, pairs, ws["rel_logits"], a=ws["H2r"], lda=256, ldo=P)
+        call("egtr_small_linear_f32", _ptr(ws["H2c"]), 256, _ptr(self.con_w3_w), _ptr(self.con_w3_b), pairs, 256, 1, 0,
+             None, 0, 0, _ptr(ws["con_logits"]), 1, st)
+        pred_rel = torch.empty(B, N, N, P, **f32)
+        pred_con = torch.empty(B, N, N, 1, **f32)
+        call("egtr_relation_finish_f32", _ptr(ws["rel_logits"]), P, _ptr(ws["con_logits"]), 1, _ptr(logits), K,
+             _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
+             int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), _ptr(pred_con), st)
+
+        # captured decoder self-attention states as [B, heads, N, 32] views (deformable_detr.py:1179-1185)
+        qs = tuple(q.view(B, N, 3, 8, 32)[:, :, 0].permute(0, 2, 1, 3) for q in qkvs)
+        ks = tuple(q.view(B, N, 3, 8, 32)[:, :, 1].permute(0, 2, 1, 3) for q in qkvs)
+        return dict(
+            logits=logits, pred_boxes=boxes, pred_rel=pred_rel, pred_connectivity=pred_con,
+            last_hidden_state=inter[:, nl - 1], intermediate_hidden_states=inter,
+            encoder_last_hidden_state=enc_out, init_reference_points=ws["ref"].unsqueeze(0).expand(B, -1, -1).clone(),
+            decoder_attention_queries=qs, decoder_attention_keys=ks,
+        )

@@ -1,0 +1,150 @@
+/*
+ * egtr_b200 — C ABI of the B200-native EGTR inference hot path (libegtr_b200.so).
+ *
+ * Every entry point takes raw DEVICE pointers, plain sizes and a CUDA stream (passed as void*,
+ * i.e. a cudaStream_t), enqueues work on that stream without synchronising, and returns a status
+ * code (0 = ok; `egtr_last_error()` describes the last failure on this thread).  Inputs are
+ * borrowed, outputs are caller-allocated.  No torch/ATen types cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   egtr_msda_fwd_f32          <- ms_deform_attn_forward, model/custom_kernel/vision.cpp:13,
+ *                                 ms_deform_attn.h:20-39, cuda/ms_deform_attn_cuda.cu:23-83
+ *   egtr_msda_fused_fwd_f32    <- softmax + sampling-location arithmetic + the same op,
+ *                                 model/deformable_detr.py:1056-1095
+ *   egtr_gemm_* / egtr_conv_*  <- nn.Linear / nn.Conv2d call sites of the path (cuBLAS / cuDNN in
+ *                                 the reference), model/deformable_detr.py:778,1049-1102,1166-1168,
+ *                                 1255,1333-1338,1995-2011; model/egtr.py:292-293,339,355,380-416
+ *   egtr_relation_*            <- the inline relation head, model/egtr.py:322-418,507-516
+ *   the remaining egtr_* ops   <- ATen library kernels the reference reaches implicitly
+ *                                 (layer_norm, group_norm, max_pool2d, softmax/bmm attention,
+ *                                 sine position embedding, mask interpolation), SURVEY.md §2.3
+ */
+#ifndef EGTR_B200_H_
+#define EGTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  EGTR_OK = 0,
+  EGTR_ERR_ARG = 1,         /* bad shape / null pointer / unsupported size */
+  EGTR_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed */
+  EGTR_ERR_UNSUPPORTED = 3  /* valid in the reference, not implemented here (documented) */
+};
+
+typedef void* egtr_stream_t; /* cudaStream_t */
+
+const char* egtr_last_error(void);
+int egtr_abi_version(void);
+/* Launches issued by this library since the last reset (bench.py's gpu_launches). */
+long long egtr_launch_count(void);
+void egtr_launch_count_reset(void);
+
+/* ---------------------------------------------------------------- GEMM-class operators ---- */
+/* Left-operand source: rows of 64-float runs.  mode 0: row m = a + m*lda (+ a2 + m*lda when a2
+ * is non-null, the "x + pos" of deformable_detr.py:1040,1163).  mode 1: implicit im2col over an
+ * NHWC tensor [B,H,W,C] for a KHxKW/stride/pad convolution, k = (ky*KW + kx)*C + c.  mode 2: the
+ * same gather over an NCHW image with few channels (the 7x7/2 stem on pixel_values [B,3,H,W]):
+ * k = (ky*KW + kx)*C + c for k < KH*KW*C, zero for the padding columns up to K. */
+typedef struct {
+  const float* a;
+  const float* a2;
+  int mode;
+  int lda;
+  int H, W, C, OH, OW, KH, KW, stride, pad;
+} egtr_asrc_t;
+
+/* out[orow(m)*ldo + n] = act(acc + bias[n] + res[orow(m)*ldr + n]);
+ * orow(m) = (m / rows_per_b)*bstride + off + m % rows_per_b when rows_per_b > 0, else m. */
+typedef struct {
+  const float* bias;
+  const float* res;
+  float* out;
+  int ldo, ldr;
+  int relu;
+  int rows_per_b, bstride, off;
+} egtr_epilogue_t;
+
+/* fp32 weight [N,K] -> split-bf16 planes [2][Npad][K] (hi, lo; rows >= N zero). Npad % 64 == 0. */
+int egtr_split_weight_bf16(const float* w, int N, int K, int Npad, void* planes, egtr_stream_t s);
+
+/* D = A * W^T on tcgen05 tensor cores (bf16x3 split products, fp32 accumulate in TMEM); W planes
+ * from egtr_split_weight_bf16, streamed by TMA.  K % 64 == 0, Npad % 64 == 0. */
+int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M, int N, int Npad, int K,
+                    const egtr_epilogue_t* ep, egtr_stream_t s);
+
+/* Same contract on fp32 CUDA cores with W fp32 [N,K]: the small/odd-shape path (K % 16 == 0). */
+int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N, int K,
+                  const egtr_epilogue_t* ep, egtr_stream_t s);
+
+/* ---------------------------------------------------------------- MSDeformAttn ----------- */
+/* Drop-in for ms_deform_attn_forward: value [B,S,M,D], spatial_shapes [L,2] int64 (device),
+ * level_start_index [L] int64 (device), sampling_loc [B,Lq,M,L,P,2], attn_weight [B,Lq,M,L,P]
+ * -> out [B,Lq,M*D].  All contiguous fp32.  D must be 32; L <= 8. */
+int egtr_msda_fwd_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D,
+                      int L, int Lq, int P, float* out, egtr_stream_t s);
+
+/* Fused form: `offaw` [B*Lq, ld_offaw] holds the raw sampling offsets (M*L*P*2 floats) followed by
+ * the raw attention logits (M*L*P floats) of one query row; shapes_hw is a HOST array of L (H,W)
+ * pairs.  Computes softmax over L*P, loc = ref + off/(W,H) and the gather in one kernel.  value row
+ * stride = ld_value floats.  Reference points: enc_ref == 0 (decoder): ref_points [Lq,2] (sigmoid
+ * outputs, shared by the batch) times valid_ratios [B,L,2] (deformable_detr.py:1865-1867);
+ * enc_ref != 0 (encoder): ref_points is NULL and the pixel-centre points are generated in-kernel
+ * from valid_ratios (deformable_detr.py:1616-1648). */
+int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
+                            int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                            int B, int S, int M, int D, int L, int Lq, int P, float* out, egtr_stream_t s);
+
+/* ---------------------------------------------------------------- row-wise / image ops --- */
+/* out = LayerNorm(x + res) over the last dim C (== 256), eps 1e-5; res may be NULL. */
+int egtr_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
+                           int rows, int C, float* out, egtr_stream_t s);
+/* zero rows of x[rows, C] where keep[row] == 0 (value.masked_fill, deformable_detr.py:1050-1052). */
+int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s);
+/* NHWC 3x3/2 pad 1 max-pool. */
+int egtr_maxpool3x3s2_nhwc_f32(const float* x, int B, int H, int W, int C, float* out, egtr_stream_t s);
+/* GroupNorm(32 groups) in place over x[B, rows_per_b (at row offset `off`, batch stride `bstride`
+ * rows), C], eps 1e-5 (deformable_detr.py:1996). */
+int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups,
+                       const float* gamma, const float* beta, double* scratch, egtr_stream_t s);
+/* doubles of scratch egtr_groupnorm_f32 needs for (B, rows_per_b). */
+long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b);
+/* pixel_mask [B,H,W] int64 -> per-level nearest-neighbour masks (uint8 [B,S]), sine position
+ * embedding + level_embed ([B,S,C]), valid ratios [B,L,2] (deformable_detr.py:783-785, 850-876,
+ * 2064-2073, 2262).  shapes_hw: HOST array of L (h,w). */
+int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H, int W, const int* shapes_hw, int L,
+                             const float* level_embed, int C, uint8_t* mask_flat, float* pos_flat,
+                             float* valid_ratios, float* scratch /* 2*B*S floats */, egtr_stream_t s);
+/* Decoder self-attention core: qkv [B*N, ld] with q (already scaled) at col 0, k at col C, v at
+ * col 2C; softmax(q k^T) v per head -> out [B*N, C] (deformable_detr.py:1190-1253). */
+int egtr_mha_core_f32(const float* qkv, int ld, int B, int N, int heads, int D, float* out, egtr_stream_t s);
+/* y[r, n] = act(x[r, :K] . w[n, :K] + b[n]) for tiny N (<= 8), one warp per row.  act 0: none,
+ * 1: sigmoid, 2: bbox head — add inverse_sigmoid(ref[r, n]) (eps 1e-5) to n < 2, then sigmoid
+ * (model/egtr.py:291-303, model/deformable_detr.py:658-662). */
+int egtr_small_linear_f32(const float* x, int ldx, const float* w, const float* b, int rows, int K, int N,
+                          int act, const float* ref, int ld_ref, int ref_rows /* ref row = r % ref_rows */,
+                          float* y, int ldy, egtr_stream_t s);
+
+/* ---------------------------------------------------------------- relation head ---------- */
+/* Pair stage of the relation head (model/egtr.py:366-416, 507-516) given the per-query tensors
+ *   U [B,N,7,ldu]: subject-side layer-1 partials (rel 0..255 | conn 256..511) then gate scalar at 512
+ *   V [B,N,7,ldu]: object-side partials, same layout (gate bias folded into V's scalar)
+ * writes H1 [B*N*N, 512] = relu(b1 + sum_l sigmoid(a_l(i)+b_l(j)) * (U_l(i) + V_l(j))).
+ * (bring-up path; the fused kernel below never materialises H1) */
+int egtr_relation_pair_hidden_f32(const float* U, const float* V, int ldu, const float* b1, int B, int N, int Lr,
+                                  float* H1, egtr_stream_t s);
+/* pred_rel = sigmoid(rel_logits + triplet_dist[c_i, c_j, :] - tau*log(rel_dist)), c = argmax(logits);
+ * pred_conn = sigmoid(conn_logits).  rel_logits [B*N*N, ld_rel], conn_logits [B*N*N, ld_conn]. */
+int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, const float* conn_logits, int ld_conn,
+                             const float* logits, int K, const float* triplet_dist, const float* rel_dist,
+                             float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
+                             int* cls_scratch /* B*N ints */, float* pred_rel, float* pred_conn, egtr_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGTR_B200_H_ */

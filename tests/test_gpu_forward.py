@@ -1,0 +1,85 @@
+"""GPU: the whole hot path through the reference-facing model API, vs golden fixtures (made by the
+unmodified reference) and vs the CPU oracle run live on the same seeded inputs."""
+import os
+
+import pytest
+import torch
+
+from tests.util import TOL, case_inputs, compare_forward, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq", "forward_A"]
+
+
+def _run(cfg, sd, px, mask, cuda):
+    from egtr_b200.model.egtr import DetrForSceneGraphGeneration
+    model = DetrForSceneGraphGeneration(cfg)
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    out = model(pixel_values=px.to(cuda), pixel_mask=mask.to(cuda), output_attentions=False,
+                output_attention_states=True, output_hidden_states=True)
+    torch.cuda.synchronize()
+    return model, out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(cuda, name):
+    ref, meta = load_golden(name)
+    cfg, sd, px, mask = case_inputs(meta)
+    _, out = _run(cfg, sd, px, mask, cuda)
+    assert out["logits"].shape == (meta["batch"], cfg.num_queries, cfg.num_labels)
+    assert "pred_connectivity" in out and out.pred_rel.shape[-1] == cfg.num_rel_labels
+    errs = compare_forward(out, ref)
+    print(name, os.environ.get("EGTR_B200_GEMM", "tc"), {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+def test_forward_matches_live_oracle_with_taps(cuda):
+    """Stage-by-stage check on a ragged batch: where would a deviation first appear?"""
+    from egtr_b200.config import workload_config
+    from egtr_b200.engine import Engine
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from oracle import egtr_oracle as orc
+    from tests.util import relerr
+    cfg = workload_config("small")
+    sd = synth_state_dict(cfg, 40)
+    px, mask = synth_images(2, 160, 224, seed=41, pad_to=[(160, 224), (120, 190)])
+    taps_o, taps_g = {}, {}
+    want = orc.forward(sd, cfg, px, mask, taps=taps_o)
+    eng = Engine(cfg, sd, cuda)
+    got = eng.forward(px.to(cuda), mask.to(cuda), taps=taps_g)
+    torch.cuda.synchronize()
+    stage = {}
+    for k in ("c3", "c4", "c5", "source_flatten", "lvl_pos_embed_flatten", "valid_ratios", "enc0_out"):
+        stage[k] = relerr(taps_g[k], taps_o[k])
+    assert torch.equal(taps_g["mask_flatten"].cpu(), taps_o["mask_flatten"])
+    for i in (0, 5):
+        stage[f"q{i}"] = relerr(got["decoder_attention_queries"][i], want["decoder_attention_queries"][i])
+        stage[f"k{i}"] = relerr(got["decoder_attention_keys"][i], want["decoder_attention_keys"][i])
+    stage["intermediate"] = relerr(got["intermediate_hidden_states"], want["intermediate_hidden_states"])
+    stage["init_ref"] = relerr(got["init_reference_points"], want["init_reference_points"])
+    errs = compare_forward(got, want)
+    print({k: f"{v:.2e}" for k, v in {**stage, **errs}.items()})
+    assert max(stage.values()) < TOL and max(errs.values()) < TOL, (stage, errs)
+
+
+def test_model_api_contract(cuda):
+    from egtr_b200.config import workload_config
+    from egtr_b200.model.egtr import DetrForSceneGraphGeneration
+    from egtr_b200.synth import synth_images, synth_state_dict
+    cfg = workload_config("tiny")
+    model = DetrForSceneGraphGeneration.from_pretrained("SenseTime/deformable-detr", config=cfg, ignore_mismatched_sizes=True)
+    model.load_state_dict(synth_state_dict(cfg, 1))
+    model.cuda()
+    model.eval()
+    assert model.device.type == "cuda"
+    px, mask = synth_images(1, 96, 128)
+    out = model(px.cuda(), mask.cuda(), output_attention_states=True, output_hidden_states=True)
+    out2 = model(px.cuda())  # pixel_mask defaults to all ones (deformable_detr.py:2208-2211)
+    assert torch.equal(out.logits, out2.logits) and torch.equal(out.pred_rel, out2.pred_rel)
+    assert len(out.decoder_hidden_states) == cfg.decoder_layers + 1
+    tup = model(px.cuda(), return_dict=False)
+    assert isinstance(tup, tuple) and torch.equal(tup[0], out.logits)
+    with pytest.raises(NotImplementedError):
+        model(px.cuda(), labels=[{}])

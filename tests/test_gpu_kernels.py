@@ -1,0 +1,242 @@
+"""GPU: every kernel of libegtr_b200.so, called through the C ABI, against the CPU oracle / torch fp64."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.util import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng_helpers():
+    from egtr_b200 import _lib
+    from egtr_b200.engine import Lin, _ptr, _stream
+    return _lib, Lin, _ptr, _stream
+
+
+def _gemm(lib, Lin, _ptr, _stream, backend, a, w, bias, *, relu=False, res=None, a2=None, conv=None, M=None, remap=None, out=None, ldo=None):
+    from egtr_b200._lib import ASrc, Epilogue
+    dev = w.device
+    lin = Lin(w, bias, dev)
+    src, ep = ASrc(), Epilogue()
+    if conv is None:
+        src.a, src.a2, src.mode, src.lda = _ptr(a), _ptr(a2), 0, a.shape[1]
+        M = a.shape[0]
+    else:
+        src.a, src.a2, src.mode, src.lda = _ptr(conv["x"]), None, conv.get("mode", 1), 0
+        for k in ("H", "W", "C", "OH", "OW", "KH", "KW", "stride", "pad"):
+            setattr(src, k, conv[k])
+    if out is None:
+        out = torch.full((M, lin.N), float("nan"), device=dev)
+    ep.bias, ep.res, ep.out = _ptr(lin.b), _ptr(res), _ptr(out)
+    ep.ldo = ldo or lin.N
+    ep.ldr = ep.ldo
+    ep.relu = int(relu)
+    ep.rows_per_b, ep.bstride, ep.off = remap or (0, 0, 0)
+    if backend == "simt":
+        lib.call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
+    else:
+        lib.call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+    torch.cuda.synchronize()
+    return out
+
+
+GEMM_SHAPES = [(128, 64, 64), (200, 256, 256), (1000, 384, 256), (333, 150, 256), (4100, 1024, 256),
+               (2500, 256, 1024), (77, 513, 256), (129, 50, 256), (40000, 256, 256), (5, 64, 128)]
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(cuda, backend, M, N, K):
+    lib, Lin, _ptr, _stream = _eng_helpers()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    a2 = torch.randn(M, K, generator=g).to(cuda)
+    ref = ((a.double() + a2.double()) @ w.double().t() + b.double() + res.double()).relu()
+    out = _gemm(lib, Lin, _ptr, _stream, backend, a, w, b, relu=True, res=res, a2=a2)
+    assert relerr(out, ref) < (2e-6 if backend == "simt" else 2e-5)
+    ref2 = a.double() @ w.double().t()
+    out2 = _gemm(lib, Lin, _ptr, _stream, backend, a, w, None)
+    assert relerr(out2, ref2) < (2e-6 if backend == "simt" else 2e-5)
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 13, 17, 64, 64, 3, 1, 1), (1, 20, 31, 128, 256, 3, 2, 1),
+                                                  (2, 9, 11, 256, 512, 1, 2, 0), (1, 7, 5, 2048, 256, 3, 2, 1)])
+def test_gemm_conv_nhwc(cuda, backend, B, H, W, Cin, Cout, k, s, p):
+    lib, Lin, _ptr, _stream = _eng_helpers()
+    from egtr_b200.engine import _conv_mat, conv_out
+    g = torch.Generator().manual_seed(H * W + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p).permute(0, 2, 3, 1).reshape(-1, Cout)
+    OH, OW = conv_out(H, k, s, p), conv_out(W, k, s, p)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    out = _gemm(lib, Lin, _ptr, _stream, backend, None, _conv_mat(w).to(cuda), b.to(cuda), M=B * OH * OW,
+                conv=dict(x=xn, H=H, W=W, C=Cin, OH=OH, OW=OW, KH=k, KW=k, stride=s, pad=p))
+    assert relerr(out, ref) < (2e-6 if backend == "simt" else 2e-5)
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_gemm_stem_nchw_gather_and_remap(cuda, backend):
+    lib, Lin, _ptr, _stream = _eng_helpers()
+    from egtr_b200.engine import _conv_mat, conv_out
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 37, 45
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    b = torch.randn(64, generator=g)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=2, padding=3).relu().permute(0, 2, 3, 1).reshape(B, -1, 64)
+    OH, OW = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+    # write each image's rows at offset 5 of a [B, OH*OW + 9, 64] buffer (the level-slice remap)
+    S = OH * OW + 9
+    out = torch.zeros(B * S, 64, device=cuda)
+    _gemm(lib, Lin, _ptr, _stream, backend, None, _conv_mat(w, 192).to(cuda), b.to(cuda), relu=True, M=B * OH * OW, out=out,
+          remap=(OH * OW, S, 5), conv=dict(x=x.to(cuda), mode=2, H=H, W=W, C=3, OH=OH, OW=OW, KH=7, KW=7, stride=2, pad=3))
+    got = out.view(B, S, 64)[:, 5:5 + OH * OW]
+    assert relerr(got, ref) < (2e-6 if backend == "simt" else 2e-5)
+    assert float(out.view(B, S, 64)[:, :5].abs().max()) == 0.0 and float(out.view(B, S, 64)[:, 5 + OH * OW:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["msda_enc_small", "msda_dec_small", "msda_edge"])
+def test_msda_dropin_matches_reference_golden(cuda, name):
+    from egtr_b200.model.deformable_detr import MultiScaleDeformableAttentionFunction
+    from egtr_b200.synth import synth_msda_inputs
+    ref, meta = load_golden(name)
+    value, spatial, start, loc, w = synth_msda_inputs(meta["batch"], [tuple(s) for s in meta["shapes"]], meta["n_query"], seed=meta["seed"])
+    if meta["edge"]:
+        loc = ref["loc"]
+    out = MultiScaleDeformableAttentionFunction.apply(value.to(cuda), spatial.to(cuda), start.to(cuda), loc.to(cuda), w.to(cuda), 64)
+    assert out.shape == ref["out"].shape
+    assert relerr(out, ref["out"]) < 1e-5
+
+
+def test_msda_dropin_errors_like_reference(cuda):
+    from egtr_b200.model.deformable_detr import ms_deform_attn_forward
+    from egtr_b200.synth import synth_msda_inputs
+    v, sp, st, loc, w = synth_msda_inputs(1, [(4, 4), (2, 2), (1, 1), (1, 1)], 3)
+    with pytest.raises(RuntimeError):
+        ms_deform_attn_forward(v, sp, st, loc, w, 64)  # CPU tensors: "Not implemented on the CPU"
+    with pytest.raises(RuntimeError):
+        ms_deform_attn_forward(v.to(cuda).transpose(1, 2), sp.to(cuda), st.to(cuda), loc.to(cuda), w.to(cuda), 64)  # non-contiguous
+
+
+@pytest.mark.parametrize("enc", [True, False])
+def test_msda_fused_matches_oracle_module_arithmetic(cuda, enc):
+    """softmax + sampling locations + gather fused, vs the oracle's step-by-step msda_module."""
+    from egtr_b200 import _lib
+    from oracle import egtr_oracle as orc
+    g = torch.Generator().manual_seed(11)
+    B, shapes = 2, [(9, 13), (5, 7), (3, 4), (2, 2)]
+    S = sum(h * w for h, w in shapes)
+    Lq = S if enc else 21
+    value = torch.randn(B, S, 8, 32, generator=g)
+    offaw = torch.randn(B, Lq, 384, generator=g) * torch.cat([torch.full((256,), 2.0), torch.ones(128)])
+    vr = torch.rand(B, 4, 2, generator=g) * 0.4 + 0.6
+    if enc:
+        ref_pts = orc.encoder_reference_points(shapes, vr)
+        refarg = None
+    else:
+        pts = torch.rand(Lq, 2, generator=g)
+        ref_pts = pts[None, :, None, :] * vr[:, None]
+        refarg = pts.to(cuda)
+    off = offaw[..., :256].view(B, Lq, 8, 4, 4, 2)
+    aw = torch.softmax(offaw[..., 256:].view(B, Lq, 8, 16), -1).view(B, Lq, 8, 4, 4)
+    norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+    loc = ref_pts[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    want = orc.msda_core(value, shapes, loc, aw)
+    out = torch.full((B, Lq, 256), float("nan"), device=cuda)
+    shp = (C.c_int * 8)(*[v for hw in shapes for v in hw])
+    vd, od, vrd = value.to(cuda), offaw.to(cuda), vr.to(cuda)
+    _lib.call("egtr_msda_fused_fwd_f32", vd.data_ptr(), 256, shp, od.data_ptr(), 384, refarg.data_ptr() if refarg is not None else None,
+              vrd.data_ptr(), int(enc), B, S, 8, 32, 4, Lq, 4, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert relerr(out, want) < 1e-5
+
+
+def test_layernorm_maxpool_groupnorm(cuda):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    st = torch.cuda.current_stream().cuda_stream
+    x, r = torch.randn(1001, 256, generator=g) * 3 + 1, torch.randn(1001, 256, generator=g)
+    gam, bet = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    out = torch.empty(1001, 256, device=cuda)
+    xd, rd, gd, bd = x.to(cuda), r.to(cuda), gam.to(cuda), bet.to(cuda)
+    _lib.call("egtr_add_layernorm_f32", xd.data_ptr(), rd.data_ptr(), gd.data_ptr(), bd.data_ptr(), 1001, 256, out.data_ptr(), st)
+    assert relerr(out, torch.nn.functional.layer_norm((x + r).double(), (256,), gam.double(), bet.double())) < 1e-5
+    # max-pool
+    xi = torch.randn(2, 64, 23, 31, generator=g)
+    want = torch.nn.functional.max_pool2d(xi, 3, 2, 1).permute(0, 2, 3, 1)
+    xn = xi.permute(0, 2, 3, 1).contiguous().to(cuda)
+    o = torch.empty(2, 12, 16, 64, device=cuda)
+    _lib.call("egtr_maxpool3x3s2_nhwc_f32", xn.data_ptr(), 2, 23, 31, 64, o.data_ptr(), st)
+    assert torch.equal(o.cpu(), want.contiguous())
+    # GroupNorm on a level slice of a [B,S,256] buffer
+    B, S, off, rows = 2, 700, 130, 431
+    buf = torch.randn(B, S, 256, generator=g) * 2 + 0.5
+    want = buf.clone()
+    sl = buf[:, off:off + rows].permute(0, 2, 1).reshape(B, 256, rows, 1)
+    want[:, off:off + rows] = torch.nn.functional.group_norm(sl.double(), 32, gam.double(), bet.double(), 1e-5).float().reshape(B, 256, rows).permute(0, 2, 1)
+    bd2 = buf.to(cuda)
+    scratch = torch.empty(int(_lib.call("egtr_groupnorm_scratch_doubles", B, rows)), dtype=torch.float64, device=cuda)
+    _lib.call("egtr_groupnorm_f32", bd2.data_ptr(), B, rows, S, off, 256, 32, gd.data_ptr(), bd.data_ptr(), scratch.data_ptr(), st)
+    assert relerr(bd2, want) < 1e-5
+
+
+def test_levels_geometry_matches_oracle(cuda):
+    from egtr_b200 import _lib
+    from egtr_b200.engine import level_shapes
+    from egtr_b200.synth import synth_images
+    from oracle import egtr_oracle as orc
+    H, W, B = 150, 203, 3
+    _, mask = synth_images(B, H, W, pad_to=[(150, 203), (97, 203), (150, 121)])
+    shapes = level_shapes(H, W)
+    S = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(9)
+    lvl = torch.randn(4, 256, generator=g)
+    masks = [orc.nearest_mask(mask, s) for s in shapes]
+    want_mask = torch.cat([m.flatten(1) for m in masks], 1)
+    want_pos = torch.cat([orc.sine_position_embedding(m).flatten(2).transpose(1, 2) + lvl[l] for l, m in enumerate(masks)], 1)
+    want_vr = torch.stack([orc.valid_ratio(m) for m in masks], 1)
+    md, ld = mask.to(cuda), lvl.to(cuda)
+    mf = torch.empty(B, S, dtype=torch.uint8, device=cuda)
+    pos = torch.empty(B, S, 256, device=cuda)
+    vr = torch.empty(B, 4, 2, device=cuda)
+    scr = torch.empty(2 * B * S, device=cuda)
+    shp = (C.c_int * 8)(*[v for hw in shapes for v in hw])
+    _lib.call("egtr_levels_geometry_f32", md.data_ptr(), B, H, W, shp, 4, ld.data_ptr(), 256, mf.data_ptr(), pos.data_ptr(), vr.data_ptr(),
+              scr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(mf.cpu().bool(), want_mask)
+    assert torch.equal(vr.cpu(), want_vr)
+    assert float((pos.cpu() - want_pos).abs().max()) < 2e-5
+
+
+def test_mha_core_and_small_linear(cuda):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    st = torch.cuda.current_stream().cuda_stream
+    B, N = 2, 77
+    qkv = torch.randn(B * N, 768, generator=g)
+    q, k, v = [qkv[:, i * 256:(i + 1) * 256].view(B, N, 8, 32).transpose(1, 2).double() for i in range(3)]
+    want = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).transpose(1, 2).reshape(B * N, 256)
+    qd = qkv.to(cuda)
+    out = torch.empty(B * N, 256, device=cuda)
+    _lib.call("egtr_mha_core_f32", qd.data_ptr(), 768, B, N, 8, 32, out.data_ptr(), st)
+    assert relerr(out, want) < 1e-5
+    # bbox-style small linear with inverse-sigmoid reference add
+    x = torch.randn(B * N, 256, generator=g)
+    w, b = torch.randn(4, 256, generator=g) / 16, torch.randn(4, generator=g)
+    ref = torch.rand(N, 2, generator=g)
+    ref[0, 0], ref[1, 1] = 0.0, 1.0
+    y = x.double() @ w.double().t() + b.double()
+    r = ref.double().repeat(B, 1).clamp(0, 1)
+    y[:, :2] += torch.log(r.clamp(min=1e-5) / (1 - r).clamp(min=1e-5))
+    xd, wd, bd, rd = x.to(cuda), w.to(cuda), b.to(cuda), ref.to(cuda)
+    o = torch.empty(B * N, 4, device=cuda)
+    _lib.call("egtr_small_linear_f32", xd.data_ptr(), 256, wd.data_ptr(), bd.data_ptr(), B * N, 256, 4, 2, rd.data_ptr(), 2, N, o.data_ptr(), 4, st)
+    assert relerr(o, y.sigmoid()) < 1e-5

@@ -1,0 +1,37 @@
+"""CPU: the oracle against the golden fixtures produced by the unmodified reference."""
+import pytest
+import torch
+
+from oracle import egtr_oracle as orc
+from tests.util import case_inputs, compare_forward, load_golden, relerr
+
+FORWARD_CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq"]
+
+
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_oracle_matches_reference_forward(name):
+    ref, meta = load_golden(name)
+    cfg, sd, px, mask = case_inputs(meta)
+    out = orc.forward(sd, cfg, px, mask)
+    errs = compare_forward(out, ref)
+    assert max(errs.values()) < 5e-5, errs
+
+
+@pytest.mark.parametrize("name", ["msda_enc_small", "msda_dec_small", "msda_edge"])
+def test_oracle_msda_core_matches_reference_kernel_twin(name):
+    from egtr_b200.synth import synth_msda_inputs
+
+    ref, meta = load_golden(name)
+    value, spatial, start, loc, w = synth_msda_inputs(meta["batch"], [tuple(s) for s in meta["shapes"]], meta["n_query"], seed=meta["seed"])
+    if meta["edge"]:
+        loc = ref["loc"]
+    out = orc.msda_core(value, [tuple(s) for s in meta["shapes"]], loc, w)
+    assert relerr(out, ref["out"]) < 1e-5
+
+
+def test_nearest_mask_matches_interpolate():
+    torch.manual_seed(0)
+    m = (torch.rand(2, 37, 53) > 0.3).long()
+    for size in [(5, 7), (10, 14), (19, 27), (3, 4)]:
+        ref = torch.nn.functional.interpolate(m[None].float(), size=size).to(torch.bool)[0]
+        assert torch.equal(orc.nearest_mask(m, size), ref)
