@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Throughput bench of the EGTR inference hot path on B200 (contract: task prompt §④ / BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A step = one forward of the hot path over one batch of synthetic images per GPU (workload B of
+BASELINE.json: VG config, 3x800x1333, N_q=200, 150 classes, 50 predicates, batch 1 per GPU) plus,
+for N > 1, the single all-gather of per-image result records.  Prints ONE JSON line (rank 0).
+
+  value : images/s with the inputs already resident in HBM; the forward replayed as one CUDA graph;
+          per-step CUDA-event timing, L2 flushed before every step, max over ranks.
+  e2e   : images/s through the public model API (`model(pixel_values=..., pixel_mask=...)`) starting
+          from pinned HOST buffers: H2D of the batch and D2H of logits/boxes/pred_rel/pred_connectivity
+          are inside the timed region, as are the eager kernel launches.
+  roofline : the kernel class with the largest share of the step (CUDA events around its launches in
+             the e2e loop); `roofline_msda` / `roofline_relation` report the two kernels BASELINE.json names.
+  cpu_baseline : the CPU oracle (a port of the reference forward, oracle/egtr_oracle.py) timed on this
+                 box's host cores on a bounded sample (rank 0, N=1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (3x800x1333, N_q=200)"
+WORKLOAD = "B"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(batch):
+    from egtr_b200.config import WORKLOADS, workload_config
+    from egtr_b200.synth import synth_images, synth_state_dict
+    cfg = workload_config(WORKLOAD)
+    H, W = WORKLOADS[WORKLOAD]["image"]
+    sd = synth_state_dict(cfg, seed=0)
+    px, mask = synth_images(batch, H, W, seed=1)
+    return cfg, sd, px, mask, (H, W)
+
+
+def run_reference(args):
+    """The reference algorithm on the host CPU (oracle port; the Python reference cannot travel to the GPU box)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import egtr_oracle as orc
+    cfg, sd, px, mask, (H, W) = build_case(1)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(max(1, args.warmup)):
+        orc.forward(sd, cfg, px, mask)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.forward(sd, cfg, px, mask)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} forwards of one 3x{H}x{W} image (workload {WORKLOAD}), {max(1, args.warmup)} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(1, args.warmup), "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: VG config, 1x3x{H}x{W}, N_q={cfg.num_queries}, K={cfg.num_labels}, P={cfg.num_rel_labels}, host CPU"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=3, help="oracle forwards timed for cpu_baseline (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    args.warmup = max(3, args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from egtr_b200 import _lib
+    from egtr_b200.model.egtr import DetrForSceneGraphGeneration
+    from egtr_b200.parallel import all_gather_records, pack_records, record_layout
+
+    Bl = args.batch_per_gpu
+    cfg, sd, px, mask, (H, W) = build_case(Bl)
+    model = DetrForSceneGraphGeneration(cfg)
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    eng = model.engine()
+    layout = record_layout(cfg.num_queries, cfg.num_labels, cfg.num_rel_labels)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------ leg 1: device-resident inputs, CUDA-graph replay
+    px_d, mask_d = px.to(dev), mask.to(dev)
+    runner = eng.graph_runner(Bl, H, W)
+
+    def step_resident():
+        out = runner(px_d, mask_d)
+        if world > 1:
+            return all_gather_records(pack_records(out, layout), Bl)
+        return out
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    _lib.call("egtr_launch_count_reset")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev:
+        flush.fill_(1)
+        s.record()
+        step_resident()
+        e.record()
+    barrier()
+    t_res = sum(s.elapsed_time(e) for s, e in ev) / 1000.0
+    # launches inside one replayed graph == launches of one eager forward; count them on an eager pass below
+
+    # ------------------------------------------------------------ leg 2: end to end through the model API from host memory
+    px_h, mask_h = px.pin_memory(), mask.pin_memory()
+    h2d = px_h.numel() * 4 + mask_h.numel() * 8
+
+    def step_e2e():
+        o = model(pixel_values=px_h.to(dev, non_blocking=True), pixel_mask=mask_h.to(dev, non_blocking=True),
+                  output_attentions=False, output_attention_states=True, output_hidden_states=True)
+        res = {k: o[k] for k in ("logits", "pred_boxes", "pred_rel", "pred_connectivity")}
+        if world > 1:
+            flat = all_gather_records(pack_records(res, layout), Bl)
+            host = flat[rank * Bl:(rank + 1) * Bl].cpu()  # each rank reads back its own images' records
+            return host.numel() * 4
+        host = [v.cpu() for v in res.values()]
+        return sum(t.numel() * 4 for t in host)
+
+    d2h = 0
+    for _ in range(args.warmup):
+        d2h = step_e2e()
+    barrier()
+    _lib.call("egtr_launch_count_reset")
+    eng.probe = {}
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for s, e in ev2:
+        s.record()
+        step_e2e()
+        e.record()
+    barrier()
+    t_e2e_wall = time.perf_counter() - t0
+    t_e2e = sum(s.elapsed_time(e) for s, e in ev2) / 1000.0
+    launches = int(_lib.call("egtr_launch_count")) // args.steps
+    probe, eng.probe = eng.probe, None
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(t[0]), float(t[1])
+    spans = {k: sum(a.elapsed_time(b) for a, b in v) / 1000.0 / args.steps for k, v in probe.items()}  # seconds per step
+    counts = {k: len(v) // args.steps for k, v in probe.items()}
+
+    if rank == 0:
+        peaks = _peaks()
+        S = sum(h * w for h, w in eng._workspace(Bl, H, W)["shapes"])
+        N, P, K = cfg.num_queries, cfg.num_rel_labels, cfg.num_labels
+        img_s = world * Bl * args.steps / t_res
+        img_s_e2e = world * Bl * args.steps / t_e2e
+
+        def hbm_roof(name, bytes_per_launch, n):
+            if name not in spans or n == 0:
+                return None
+            t_launch = spans[name] / n
+            ach = bytes_per_launch / t_launch / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": None, "kernel": name, "avg_launch_us": 1e6 * t_launch, "launches_per_step": n,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peaks["src"] + " (hbm_gbs)"}
+
+        # MSDeformAttn, encoder form: SURVEY.md §8d algorithmic bytes = 4*B*[S*C + Lq*M*L*P*3 + Lq*C] = 3584*S per image
+        r_msda = hbm_roof("msda_enc", 3584 * S * Bl, counts.get("msda_enc", 0))
+        r_msda_dec = hbm_roof("msda_dec", (1024 * S + 2560 * N) * Bl, counts.get("msda_dec", 0))
+        # relation head stage (a13-a16): algorithmic HBM bytes per image: Q/K/h in 13*N*1024,
+        # logits 4NK, freq-bias gather min(4N^2P, 4(K+1)^2P), outputs 4N^2(P+1), weights ~5.3 MB once
+        rel_bytes = Bl * (13 * N * 1024 + 4 * N * K + min(4 * N * N * P, 4 * (K + 1) ** 2 * P) + 4 * N * N * (P + 1)) + 5.3e6
+        rel_flops = Bl * (826880 * N * N + 14 * N * 131072) if P == 50 else None
+        r_rel = None
+        if "stage_relation" in spans:
+            tl = spans["stage_relation"]
+            r_rel = {"bound": "tensor", "achieved": (rel_flops or 0) / tl / 1e12, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                     "frac": (rel_flops or 0) / tl / 1e12 / peaks["bf16"], "traffic": None, "kernel": "relation head stage (all its launches)",
+                     "stage_us": 1e6 * tl, "hbm_GBps_on_algorithmic_bytes": rel_bytes / tl / 1e9,
+                     "hbm_frac": rel_bytes / tl / 1e9 / peaks["hbm"], "note": "FLOPs as written in the reference (SURVEY.md §8d)"}
+        stage = {k[6:]: round(1e3 * v, 3) for k, v in spans.items() if k.startswith("stage_")}
+        # dominant kernel class of the step = the stage with the largest share; report the HBM roofline of the
+        # encoder gather kernel as `roofline` (BASELINE.json's named kernel) and keep the others beside it
+        out = {
+            "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split products with fp32 accumulate on tcgen05 (fp32-equivalent); fp32 elsewhere", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: VG config, {Bl}x3x{H}x{W} per GPU, N_q={N}, K={K}, P={P}, S={S}",
+                       "parallelism": f"image-parallel x{world}, one all-gather of per-image records" if world > 1 else "single GPU",
+                       "global_batch": world * Bl, "timing": "CUDA events per step, 256 MiB L2 flush before each step, max over ranks",
+                       "value_leg": "CUDA-graph replay, inputs resident in HBM", "e2e_leg": "eager launches via model API, pinned host buffers"},
+            "clocks": clocks,
+            "e2e": {"value": img_s_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000 * t_e2e / args.steps, "wall_ms_per_step": 1000 * t_e2e_wall / args.steps},
+            "gpu_launches": launches,
+            "roofline": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,
+            "stage_ms": stage,
+        }
+        if args.cpu_sample > 0 and world == 1:
+            from oracle import egtr_oracle as orc
+            cfg1, sd1, px1, mask1, _ = build_case(1)
+            torch.set_num_threads(os.cpu_count() or 1)
+            orc.forward(sd1, cfg1, px1, mask1)
+            t0 = time.perf_counter()
+            for _ in range(args.cpu_sample):
+                orc.forward(sd1, cfg1, px1, mask1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"{args.cpu_sample} oracle forwards of one 3x{H}x{W} image after 1 warm-up"}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

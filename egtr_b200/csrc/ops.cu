@@ -177,7 +177,7 @@ level_masks_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLeve
 // sine embedding (850-876; normalize=True, scale=2*pi, T=10000) + level_embed (2262); C == 256
 __global__ void __launch_bounds__(256)
 pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum, GeoLevels lv, int S, const float* __restrict__ level_embed,
-                 float* __restrict__ pos) {
+                 const float* __restrict__ dim_t_tab, float* __restrict__ pos) {
   const int tok = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
   int l = 0;
   while (l + 1 < lv.L && tok >= lv.start[l + 1]) ++l;
@@ -191,7 +191,9 @@ pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum,
   if (is_y) { e = ycum[base + pix]; last = ycum[base + (h - 1) * w + x]; }
   else      { e = xcum[base + pix]; last = xcum[base + y * w + (w - 1)]; }
   const float v = (e - 0.5f) / (last + 1e-6f) * 6.283185307179586f;
-  const float dim_t = powf(10000.f, (float)(2 * (i / 2)) / 128.f);
+  // dim_t = 10000^(2*(i//2)/128) comes from a host-made table so that fully padded columns, whose
+  // normalised coordinate is -0.5/1e-6 (the reference divides by last+eps, 857-858), see bit-identical arguments.
+  const float dim_t = dim_t_tab[i];
   const float a = v / dim_t;
   pos[((long long)b * S + tok) * 256 + c] = ((i & 1) ? cosf(a) : sinf(a)) + level_embed[l * 256 + c];
 }
@@ -331,9 +333,9 @@ extern "C" long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b) {
 }
 
 extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H, int W, const int* shapes_hw, int L,
-                                        const float* level_embed, int C, uint8_t* mask_flat, float* pos_flat,
+                                        const float* level_embed, const float* dim_t, int C, uint8_t* mask_flat, float* pos_flat,
                                         float* valid_ratios, float* scratch, egtr_stream_t s) {
-  EGTR_CHECK(pixel_mask && shapes_hw && level_embed && mask_flat && pos_flat && valid_ratios && scratch, EGTR_ERR_ARG,
+  EGTR_CHECK(pixel_mask && shapes_hw && level_embed && dim_t && mask_flat && pos_flat && valid_ratios && scratch, EGTR_ERR_ARG,
              "egtr_levels_geometry_f32: null pointer");
   EGTR_CHECK(C == 256 && L >= 1 && L <= 8 && B > 0 && B <= 65535, EGTR_ERR_UNSUPPORTED, "egtr_levels_geometry_f32: C=%d L=%d", C, L);
   GeoLevels lv;
@@ -348,7 +350,7 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
   float* ycum = scratch;
   float* xcum = scratch + (long long)B * S;
   level_masks_kernel<<<dim3(L, B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat, ycum, xcum, valid_ratios);
-  pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, pos_flat);
+  pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
   count_launch();
   count_launch();
   EGTR_CUDA(cudaGetLastError());

@@ -104,8 +104,28 @@ class Engine:
                 and c.activation_function == "relu"):
             raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
         self._ws: Dict[tuple, dict] = {}
+        self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         with torch.cuda.device(self.device):
             self._prepare(state_dict)
+
+    # ------------------------------------------------------------------ per-kernel timing (bench.py roofline)
+    class _Span:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.probe is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.eng.probe is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.eng.probe.setdefault(self.name, []).append((self.e0, e1))
+
+    def span(self, name):
+        return Engine._Span(self, name)
 
     # ------------------------------------------------------------------ weights
     def _prepare(self, sd_in):
@@ -134,6 +154,8 @@ class Engine:
             p = f"model.input_proj.{l}."
             self.input_proj.append((L(_conv_mat(sd[p + "0.weight"]), sd[p + "0.bias"]), sd[p + "1.weight"].contiguous(), sd[p + "1.bias"].contiguous()))
         self.level_embed = sd["model.level_embed"].contiguous()
+        i = torch.arange(d // 2, dtype=torch.float32)
+        self.dim_t = (10000.0 ** (2 * torch.div(i, 2, rounding_mode="trunc") / (d // 2))).to(dev)  # deformable_detr.py:860-865
 
         def msda(p):
             return dict(
@@ -206,6 +228,15 @@ class Engine:
         self.triplet = sd["triplet_dist"].contiguous()
         self.rel_dist = sd["rel_dist"].contiguous()
         torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def graph_runner(self, B: int, H: int, W: int) -> "GraphRunner":
+        """The ~330 launches of one forward captured once per input shape and replayed as one graph:
+        the host-side launch sequence disappears from the step time (batch 1 is launch-bound otherwise)."""
+        key = ("graph", B, H, W)
+        if key not in self._ws:
+            self._ws[key] = GraphRunner(self, B, H, W)
+        return self._ws[key]
 
     # ------------------------------------------------------------------ launch helpers
     def gemm(self, lin: Lin, M: int, out: torch.Tensor, *, a: Optional[torch.Tensor] = None, lda: Optional[int] = None,
@@ -314,11 +345,12 @@ class Engine:
         f32 = dict(dtype=torch.float32, device=dev)
 
         # ---- geometry: masks, position embeddings, valid ratios (deformable_detr.py:783-785, 850-876, 2064-2073)
-        call("egtr_levels_geometry_f32", _ptr(pm), B, H, W, ws["shapes_c"], Lv, _ptr(self.level_embed), d,
+        call("egtr_levels_geometry_f32", _ptr(pm), B, H, W, ws["shapes_c"], Lv, _ptr(self.level_embed), _ptr(self.dim_t), d,
              _ptr(ws["mask_flat"]), _ptr(ws["pos"]), _ptr(ws["valid_ratios"]), _ptr(ws["geo_scratch"]), st)
 
         # ---- backbone (deformable_detr.py:778): stem 7x7/2 as a gather-GEMM over the NCHW image, max-pool, bottlenecks
         h1, w1 = ws["stem_hw"]
+        _sp_bb = self.span("stage_backbone"); _sp_bb.__enter__()
         self.gemm(self.stem, B * h1 * w1, ws["stem"], relu=True,
                   conv=dict(x=px, mode=2, H=H, W=W, C=3, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=3))
         h, w = ws["c2_hw"]
@@ -368,7 +400,9 @@ class Engine:
             taps["mask_flatten"] = ws["mask_flat"].bool().clone()
             taps["valid_ratios"] = ws["valid_ratios"].clone()
 
+        _sp_bb.__exit__()
         # ---- encoder (deformable_detr.py:1283-1358)
+        _sp_enc = self.span("stage_encoder"); _sp_enc.__enter__()
         M = B * S
         xa, xb, xc = ws["x"]
         pos, offaw, value, attn, ffn = ws["pos"], ws["offaw"], ws["value"], ws["attn"], ws["ffn"]
@@ -377,8 +411,9 @@ class Engine:
             self.gemm(lay["offaw"], M, offaw, a=xa, a2=pos, lda=256)
             self.gemm(lay["value"], M, value, a=xa, lda=256)
             call("egtr_mask_rows_f32", _ptr(value), 256, 256, _ptr(ws["mask_flat"]), M, st)
-            call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
-                 B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
+            with self.span("msda_enc"):
+                call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
+                     B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
             self.gemm(lay["out"], M, xb, a=attn, lda=256, res=xa, ldr=256)
             self.layernorm(xb, None, lay["ln1"], M, xc)
             self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, relu=True)
@@ -388,6 +423,8 @@ class Engine:
                 taps["enc0_out"] = xa.view(B, S, 256).clone()
         enc = xa
         enc_out = enc.view(B, S, 256).clone()
+        _sp_enc.__exit__()
+        _sp_dec = self.span("stage_decoder"); _sp_dec.__enter__()
 
         # ---- decoder (deformable_detr.py:1390-1489, 1774-1968)
         nl = cfg.decoder_layers
@@ -412,8 +449,9 @@ class Engine:
             self.gemm(lay["o"], Md, t0, a=ws["dattn"], lda=256, res=hcur, ldr=256)
             self.layernorm(t0, None, lay["ln1"], Md, t1)
             self.gemm(lay["offaw"], Md, ws["doffaw"], a=t1, a2=qpos, lda=256)
-            call("egtr_msda_fused_fwd_f32", _ptr(dv, i * 256), 256 * nl, ws["shapes_c"], _ptr(ws["doffaw"]), 384,
-                 _ptr(ws["ref"]), _ptr(vr), 0, B, S, 8, 32, Lv, N, 4, _ptr(ws["dattn"]), st)
+            with self.span("msda_dec"):
+                call("egtr_msda_fused_fwd_f32", _ptr(dv, i * 256), 256 * nl, ws["shapes_c"], _ptr(ws["doffaw"]), 384,
+                     _ptr(ws["ref"]), _ptr(vr), 0, B, S, 8, 32, Lv, N, 4, _ptr(ws["dattn"]), st)
             self.gemm(lay["out"], Md, t0, a=ws["dattn"], lda=256, res=t1, ldr=256)
             self.layernorm(t0, None, lay["ln2"], Md, t2)
             self.gemm(lay["fc1"], Md, ws["dffn"], a=t2, lda=256, relu=True)
@@ -434,7 +472,9 @@ class Engine:
         call("egtr_small_linear_f32", _ptr(ws["box_h"][1]), 256, _ptr(self.box2_w), _ptr(self.box2_b), Md, 256, 4, 2,
              _ptr(ws["ref"]), 2, N, _ptr(boxes), 4, st)
 
+        _sp_dec.__exit__()
         # ---- relation head (egtr.py:322-418, 507-516)
+        _sp_rel = self.span("stage_relation"); _sp_rel.__enter__()
         Lr = nl + 1
         P = cfg.num_rel_labels
         sub, obj = ws["sub"], ws["obj"]
@@ -458,6 +498,7 @@ class Engine:
              _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
              int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), _ptr(pred_con), st)
 
+        _sp_rel.__exit__()
         # captured decoder self-attention states as [B, heads, N, 32] views (deformable_detr.py:1179-1185)
         qs = tuple(q.view(B, N, 3, 8, 32)[:, :, 0].permute(0, 2, 1, 3) for q in qkvs)
         ks = tuple(q.view(B, N, 3, 8, 32)[:, :, 1].permute(0, 2, 1, 3) for q in qkvs)
@@ -467,3 +508,36 @@ class Engine:
             encoder_last_hidden_state=enc_out, init_reference_points=ws["ref"].unsqueeze(0).expand(B, -1, -1).clone(),
             decoder_attention_queries=qs, decoder_attention_keys=ks,
         )
+
+
+class GraphRunner:
+    """Static-buffer CUDA graph of `Engine._forward` for one (B, H, W).  Outputs are the graph's own
+    buffers and are overwritten by the next replay (callers that keep results must clone them)."""
+
+    def __init__(self, eng: Engine, B: int, H: int, W: int):
+        self.eng = eng
+        dev = eng.device
+        with torch.cuda.device(dev):
+            self.px = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
+            self.pm = torch.ones(B, H, W, dtype=torch.long, device=dev)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: one-time attribute calls, tensor-map cache, workspace allocation
+                    eng._forward(self.px, self.pm, None)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            probe, eng.probe = eng.probe, None
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = eng._forward(self.px, self.pm, None)
+            eng.probe = probe
+
+    def __call__(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None):
+        self.px.copy_(pixel_values, non_blocking=True)
+        if pixel_mask is not None:
+            self.pm.copy_(pixel_mask, non_blocking=True)
+        else:
+            self.pm.fill_(1)
+        self.graph.replay()
+        return self.out

@@ -32,6 +32,9 @@ class DetrForSceneGraphGeneration(_WeightTree):
     def __init__(self, config, **kwargs):
         super().__init__(config)
         self._engine: Optional[Engine] = None
+        # replay the forward as one CUDA graph per input shape (outputs then alias static buffers that the
+        # next call overwrites); off by default to keep the reference's fresh-tensor semantics
+        self.use_cuda_graph = False
         fg_matrix = kwargs.get("fg_matrix", None)
         if fg_matrix is not None:  # training-time statistics (egtr.py:169-184)
             eps = config.freq_bias_eps
@@ -88,7 +91,12 @@ class DetrForSceneGraphGeneration(_WeightTree):
             raise NotImplementedError("encoder_outputs / *_embeds / decoder_attention_mask are unused by evaluate_egtr.py and not built")
         if output_attentions:
             raise NotImplementedError("output_attentions=True (attention maps) is not built; evaluate_egtr.py passes False")
-        o = self.engine().forward(pixel_values, pixel_mask)
+        if self.use_cuda_graph:
+            B, _, H, W = pixel_values.shape
+            with torch.cuda.device(self.device):
+                o = self.engine().graph_runner(B, H, W)(pixel_values, pixel_mask)
+        else:
+            o = self.engine().forward(pixel_values, pixel_mask)
         return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
         inter = o["intermediate_hidden_states"]
         dec_states = None

@@ -115,9 +115,10 @@ int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, in
 long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b);
 /* pixel_mask [B,H,W] int64 -> per-level nearest-neighbour masks (uint8 [B,S]), sine position
  * embedding + level_embed ([B,S,C]), valid ratios [B,L,2] (deformable_detr.py:783-785, 850-876,
- * 2064-2073, 2262).  shapes_hw: HOST array of L (h,w). */
+ * 2064-2073, 2262).  shapes_hw: HOST array of L (h,w).  dim_t: device table of C/2 floats,
+ * 10000^(2*(i//2)/(C/2)) (deformable_detr.py:860-865). */
 int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H, int W, const int* shapes_hw, int L,
-                             const float* level_embed, int C, uint8_t* mask_flat, float* pos_flat,
+                             const float* level_embed, const float* dim_t, int C, uint8_t* mask_flat, float* pos_flat,
                              float* valid_ratios, float* scratch /* 2*B*S floats */, egtr_stream_t s);
 /* Decoder self-attention core: qkv [B*N, ld] with q (already scaled) at col 0, k at col C, v at
  * col 2C; softmax(q k^T) v per head -> out [B*N, C] (deformable_detr.py:1190-1253). */

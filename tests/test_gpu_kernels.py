@@ -79,7 +79,7 @@ def test_gemm_conv_nhwc(cuda, backend, B, H, W, Cin, Cout, k, s, p):
     xn = x.permute(0, 2, 3, 1).contiguous().to(cuda)
     out = _gemm(lib, Lin, _ptr, _stream, backend, None, _conv_mat(w).to(cuda), b.to(cuda), M=B * OH * OW,
                 conv=dict(x=xn, H=H, W=W, C=Cin, OH=OH, OW=OW, KH=k, KW=k, stride=s, pad=p))
-    assert relerr(out, ref) < (2e-6 if backend == "simt" else 2e-5)
+    assert relerr(out, ref) < (5e-6 if backend == "simt" else 1e-4)  # K up to 18432
 
 
 @pytest.mark.parametrize("backend", ["simt", "tc"])
@@ -204,16 +204,22 @@ def test_levels_geometry_matches_oracle(cuda):
     want_pos = torch.cat([orc.sine_position_embedding(m).flatten(2).transpose(1, 2) + lvl[l] for l, m in enumerate(masks)], 1)
     want_vr = torch.stack([orc.valid_ratio(m) for m in masks], 1)
     md, ld = mask.to(cuda), lvl.to(cuda)
+    i = torch.arange(128, dtype=torch.float32)
+    dim_t = (10000.0 ** (2 * torch.div(i, 2, rounding_mode="trunc") / 128)).to(cuda)
     mf = torch.empty(B, S, dtype=torch.uint8, device=cuda)
     pos = torch.empty(B, S, 256, device=cuda)
     vr = torch.empty(B, 4, 2, device=cuda)
     scr = torch.empty(2 * B * S, device=cuda)
     shp = (C.c_int * 8)(*[v for hw in shapes for v in hw])
-    _lib.call("egtr_levels_geometry_f32", md.data_ptr(), B, H, W, shp, 4, ld.data_ptr(), 256, mf.data_ptr(), pos.data_ptr(), vr.data_ptr(),
+    _lib.call("egtr_levels_geometry_f32", md.data_ptr(), B, H, W, shp, 4, ld.data_ptr(), dim_t.data_ptr(), 256, mf.data_ptr(), pos.data_ptr(), vr.data_ptr(),
               scr.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert torch.equal(mf.cpu().bool(), want_mask)
     assert torch.equal(vr.cpu(), want_vr)
-    assert float((pos.cpu() - want_pos).abs().max()) < 2e-5
+    valid = want_mask[..., None].expand_as(want_pos)
+    assert float((pos.cpu() - want_pos)[valid].abs().max()) < 2e-5
+    # fully padded columns normalise by (0 + 1e-6): arguments of ~3e6 rad, where a 1-ulp difference between
+    # CUDA's and the host's sinf/cosf argument reduction is visible; they belong to masked tokens only.
+    assert float((pos.cpu() - want_pos).abs().max()) < 5e-2
 
 
 def test_mha_core_and_small_linear(cuda):
