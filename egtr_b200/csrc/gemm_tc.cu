@@ -27,6 +27,8 @@
 
 namespace egtr {
 
+void count_launch();
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -52,7 +54,7 @@ struct RowSlot {  // RowInfo packed for shared memory
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
-                  int Npad, int K, int* __restrict__ err) {
+                  int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int* __restrict__ err) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -68,8 +70,10 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = Npad / BLOCK_N;
-  const int total_tiles = m_tiles * n_tiles;
-  const int k_blocks = K / BLOCK_K;
+  // work item = (output tile, K split): few-tile GEMMs with a long K (3x3 convs on C5, decoder FFN) are
+  // spread over the SMs along K; their raw partial sums go to `partial` and a reduce kernel applies the epilogue
+  const int total_tiles = m_tiles * n_tiles * splits;
+  const int k_blocks_all = K / BLOCK_K;
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_w);
@@ -93,9 +97,11 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     // ------------------------------------------------------------------ TMA: weight tiles
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        const int t = w / splits, sp = w - t * splits;
         const int n0 = (t % n_tiles) * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 101);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_TILE_BYTES);
@@ -109,12 +115,14 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
     int stage = 0, phase = 0, it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+      const int sp = w % splits;
+      const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, err, 102);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase, err, 103);
         ptx::tc_fence_after();
         if (lane == 0) {
@@ -127,12 +135,12 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             const uint32_t koff = ks * UMMA_K * 2;  // bytes along K inside the swizzle row
             const uint64_t dah = ptx::umma_desc_sw128(a_hi + koff), dal = ptx::umma_desc_sw128(a_lo + koff);
             const uint64_t dbh = ptx::umma_desc_sw128(b_hi + koff), dbl = ptx::umma_desc_sw128(b_lo + koff);
-            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb | ks) != 0);  // small terms first
+            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb != kb_lo) || (ks != 0));  // small terms first
             ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
             ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+          if (kb == kb_hi - 1) ptx::umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -145,7 +153,9 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     const int kc = lane & 15;   // which float4 of the 64-float run
     const int rsub = lane >> 4; // 0/1: two rows per warp-wide load
     int stage = 0, phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+      const int t = w / splits, sp = w - t * splits;
+      const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
       const long long m0 = (long long)(t / n_tiles) * BLOCK_M;
       ptx::named_bar_sync(1, 128);  // previous tile's readers are done with `rows`
       {
@@ -157,7 +167,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         rows[ptid] = rs;
       }
       ptx::named_bar_sync(1, 128);
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         const int k0 = kb * BLOCK_K;
         int ky = 0, kx = 0, c0 = k0;
         if (src.mode == 1) {
@@ -166,46 +176,18 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           ky = tap / src.KW;
           kx = tap - ky * src.KW;
         }
-        float4 v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = p * 32 + 2 * i + rsub;
-          const RowSlot rs = rows[r];
-          long long off = -1;
-          if (src.mode == 2) {
-            v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
-          }
-          if (rs.base >= 0) {
-            if (src.mode == 0) {
-              off = rs.base + k0;
-            } else {
-              const int iy = rs.iy0 + ky, ix = rs.ix0 + kx;
-              if ((unsigned)iy < (unsigned)src.H && (unsigned)ix < (unsigned)src.W)
-                off = (rs.base + (long long)iy * src.W + ix) * src.C + c0;
-            }
-          }
-          if (off >= 0) {
-            v[i] = __ldg((const float4*)(src.a + off) + kc);
-            if (src.a2 != nullptr) {
-              const float4 w = __ldg((const float4*)(src.a2 + off) + kc);
-              v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
-            }
-          } else {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
         uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
         uint8_t* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        // All global loads of a batch are issued back to back (predicated, no branches) before anything
+        // consumes them, so the 16 (or 2 x 8 with the x+pos addend) 16-byte loads of a thread overlap
+        // in the memory system; the stage's empty barrier is only waited for once they are in flight.
+        auto store_row = [&](int i, const float4& x) {
           const int r = p * 32 + 2 * i + rsub;
           __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(v[i].x, h0, l0);
-          split_bf16(v[i].y, h1, l1);
-          split_bf16(v[i].z, h2, l2);
-          split_bf16(v[i].w, h3, l3);
+          split_bf16(x.x, h0, l0);
+          split_bf16(x.y, h1, l1);
+          split_bf16(x.z, h2, l2);
+          split_bf16(x.w, h3, l3);
           const uint32_t o = ptx::sw128_offset(r, kc >> 1) + (kc & 1) * 8;
           uint2 ph, pl;
           ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
@@ -214,6 +196,56 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
           *(uint2*)(a_hi + o) = ph;
           *(uint2*)(a_lo + o) = pl;
+        };
+        auto row_off = [&](int i) -> long long {
+          const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+          long long off = rs.base + k0;  // plain rows
+          if (src.mode == 1) {
+            const int iy = rs.iy0 + ky, ix = rs.ix0 + kx;
+            const bool in = (unsigned)iy < (unsigned)src.H && (unsigned)ix < (unsigned)src.W;
+            off = in ? (rs.base + (long long)iy * src.W + ix) * src.C + c0 : -1;
+          }
+          return rs.base >= 0 ? off : -1;
+        };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src.mode == 2) {
+          float4 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+            v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : zero4;
+          }
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) store_row(i, v[i]);
+        } else if (src.a2 == nullptr) {
+          long long off[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) off[i] = row_off(i);
+          float4 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(src.a + off[i]) + kc) : zero4;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) store_row(i, v[i]);
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            long long off[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) off[i] = row_off(half * 8 + i);
+            float4 v[8], w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(src.a + off[i]) + kc) : zero4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = off[i] >= 0 ? __ldg((const float4*)(src.a2 + off[i]) + kc) : zero4;
+            if (half == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i].x += w[i].x; v[i].y += w[i].y; v[i].z += w[i].z; v[i].w += w[i].w;
+              store_row(half * 8 + i, v[i]);
+            }
+          }
         }
         ptx::fence_proxy_async_smem();  // make the st.shared visible to the tensor core's async proxy
         ptx::mbar_arrive(&full_bar[stage]);
@@ -223,50 +255,69 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quadrants)
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+      const int t = w / splits, sp = w - t * splits;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const long long m = (long long)(t / n_tiles) * BLOCK_M + warp * 32 + lane;
       const int n0 = (t % n_tiles) * BLOCK_N;
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
       ptx::tc_fence_after();
+      if (splits > 1) {  // raw partial sums [split][M][Npad]
+        float* __restrict__ pp = partial + ((long long)sp * M + m) * Npad + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
+          ptx::tmem_ld_wait();
+          if (m < M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *((float4*)(pp + c0) + j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
       const long long orow = out_row(ep, m);
       float* __restrict__ optr = ep.out + orow * ep.ldo;
       const float* __restrict__ rptr = ep.res ? ep.res + orow * ep.ldr : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
+        const int nb = n0 + c0;
+        const bool vec = (m < M) && (nb + 32 <= N) && ((ep.ldo & 3) == 0) && (!rptr || (ep.ldr & 3) == 0);
+        // bias / residual loads are issued before the TMEM load is waited for, all eight at once
+        float4 bs[8], rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bs[j] = (vec && ep.bias) ? __ldg((const float4*)(ep.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rs[j] = (vec && rptr) ? *((const float4*)(rptr + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
         ptx::tmem_ld_wait();
-        if (m < M) {
-          const int nb = n0 + c0;
-          if (nb + 32 <= N && (ep.ldo & 3) == 0) {
+        if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
-              o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-              if (ep.bias) {
-                const float4 b = __ldg((const float4*)(ep.bias + nb + j));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (rptr) {
-                const float4 q = *(const float4*)(rptr + nb + j);
-                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-              }
-              if (ep.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *(float4*)(optr + nb + j) = o;
-            }
-          } else {
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = __uint_as_float(r[4 * j]) + bs[j].x + rs[j].x;
+            o.y = __uint_as_float(r[4 * j + 1]) + bs[j].y + rs[j].y;
+            o.z = __uint_as_float(r[4 * j + 2]) + bs[j].z + rs[j].z;
+            o.w = __uint_as_float(r[4 * j + 3]) + bs[j].w + rs[j].w;
+            if (ep.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *((float4*)(optr + nb) + j) = o;
+          }
+        } else if (m < M) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = nb + j;
-              if (n < N) {
-                float o = __uint_as_float(r[j]);
-                if (ep.bias) o += __ldg(ep.bias + n);
-                if (rptr) o += rptr[n];
-                if (ep.relu) o = fmaxf(o, 0.f);
-                optr[n] = o;
-              }
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < N) {
+              float o = __uint_as_float(r[j]);
+              if (ep.bias) o += __ldg(ep.bias + n);
+              if (rptr) o += rptr[n];
+              if (ep.relu) o = fmaxf(o, 0.f);
+              optr[n] = o;
             }
           }
         }
@@ -349,6 +400,48 @@ int* device_error_flag() {
   return flag;
 }
 
+// out = epilogue(sum over splits of partial[s][m][n])
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, int Npad, const Epilogue ep) {
+  const int n4 = (N + 3) / 4;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)M * n4) return;
+  const long long m = i / n4;
+  const int n = (int)(i - m * n4) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *(const float4*)(partial + ((long long)s * M + m) * Npad + n);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const long long orow = out_row(ep, m);
+  const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n + j < N) {
+      float v = o[j];
+      if (ep.bias) v += __ldg(ep.bias + n + j);
+      if (ep.res) v += ep.res[orow * ep.ldr + n + j];
+      if (ep.relu) v = fmaxf(v, 0.f);
+      ep.out[orow * ep.ldo + n + j] = v;
+    }
+  }
+}
+
+// grow-only scratch for split-K partial sums (allocated outside graph capture, during warm-up)
+float* partial_buffer(size_t floats) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    // the previous (smaller) buffer is deliberately kept alive: captured CUDA graphs may still point at it
+    float* nb = nullptr;
+    size_t want = floats + floats / 2;
+    if (cudaMalloc(&nb, want * sizeof(float)) != cudaSuccess) return nullptr;
+    buf = nb;
+    cap = want;
+  }
+  return buf;
+}
+
 template <int BLOCK_N>
 int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
@@ -361,9 +454,30 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
     attr_set = true;
   }
   const int tiles = cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, device_error_flag());
+  const int k_blocks = K / BLOCK_K;
+  int splits = 1;
+  if (tiles * 2 <= num_sms() && k_blocks >= 8) {
+    splits = num_sms() / tiles;
+    if (splits > k_blocks / 4) splits = k_blocks / 4;
+    if (splits < 1) splits = 1;
+  }
+  int kbps = cdiv(k_blocks, splits);
+  splits = cdiv(k_blocks, kbps);
+  float* partial = nullptr;
+  if (splits > 1) {
+    partial = partial_buffer((size_t)splits * M * Npad);
+    EGTR_CHECK(partial != nullptr, EGTR_ERR_CUDA, "split-K scratch allocation failed");
+  }
+  const int work = tiles * splits;
+  const int grid = work < num_sms() ? work : num_sms();
+  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
+  if (splits > 1) {
+    const long long n = (long long)M * ((N + 3) / 4);
+    splitk_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(partial, splits, M, N, Npad, ep);
+    count_launch();
+    EGTR_CUDA(cudaGetLastError());
+  }
   return EGTR_OK;
 }
 
@@ -380,8 +494,6 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, i
 }
 
 }  // namespace
-
-void count_launch();
 
 }  // namespace egtr
 
