@@ -82,6 +82,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_threads():
+    """Threads for the CPU legs: all host cores up to 32 — on the 128-core shared GPU hosts torch's CPU
+    kernels at these sizes get slower, not faster, beyond that (round-1 measurement: 108 s/forward at 128)."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("EGTR_CPU_THREADS", "32"))))
+
+
 def build_case(batch):
     from egtr_b200.config import WORKLOADS, workload_config
     from egtr_b200.synth import synth_images, synth_state_dict
@@ -99,8 +105,9 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import egtr_oracle as orc
+    orc.set_msda_impl("grid_sample")  # the reference's own CPU path for MSDeformAttn (deformable_detr.py:925-960, 1096-1101)
     cfg, sd, px, mask, (H, W) = build_case(1)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     for _ in range(max(1, args.warmup)):
         orc.forward(sd, cfg, px, mask)
@@ -127,7 +134,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=3, help="oracle forwards timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="oracle forwards timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -282,8 +289,9 @@ def main():
         }
         if args.cpu_sample > 0 and world == 1:
             from oracle import egtr_oracle as orc
+            orc.set_msda_impl("grid_sample")
             cfg1, sd1, px1, mask1, _ = build_case(1)
-            torch.set_num_threads(os.cpu_count() or 1)
+            torch.set_num_threads(cpu_threads())
             orc.forward(sd1, cfg1, px1, mask1)
             t0 = time.perf_counter()
             for _ in range(args.cpu_sample):

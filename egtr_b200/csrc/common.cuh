@@ -60,7 +60,7 @@ __device__ __forceinline__ RowInfo decode_row(const ASrc& s, long long m, long l
     r.base = b;  // image index; elements are gathered one by one from the NCHW planes
     r.iy0 = oy * s.stride - s.pad;
     r.ix0 = ox * s.stride - s.pad;
-  } else {
+  } else {  // modes 1 and 3: NHWC pixel addressing (mode 3: zero-padded NHWC4 image, pad == 0 here)
     long long ohw = (long long)s.OH * s.OW;
     long long b = m / ohw;
     int rem = (int)(m - b * ohw);
@@ -83,6 +83,14 @@ __device__ __forceinline__ long long row_offset(const ASrc& s, const RowInfo& r,
   int iy = r.iy0 + ky, ix = r.ix0 + kx;
   if ((unsigned)iy >= (unsigned)s.H || (unsigned)ix >= (unsigned)s.W) return -1;
   return (r.base + (long long)iy * s.W + ix) * s.C + c0;
+}
+
+// mode 3 (zero-padded NHWC4 image, the stem): float4 number `q` of the row = filter tap q (4 channels, the 4th
+// zero); offset in floats, or -1 for the K-padding taps.  The image's own zero border replaces bounds checks.
+__device__ __forceinline__ long long tap_offset_nhwc4(const ASrc& s, const RowInfo& r, int q) {
+  if (!r.valid || q >= s.KH * s.KW) return -1;
+  const int ky = q / s.KW, kx = q - ky * s.KW;
+  return (r.base + (long long)(r.iy0 + ky) * s.W + (r.ix0 + kx)) * 4;
 }
 
 // mode 2 (NCHW stem gather): four consecutive k of one row, k = (ky*KW + kx)*C + c, zero beyond KH*KW*C.

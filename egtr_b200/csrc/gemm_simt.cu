@@ -29,9 +29,12 @@ gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K
 
   for (int k0 = 0; k0 < K; k0 += TK) {
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = av;
-    const long long off = src.mode == 2 ? -1 : row_offset(src, ri, k0);
+    const long long off = src.mode >= 2 ? -1 : row_offset(src, ri, k0);
     if (src.mode == 2) {
       if (ri.valid) av = gather4_nchw(src, ri.base, ri.iy0, ri.ix0, k0 + lq * 4);
+    } else if (src.mode == 3) {
+      const long long o3 = tap_offset_nhwc4(src, ri, (k0 >> 2) + lq);
+      if (o3 >= 0) av = __ldg((const float4*)(src.a + o3));
     } else if (off >= 0) {
       av = __ldg((const float4*)(src.a + off) + lq);
       if (src.a2) {
@@ -83,7 +86,7 @@ extern "C" int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N,
   EGTR_CHECK(a && w && ep && a->a && ep->out, EGTR_ERR_ARG, "egtr_gemm_f32: null argument");
   EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 16 == 0, EGTR_ERR_ARG, "egtr_gemm_f32: need K %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
   EGTR_CHECK(a->mode == 0 || (a->mode == 1 && a->C % 16 == 0 && K == a->KH * a->KW * a->C) ||
-                 (a->mode == 2 && K >= a->KH * a->KW * a->C), EGTR_ERR_ARG,
+                 (a->mode == 2 && K >= a->KH * a->KW * a->C) || (a->mode == 3 && a->C == 4 && a->pad == 0 && K >= a->KH * a->KW * 4), EGTR_ERR_ARG,
              "egtr_gemm_f32: conv source needs C %% 16 == 0 and K == KH*KW*C");
   EGTR_CHECK(a->mode != 0 || a->lda % 4 == 0, EGTR_ERR_ARG, "egtr_gemm_f32: lda %% 4 != 0");
   dim3 grid(cdiv(N, TN), cdiv(M, TM));

@@ -11,7 +11,8 @@
 //   warps 0-3  epilogue : tcgen05.ld accumulator rows -> bias/residual/ReLU -> global fp32
 //   warp  4    TMA      : weight tiles (hi and lo planes, pre-split once at load) -> 128B-swizzled smem
 //   warp  5    MMA      : one lane issues tcgen05.mma; owns the TMEM allocation
-//   warps 6-9  A-producer: LDG fp32 activation rows (plain rows, x+pos, or an implicit-im2col gather
+//   warps 6-13 A-producer: two groups of 4 warps take alternate k-blocks, so two k-blocks of global loads are
+//                          always in flight per CTA; each: LDG fp32 activation rows (plain rows, x+pos, or an implicit-im2col gather
 //                          for convolutions), split to bf16 hi/lo in registers, st.shared into the same
 //                          swizzled K-major layout TMA would have produced — activations stay fp32 in
 //                          HBM and there is never an im2col buffer.
@@ -34,8 +35,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;  // 4 epilogue + TMA + MMA + 2 x 4 producer warps
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // one bf16 plane
+constexpr int STG_LD = 36;                           // floats per row of an epilogue transpose tile (32 + 4 pad)
 
 template <int BLOCK_N>
 struct Cfg {
@@ -43,7 +45,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4096 /*barriers, row info*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4608 /*barriers, row info*/ +
+                                    4 * 32 * 36 * 4 /*epilogue transpose tiles*/;
 };
 
 struct RowSlot {  // RowInfo packed for shared memory
@@ -64,7 +67,8 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   uint64_t* tmem_full = empty_bar + C::STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_holder = (uint32_t*)(tmem_empty + 2);
-  RowSlot* rows = (RowSlot*)(ctrl + 256);         // [128] x 16 B
+  RowSlot* rows_all = (RowSlot*)(ctrl + 256);     // [2 groups][128] x 16 B
+  float* stage_out = (float*)(ctrl + 4608);       // [4 warps][32][STG_LD]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,17 +151,19 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       }
     }
   } else if (warp >= 6) {
-    // ------------------------------------------------------------------ A producer (4 warps)
-    const int p = warp - 6;
+    // ------------------------------------------------------------------ A producers (2 groups x 4 warps)
+    const int grp = (warp - 6) >> 2;  // group g fills the k-blocks whose running number is == g (mod 2)
+    const int p = (warp - 6) & 3;
     const int ptid = p * 32 + lane;
     const int kc = lane & 15;   // which float4 of the 64-float run
     const int rsub = lane >> 4; // 0/1: two rows per warp-wide load
-    int stage = 0, phase = 0;
+    RowSlot* rows = rows_all + grp * 128;
+    int seq = 0;  // k-blocks issued so far by this CTA (all work items)
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
       const int t = w / splits, sp = w - t * splits;
       const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
       const long long m0 = (long long)(t / n_tiles) * BLOCK_M;
-      ptx::named_bar_sync(1, 128);  // previous tile's readers are done with `rows`
+      ptx::named_bar_sync(1 + grp, 128);  // previous tile's readers are done with `rows`
       {
         RowInfo ri = decode_row(src, m0 + ptid, M);
         RowSlot rs;
@@ -166,8 +172,10 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         rs.ix0 = ri.ix0;
         rows[ptid] = rs;
       }
-      ptx::named_bar_sync(1, 128);
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      ptx::named_bar_sync(1 + grp, 128);
+      for (int kb = kb_lo; kb < kb_hi; ++kb, ++seq) {
+        if ((seq & 1) != grp) continue;
+        const int stage = seq % C::STAGES, phase = (seq / C::STAGES) & 1;
         const int k0 = kb * BLOCK_K;
         int ky = 0, kx = 0, c0 = k0;
         if (src.mode == 1) {
@@ -218,6 +226,21 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
+        } else if (src.mode == 3) {
+          // stem on the zero-padded NHWC4 image: this thread's float4 of the run is filter tap k0/4 + kc
+          const int tap = (k0 >> 2) + kc;
+          const int tky = tap / src.KW, tkx = tap - tky * src.KW;
+          const bool tap_ok = tap < src.KH * src.KW;
+          float4 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+            const long long off = (rs.base + (long long)(rs.iy0 + tky) * src.W + (rs.ix0 + tkx)) * 4;
+            v[i] = (tap_ok && rs.base >= 0) ? __ldg((const float4*)(src.a + off)) : zero4;
+          }
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) store_row(i, v[i]);
         } else if (src.a2 == nullptr) {
           long long off[16];
 #pragma unroll
@@ -249,7 +272,6 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         }
         ptx::fence_proxy_async_smem();  // make the st.shared visible to the tensor core's async proxy
         ptx::mbar_arrive(&full_bar[stage]);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -258,68 +280,66 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
       const int t = w / splits, sp = w - t * splits;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
-      const long long m = (long long)(t / n_tiles) * BLOCK_M + warp * 32 + lane;
       const int n0 = (t % n_tiles) * BLOCK_N;
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
       ptx::tc_fence_after();
-      if (splits > 1) {  // raw partial sums [split][M][Npad]
-        float* __restrict__ pp = partial + ((long long)sp * M + m) * Npad + n0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
-          ptx::tmem_ld_wait();
-          if (m < M) {
+      // Accumulator rows live one per thread in TMEM (lane = row).  Each 32x32 chunk is transposed through a
+      // padded smem tile so that global traffic is row-contiguous: 8 lanes x float4 cover 128 B of one output
+      // row (4 rows per warp instruction) for the stores and for the residual loads alike.
+      float* stg = stage_out + warp * (32 * STG_LD);
+      const int rsub = lane >> 3, cc = (lane & 7) * 4;
+      const long long m_base = (long long)(t / n_tiles) * BLOCK_M + warp * 32;
+      long long orow[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *((float4*)(pp + c0) + j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tmem_empty[acc]);
-        continue;
+      for (int i = 0; i < 8; ++i) {
+        const long long mr = m_base + i * 4 + rsub;
+        orow[i] = mr < M ? (splits > 1 ? (long long)sp * M + mr : out_row(ep, mr)) : -1;
       }
-      const long long orow = out_row(ep, m);
-      float* __restrict__ optr = ep.out + orow * ep.ldo;
-      const float* __restrict__ rptr = ep.res ? ep.res + orow * ep.ldr : nullptr;
+      float* __restrict__ obase = splits > 1 ? partial : ep.out;
+      const int ldo = splits > 1 ? Npad : ep.ldo;
+      const float* __restrict__ rbase = splits > 1 ? nullptr : ep.res;
+      const float* __restrict__ bias = splits > 1 ? nullptr : ep.bias;
+      const int relu = splits > 1 ? 0 : ep.relu;
+      const int ncols = splits > 1 ? Npad : N;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        const int nb = n0 + c0;
-        const bool vec = (m < M) && (nb + 32 <= N) && ((ep.ldo & 3) == 0) && (!rptr || (ep.ldr & 3) == 0);
-        // bias / residual loads are issued before the TMEM load is waited for, all eight at once
-        float4 bs[8], rs[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bs[j] = (vec && ep.bias) ? __ldg((const float4*)(ep.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          rs[j] = (vec && rptr) ? *((const float4*)(rptr + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = n0 + c0 + cc;  // first of this lane's 4 columns
+        const bool full4 = (n + 4 <= ncols) && ((ldo & 3) == 0) && (!rbase || (ep.ldr & 3) == 0);
+        float4 rs[8];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) {
+          if (full4) b4 = __ldg((const float4*)(bias + n));
+          else { if (n < ncols) b4.x = __ldg(bias + n); if (n + 1 < ncols) b4.y = __ldg(bias + n + 1);
+                 if (n + 2 < ncols) b4.z = __ldg(bias + n + 2); if (n + 3 < ncols) b4.w = __ldg(bias + n + 3); }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rbase && orow[i] >= 0) {
+            const float* rp = rbase + orow[i] * ep.ldr + n;
+            if (full4) rs[i] = *(const float4*)rp;
+            else { if (n < ncols) rs[i].x = rp[0]; if (n + 1 < ncols) rs[i].y = rp[1];
+                   if (n + 2 < ncols) rs[i].z = rp[2]; if (n + 3 < ncols) rs[i].w = rp[3]; }
+          }
+        }
+        uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
         ptx::tmem_ld_wait();
-        if (vec) {
+        __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = __uint_as_float(r[4 * j]) + bs[j].x + rs[j].x;
-            o.y = __uint_as_float(r[4 * j + 1]) + bs[j].y + rs[j].y;
-            o.z = __uint_as_float(r[4 * j + 2]) + bs[j].z + rs[j].z;
-            o.w = __uint_as_float(r[4 * j + 3]) + bs[j].w + rs[j].w;
-            if (ep.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *((float4*)(optr + nb) + j) = o;
-          }
-        } else if (m < M) {
+        for (int j = 0; j < 8; ++j)
+          *(float4*)(stg + lane * STG_LD + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < N) {
-              float o = __uint_as_float(r[j]);
-              if (ep.bias) o += __ldg(ep.bias + n);
-              if (rptr) o += rptr[n];
-              if (ep.relu) o = fmaxf(o, 0.f);
-              optr[n] = o;
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          if (orow[i] < 0) continue;
+          float4 o = *(const float4*)(stg + (i * 4 + rsub) * STG_LD + cc);
+          o.x += b4.x + rs[i].x; o.y += b4.y + rs[i].y; o.z += b4.z + rs[i].z; o.w += b4.w + rs[i].w;
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          float* op = obase + orow[i] * ldo + n;
+          if (full4) *(float4*)op = o;
+          else { if (n < ncols) op[0] = o.x; if (n + 1 < ncols) op[1] = o.y; if (n + 2 < ncols) op[2] = o.z; if (n + 3 < ncols) op[3] = o.w; }
         }
       }
       ptx::tc_fence_before();
@@ -517,8 +537,8 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0 && Npad % 64 == 0 && Npad >= N, EGTR_ERR_ARG,
              "egtr_gemm_sbf16: need K %% 64 == 0 and Npad %% 64 == 0 (M=%d N=%d Npad=%d K=%d)", M, N, Npad, K);
   EGTR_CHECK(a->mode == 0 || (a->mode == 1 && a->C % 64 == 0 && K == a->KH * a->KW * a->C) ||
-                 (a->mode == 2 && K >= a->KH * a->KW * a->C), EGTR_ERR_ARG,
-             "egtr_gemm_sbf16: conv source needs C %% 64 == 0 and K == KH*KW*C (mode=%d C=%d K=%d)", a->mode, a->C, K);
+                 (a->mode == 2 && K >= a->KH * a->KW * a->C) || (a->mode == 3 && a->C == 4 && a->pad == 0 && K >= a->KH * a->KW * 4),
+             EGTR_ERR_ARG, "egtr_gemm_sbf16: conv source needs C %% 64 == 0 and K == KH*KW*C (mode=%d C=%d K=%d)", a->mode, a->C, K);
   EGTR_CHECK(a->mode != 0 || (a->lda % 4 == 0 && a->lda >= K), EGTR_ERR_ARG, "egtr_gemm_sbf16: lda=%d", a->lda);
   EGTR_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)w_planes & 127) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16: alignment");
   count_launch();

@@ -45,6 +45,24 @@ __global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const ui
   if (!keep[row]) ((float4*)(x + row * ld))[i - row * C4] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ------------------------------------------------------------------ NCHW (C=3) -> zero-padded NHWC4
+// one float4 per padded pixel; the border and the 4th channel are zero so the stem's gather needs no bounds checks
+__global__ void pad_nhwc4_kernel(const float* __restrict__ img, int B, int H, int W, int pad, float4* __restrict__ out) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Hp * Wp) return;
+  const int xp = (int)(i % Wp);
+  const long long t = i / Wp;
+  const int yp = (int)(t % Hp), b = (int)(t / Hp);
+  const int x = xp - pad, y = yp - pad;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
+    const long long plane = (long long)H * W, o = (long long)b * 3 * plane + (long long)y * W + x;
+    v.x = __ldg(img + o); v.y = __ldg(img + o + plane); v.z = __ldg(img + o + 2 * plane);
+  }
+  out[i] = v;
+}
+
 // ------------------------------------------------------------------ 3x3/2 pad 1 max-pool, NHWC
 __global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int OH, int OW, float* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -73,7 +91,7 @@ __global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W,
 
 // ------------------------------------------------------------------ GroupNorm (C == 256, 32 groups of 8)
 // pass 1: per (b, row chunk) partial sums per group in double; pass 2: normalise in place.
-constexpr int GN_ROWS = 256;  // rows per CTA
+constexpr int GN_ROWS = 64;  // rows per CTA
 __global__ void __launch_bounds__(256)
 groupnorm_partial_kernel(const float* __restrict__ x, int rows_per_b, int bstride, int off, double* __restrict__ part) {
   // thread = (row lane r8 in 0..7, float4 column c in 0..63 -> group c/2)
@@ -300,6 +318,15 @@ extern "C" int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, 
   EGTR_CHECK(x && keep && rows > 0 && C % 4 == 0 && ld % 4 == 0, EGTR_ERR_ARG, "egtr_mask_rows_f32: bad arguments");
   const long long total = (long long)rows * (C / 4);
   mask_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, ld, C / 4, keep, rows);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_pad_nchw3_to_nhwc4_f32(const float* img, int B, int H, int W, int pad, float* out, egtr_stream_t s) {
+  EGTR_CHECK(img && out && B > 0 && H > 0 && W > 0 && pad >= 0, EGTR_ERR_ARG, "egtr_pad_nchw3_to_nhwc4_f32: bad arguments");
+  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad);
+  pad_nhwc4_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(img, B, H, W, pad, (float4*)out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -136,7 +136,9 @@ class Engine:
         L = lambda w, b=None: Lin(w, b, dev)  # noqa: E731
         bb = "model.backbone.conv_encoder.model."
         w, b = _fold_bn(sd, bb + "conv1", bb + "bn1")
-        self.stem = L(_conv_mat(w, 192), b)
+        # stem weights for the NHWC4 gather: k = (ky*7 + kx)*4 + c, 49 taps x 4 -> 196, padded to K = 256
+        w4 = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1)
+        self.stem = L(_conv_mat(w4, 256), b)
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS, start=1):
             for bi in range(nblk):
@@ -281,6 +283,7 @@ class Engine:
         ws = dict(shapes=shapes, S=S, stem_hw=(h1, w1), c2_hw=(h2, w2))
         ws["shapes_c"] = (C.c_int * (2 * len(shapes)))(*[v for hw in shapes for v in hw])
         ws["starts"] = [sum(h * w for h, w in shapes[:l]) for l in range(len(shapes))]
+        ws["px4"] = torch.empty(B * (H + 6) * (W + 6) * 4, **f32)
         ws["stem"] = torch.empty(B * h1 * w1, 64, **f32)
         # backbone ping-pong buffers sized for the largest stage output (layer1: h2*w2 x 256)
         big = B * h2 * w2 * 256
@@ -351,8 +354,9 @@ class Engine:
         # ---- backbone (deformable_detr.py:778): stem 7x7/2 as a gather-GEMM over the NCHW image, max-pool, bottlenecks
         h1, w1 = ws["stem_hw"]
         _sp_bb = self.span("stage_backbone"); _sp_bb.__enter__()
+        call("egtr_pad_nchw3_to_nhwc4_f32", _ptr(px), B, H, W, 3, _ptr(ws["px4"]), st)
         self.gemm(self.stem, B * h1 * w1, ws["stem"], relu=True,
-                  conv=dict(x=px, mode=2, H=H, W=W, C=3, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=3))
+                  conv=dict(x=ws["px4"], mode=3, H=H + 6, W=W + 6, C=4, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=0))
         h, w = ws["c2_hw"]
         bufs = ws["bb"]
         x = bufs[0]

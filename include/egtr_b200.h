@@ -48,7 +48,9 @@ void egtr_launch_count_reset(void);
  * is non-null, the "x + pos" of deformable_detr.py:1040,1163).  mode 1: implicit im2col over an
  * NHWC tensor [B,H,W,C] for a KHxKW/stride/pad convolution, k = (ky*KW + kx)*C + c.  mode 2: the
  * same gather over an NCHW image with few channels (the 7x7/2 stem on pixel_values [B,3,H,W]):
- * k = (ky*KW + kx)*C + c for k < KH*KW*C, zero for the padding columns up to K. */
+ * k = (ky*KW + kx)*C + c for k < KH*KW*C, zero for the padding columns up to K.  mode 3: the stem on
+ * the zero-padded NHWC4 copy of the image made by egtr_pad_nchw3_to_nhwc4_f32 (C = 4, pad = 0, H/W the
+ * padded sizes): k = (ky*KW + kx)*4 + c, every tap one aligned float4 and no bounds checks. */
 typedef struct {
   const float* a;
   const float* a2;
@@ -105,6 +107,8 @@ int egtr_add_layernorm_f32(const float* x, const float* res, const float* gamma,
                            int rows, int C, float* out, egtr_stream_t s);
 /* zero rows of x[rows, C] where keep[row] == 0 (value.masked_fill, deformable_detr.py:1050-1052). */
 int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s);
+/* pixel_values [B,3,H,W] -> zero-bordered NHWC4 [B,H+2*pad,W+2*pad,4] (4th channel zero). */
+int egtr_pad_nchw3_to_nhwc4_f32(const float* img, int B, int H, int W, int pad, float* out, egtr_stream_t s);
 /* NHWC 3x3/2 pad 1 max-pool. */
 int egtr_maxpool3x3s2_nhwc_f32(const float* x, int B, int H, int W, int C, float* out, egtr_stream_t s);
 /* GroupNorm(32 groups) in place over x[B, rows_per_b (at row offset `off`, batch stride `bstride`

@@ -133,6 +133,36 @@ def msda_core(value: Tensor, shapes: Sequence[Tuple[int, int]], loc: Tensor, wei
     return out.reshape(B, Lq, M * D)
 
 
+def msda_core_grid_sample(value: Tensor, shapes: Sequence[Tuple[int, int]], loc: Tensor, weight: Tensor) -> Tensor:
+    """The reference's own CPU path for K1 — `ms_deform_attn_core_pytorch`, deformable_detr.py:925-960:
+    per level a bilinear `grid_sample(align_corners=False, padding_mode="zeros")` on grids 2*loc-1.  Same
+    result as `msda_core` (tests/test_oracle.py); used by bench.py's CPU legs because it is what the
+    reference actually executes on a CPU (the fallback at deformable_detr.py:1096-1101)."""
+    B, S, M, D = value.shape
+    _, Lq, _, L, P, _ = loc.shape
+    grids = 2 * loc - 1
+    start, sampled = 0, []
+    for l, (H, W) in enumerate(shapes):
+        v = value[:, start : start + H * W].flatten(2).transpose(1, 2).reshape(B * M, D, H, W)
+        start += H * W
+        g = grids[:, :, :, l].transpose(1, 2).flatten(0, 1)  # [B*M, Lq, P, 2]
+        sampled.append(F.grid_sample(v, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+    w = weight.transpose(1, 2).reshape(B * M, 1, Lq, L * P)
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * w).sum(-1).view(B, M * D, Lq)
+    return out.transpose(1, 2).contiguous()
+
+
+MSDA_IMPL = {"gather": msda_core, "grid_sample": msda_core_grid_sample}
+_msda_impl = "gather"
+
+
+def set_msda_impl(name: str) -> None:
+    """`gather` (default; the CUDA kernel's arithmetic, cuh:237-299) or `grid_sample` (the reference's CPU path)."""
+    global _msda_impl
+    assert name in MSDA_IMPL
+    _msda_impl = name
+
+
 def _linear(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return F.linear(x, sd[p + ".weight"], sd[p + ".bias"])
 
@@ -152,7 +182,7 @@ def msda_module(sd, p, query, pos, enc, enc_mask, ref, shapes, heads, points, ta
     aw = F.softmax(aw, -1).view(B, Lq, heads, L, points)
     norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)  # (W_l, H_l)
     loc = ref[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
-    core = msda_core(value, shapes, loc, aw)
+    core = MSDA_IMPL[_msda_impl](value, shapes, loc, aw)
     if taps is not None:
         taps.update(value=value, sampling_locations=loc, attention_weights=aw, core=core)
     return _linear(sd, p + ".output_proj", core)

@@ -105,6 +105,27 @@ def test_gemm_stem_nchw_gather_and_remap(cuda, backend):
     assert float(out.view(B, S, 64)[:, :5].abs().max()) == 0.0 and float(out.view(B, S, 64)[:, 5 + OH * OW:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_gemm_stem_padded_nhwc4(cuda, backend):
+    lib, Lin, _ptr, _stream = _eng_helpers()
+    from egtr_b200.engine import _conv_mat, conv_out
+    g = torch.Generator().manual_seed(6)
+    B, H, W = 2, 41, 53
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    b = torch.randn(64, generator=g)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=2, padding=3).relu().permute(0, 2, 3, 1).reshape(-1, 64)
+    OH, OW = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+    xd = x.to(cuda)
+    x4 = torch.full((B, H + 6, W + 6, 4), float("nan"), device=cuda)
+    lib.call("egtr_pad_nchw3_to_nhwc4_f32", xd.data_ptr(), B, H, W, 3, x4.data_ptr(), _stream())
+    assert torch.equal(x4[:, 3:-3, 3:-3, :3].permute(0, 3, 1, 2).cpu(), x) and float(x4[..., 3].abs().max()) == 0 and float(x4[:, :3].abs().max()) == 0
+    w4 = torch.cat([w, torch.zeros(64, 1, 7, 7)], 1)
+    out = _gemm(lib, Lin, _ptr, _stream, backend, None, _conv_mat(w4, 256).to(cuda), b.to(cuda), relu=True, M=B * OH * OW,
+                conv=dict(x=x4, mode=3, H=H + 6, W=W + 6, C=4, OH=OH, OW=OW, KH=7, KW=7, stride=2, pad=0))
+    assert relerr(out, ref) < (2e-6 if backend == "simt" else 2e-5)
+
+
 @pytest.mark.parametrize("name", ["msda_enc_small", "msda_dec_small", "msda_edge"])
 def test_msda_dropin_matches_reference_golden(cuda, name):
     from egtr_b200.model.deformable_detr import MultiScaleDeformableAttentionFunction

@@ -35,3 +35,13 @@ def test_nearest_mask_matches_interpolate():
     for size in [(5, 7), (10, 14), (19, 27), (3, 4)]:
         ref = torch.nn.functional.interpolate(m[None].float(), size=size).to(torch.bool)[0]
         assert torch.equal(orc.nearest_mask(m, size), ref)
+
+
+def test_both_msda_restatements_agree():
+    from egtr_b200.synth import synth_msda_inputs
+
+    shapes = [(11, 14), (6, 7), (3, 4), (2, 2)]
+    value, spatial, start, loc, w = synth_msda_inputs(2, shapes, 23, seed=77)
+    a = orc.msda_core(value, shapes, loc, w)
+    b = orc.msda_core_grid_sample(value, shapes, loc, w)
+    assert relerr(a, b) < 1e-5
