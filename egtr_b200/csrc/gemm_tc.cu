@@ -51,6 +51,18 @@ struct Cfg {
                                     4 * 32 * 36 * 4 /*epilogue transpose tiles*/;
 };
 
+// Grouped launch: `groups` independent GEMMs of identical (M, N, K) in one grid — different left operands,
+// different weight rows (all groups' planes stacked in one [plane_rows, K] matrix) and different outputs.
+// Used for the seven relation-head projections per side and for the decoder's q|k / v pair.
+constexpr int MAX_GROUPS = 16;
+struct GroupTab {
+  const float* a[MAX_GROUPS];
+  const float* a2[MAX_GROUPS];
+  float* out[MAX_GROUPS];
+  int n_base[MAX_GROUPS];  // first weight/bias row of the group inside the stacked planes
+  int lda[MAX_GROUPS];     // row stride of a / a2 (plain mode)
+};
+
 struct RowSlot {  // RowInfo packed for shared memory
   long long base;
   int iy0, ix0;
@@ -59,7 +71,8 @@ struct RowSlot {  // RowInfo packed for shared memory
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
-                  int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int* __restrict__ err) {
+                  int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int groups, int plane_rows,
+                  const GroupTab tab, int* __restrict__ err) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -78,7 +91,8 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   const int n_tiles = Npad / BLOCK_N;
   // work item = (output tile, K split): few-tile GEMMs with a long K (3x3 convs on C5, decoder FFN) are
   // spread over the SMs along K; their raw partial sums go to `partial` and a reduce kernel applies the epilogue
-  const int total_tiles = m_tiles * n_tiles * splits;
+  const int tiles_per_group = m_tiles * n_tiles;
+  const int total_tiles = groups * tiles_per_group * splits;
   const int k_blocks_all = K / BLOCK_K;
 
   if (warp == 4 && lane == 0) {
@@ -104,15 +118,16 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-        const int t = w / splits, sp = w - t * splits;
-        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int tg = w / splits, sp = w - tg * splits;
+        const int g = tg / tiles_per_group, t = tg - g * tiles_per_group;
+        const int n0 = tab.n_base[g] + (t % n_tiles) * BLOCK_N;
         const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 101);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_TILE_BYTES);
           ptx::tma_load_2d(st + 2 * A_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
-          ptx::tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, Npad + n0);
+          ptx::tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, plane_rows + n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -162,12 +177,16 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     RowSlot* rows = rows_all + grp * 128;
     int seq = 0;  // k-blocks issued so far by this CTA (all work items)
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-      const int t = w / splits, sp = w - t * splits;
+      const int tg = w / splits, sp = w - tg * splits;
+      const int g = tg / tiles_per_group, t = tg - g * tiles_per_group;
+      const float* __restrict__ a_ptr = tab.a[g];
+      const float* __restrict__ a2_ptr = tab.a2[g];
       const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
       const long long m0 = (long long)(t / n_tiles) * BLOCK_M;
       ptx::named_bar_sync(1 + grp, 128);  // previous tile's readers are done with `rows`
       {
         RowInfo ri = decode_row(src, m0 + ptid, M);
+        if (src.mode == 0) ri.base = (m0 + ptid) * (long long)tab.lda[g];
         RowSlot rs;
         rs.base = ri.valid ? ri.base : -1;
         rs.iy0 = ri.iy0;
@@ -243,20 +262,20 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           for (int i = 0; i < 16; ++i) {
             const RowSlot rs = rows[p * 32 + 2 * i + rsub];
             const long long off = (rs.base + (long long)(rs.iy0 + tky) * src.W + (rs.ix0 + tkx)) * 4;
-            v[i] = (tap_ok && rs.base >= 0) ? __ldg((const float4*)(src.a + off)) : zero4;
+            v[i] = (tap_ok && rs.base >= 0) ? __ldg((const float4*)(a_ptr + off)) : zero4;
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) pack_row(v[i]);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
-        } else if (src.a2 == nullptr) {
+        } else if (a2_ptr == nullptr) {
           long long off[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) off[i] = row_off(i);
           float4 v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(src.a + off[i]) + kc) : zero4;
+          for (int i = 0; i < 16; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
 #pragma unroll
           for (int i = 0; i < 16; ++i) pack_row(v[i]);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
@@ -270,9 +289,9 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             for (int i = 0; i < 8; ++i) off[i] = row_off(half * 8 + i);
             float4 v[8], w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(src.a + off[i]) + kc) : zero4;
+            for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = off[i] >= 0 ? __ldg((const float4*)(src.a2 + off[i]) + kc) : zero4;
+            for (int i = 0; i < 8; ++i) w[i] = off[i] >= 0 ? __ldg((const float4*)(a2_ptr + off[i]) + kc) : zero4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v[i].x += w[i].x; v[i].y += w[i].y; v[i].z += w[i].z; v[i].w += w[i].w;
@@ -291,7 +310,8 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quadrants)
     int it = 0;
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
-      const int t = w / splits, sp = w - t * splits;
+      const int tg = w / splits, sp = w - tg * splits;
+      const int g = tg / tiles_per_group, t = tg - g * tiles_per_group;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const int n0 = (t % n_tiles) * BLOCK_N;
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
@@ -308,10 +328,10 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         const long long mr = m_base + i * 4 + rsub;
         orow[i] = mr < M ? (splits > 1 ? (long long)sp * M + mr : out_row(ep, mr)) : -1;
       }
-      float* __restrict__ obase = splits > 1 ? partial : ep.out;
+      float* __restrict__ obase = splits > 1 ? partial : tab.out[g];
       const int ldo = splits > 1 ? Npad : ep.ldo;
       const float* __restrict__ rbase = splits > 1 ? nullptr : ep.res;
-      const float* __restrict__ bias = splits > 1 ? nullptr : ep.bias;
+      const float* __restrict__ bias = (splits > 1 || !ep.bias) ? nullptr : ep.bias + tab.n_base[g];
       const int relu = splits > 1 ? 0 : ep.relu;
       const int ncols = splits > 1 ? Npad : N;
 #pragma unroll 1
@@ -476,20 +496,25 @@ float* partial_buffer(size_t floats) {
 }
 
 template <int BLOCK_N>
-int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st) {
+int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st,
+           int groups = 1, int plane_rows = 0, const GroupTab* gtab = nullptr) {
   using C = Cfg<BLOCK_N>;
+  if (plane_rows == 0) plane_rows = Npad;
+  GroupTab tab = {};
+  if (gtab) tab = *gtab;
+  else { tab.a[0] = a.a; tab.a2[0] = a.a2; tab.out[0] = ep.out; tab.n_base[0] = 0; tab.lda[0] = a.lda; }
   CUtensorMap tmap;
-  int rc = weight_tensor_map(planes, Npad, K, BLOCK_N, &tmap);
+  int rc = weight_tensor_map(planes, plane_rows, K, BLOCK_N, &tmap);
   if (rc != EGTR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
+  const int tiles = groups * cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
   const int k_blocks = K / BLOCK_K;
   int splits = 1;
-  if (tiles * 2 <= num_sms() && k_blocks >= 8) {
+  if (groups == 1 && tiles * 2 <= num_sms() && k_blocks >= 8) {
     splits = num_sms() / tiles;
     if (splits > k_blocks / 4) splits = k_blocks / 4;
     if (splits < 1) splits = 1;
@@ -503,7 +528,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   }
   const int work = tiles * splits;
   const int grid = work < num_sms() ? work : num_sms();
-  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, device_error_flag());
+  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long n = (long long)M * ((N + 3) / 4);
@@ -562,4 +587,34 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   if (Npad % 256 == 0) return launch<256>(*a, w_planes, M, N, Npad, K, *ep, st);
   if (Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
   return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);
+}
+
+extern "C" int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* const* a2_ptrs, float* const* out_ptrs,
+                                       const int* n_base, int groups, const int* lda, const void* w_planes, int plane_rows, int M,
+                                       int N, int Npad, int K, const egtr_epilogue_t* ep, egtr_stream_t s) {
+  EGTR_CHECK(a_ptrs && out_ptrs && n_base && w_planes && ep, EGTR_ERR_ARG, "egtr_gemm_sbf16_grouped: null argument");
+  EGTR_CHECK(groups >= 1 && groups <= MAX_GROUPS, EGTR_ERR_ARG, "egtr_gemm_sbf16_grouped: 1..%d groups (got %d)", MAX_GROUPS, groups);
+  EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0 && Npad % 64 == 0 && Npad >= N && plane_rows % 64 == 0, EGTR_ERR_ARG,
+             "egtr_gemm_sbf16_grouped: bad shape (M=%d N=%d Npad=%d K=%d)", M, N, Npad, K);
+  EGTR_CHECK(lda && ep->res == nullptr && ep->rows_per_b == 0, EGTR_ERR_ARG,
+             "egtr_gemm_sbf16_grouped: plain rows, no residual / row remap");
+  GroupTab tab = {};
+  for (int g = 0; g < groups; ++g) {
+    EGTR_CHECK(a_ptrs[g] && out_ptrs[g] && n_base[g] % 64 == 0 && n_base[g] + Npad <= plane_rows && lda[g] % 4 == 0 &&
+                   lda[g] >= K, EGTR_ERR_ARG, "egtr_gemm_sbf16_grouped: group %d", g);
+    tab.a[g] = a_ptrs[g];
+    tab.a2[g] = a2_ptrs ? a2_ptrs[g] : nullptr;
+    tab.out[g] = out_ptrs[g];
+    tab.n_base[g] = n_base[g];
+    tab.lda[g] = lda[g];
+  }
+  ASrc a = {};
+  a.a = a_ptrs[0];
+  a.mode = 0;
+  a.lda = lda[0];
+  count_launch();
+  cudaStream_t st = (cudaStream_t)s;
+  if (Npad % 256 == 0) return launch<256>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
+  if (Npad % 128 == 0) return launch<128>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
+  return launch<64>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
 }

@@ -54,6 +54,26 @@ class Lin:
         call("egtr_split_weight_bf16", _ptr(w), self.N, self.K, self.Npad, _ptr(self.planes), _stream())
 
 
+class LinStack:
+    """`groups` weights of identical [N,K] stacked for one grouped launch: planes [2][G*Npad][K], bias [G*Npad]."""
+
+    def __init__(self, ws: List[torch.Tensor], bs: List[Optional[torch.Tensor]], device):
+        self.G = len(ws)
+        self.N, self.K = ws[0].shape
+        self.Npad = ((self.N + 63) // 64) * 64
+        self.plane_rows = self.G * self.Npad
+        w = torch.zeros(self.plane_rows, self.K, dtype=torch.float32, device=device)
+        b = torch.zeros(self.plane_rows, dtype=torch.float32, device=device)
+        for g, (wg, bg) in enumerate(zip(ws, bs)):
+            w[g * self.Npad: g * self.Npad + self.N] = wg.to(device=device, dtype=torch.float32)
+            if bg is not None:
+                b[g * self.Npad: g * self.Npad + self.N] = bg.to(device=device, dtype=torch.float32)
+        self.w, self.b = w, b
+        self.planes = torch.empty(2 * self.plane_rows * self.K, dtype=torch.bfloat16, device=device)
+        call("egtr_split_weight_bf16", _ptr(w), self.plane_rows, self.K, self.plane_rows, _ptr(self.planes), _stream())
+        self.n_base = (C.c_int * self.G)(*[g * self.Npad for g in range(self.G)])
+
+
 def _conv_mat(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     """[Cout,Cin,KH,KW] -> [Cout, KH*KW*Cin] (k = (ky*KW + kx)*Cin + c), optionally zero-padded in K."""
     cout = w.shape[0]
@@ -186,9 +206,9 @@ class Engine:
             p = f"model.decoder.layers.{i}."
             lay = msda(p + "encoder_attn.")
             # q is scaled after the projection in the reference (deformable_detr.py:1166): fold it in.
-            lay["qk"] = L(torch.cat([sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.k_proj.weight"]], 0),
-                          torch.cat([sd[p + "self_attn.q_proj.bias"] * scaling, sd[p + "self_attn.k_proj.bias"]], 0))
-            lay["v"] = L(sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"])
+            # q | k (on h + pos) and v (on h) as three groups of one launch
+            lay["qkv"] = LinStack([sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.v_proj.weight"]],
+                                  [sd[p + "self_attn.q_proj.bias"] * scaling, sd[p + "self_attn.k_proj.bias"], sd[p + "self_attn.v_proj.bias"]], dev)
             lay["o"] = L(sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
             lay["ln1"], lay["ln2"], lay["ln3"] = ln(p + "self_attn_layer_norm"), ln(p + "encoder_attn_layer_norm"), ln(p + "final_layer_norm")
             lay["fc1"], lay["fc2"] = L(sd[p + "fc1.weight"], sd[p + "fc1.bias"]), L(sd[p + "fc2.weight"], sd[p + "fc2.bias"])
@@ -213,14 +233,22 @@ class Engine:
 
         # relation head (egtr.py:322-418): un-scaling of the captured q folded into proj_q
         unscale = (d // heads) ** 0.5
-        self.rel_sub = [L(sd[f"proj_q.{l}.weight"] * unscale, sd[f"proj_q.{l}.bias"]) for l in range(cfg.decoder_layers)]
-        self.rel_obj = [L(sd[f"proj_k.{l}.weight"], sd[f"proj_k.{l}.bias"]) for l in range(cfg.decoder_layers)]
-        self.rel_sub.append(L(sd["final_sub_proj.weight"], sd["final_sub_proj.bias"]))
-        self.rel_obj.append(L(sd["final_obj_proj.weight"], sd["final_obj_proj.bias"]))
         r1, c1, g = sd["rel_predictor.layers.0.weight"], sd["connectivity_layer.layers.0.weight"], sd["rel_predictor_gate.weight"]
-        zeros512 = torch.zeros(2 * d, device=dev)
-        self.rel_u = L(torch.cat([r1[:, :d], c1[:, :d], g[:, :d]], 0), None)
-        self.rel_v = L(torch.cat([r1[:, d:], c1[:, d:], g[:, d:]], 0), torch.cat([zeros512, sd["rel_predictor_gate.bias"]], 0))
+        w1s = torch.cat([r1[:, :d], c1[:, :d], g[:, :d]], 0).double()  # [513,256] acts on the subject half
+        w1o = torch.cat([r1[:, d:], c1[:, d:], g[:, d:]], 0).double()  # [513,256] acts on the object half
+        gate_b = torch.cat([torch.zeros(2 * d, device=dev), sd["rel_predictor_gate.bias"]], 0).double()
+        # Two stacked Linears with nothing in between (proj_q[l] then layer 1 of both MLPs and the gate,
+        # egtr.py:339 -> 400-402/416) are composed once at load, in fp64: U_l = (W1s Wq_l) q_l + W1s b_l.
+        ws, bs = [], []
+        for l in range(cfg.decoder_layers + 1):
+            wq = (sd[f"proj_q.{l}.weight"] * unscale, sd[f"proj_q.{l}.bias"]) if l < cfg.decoder_layers else (sd["final_sub_proj.weight"], sd["final_sub_proj.bias"])
+            ws.append((w1s @ wq[0].double()).float())
+            bs.append((w1s @ wq[1].double()).float())
+        for l in range(cfg.decoder_layers + 1):
+            wk = (sd[f"proj_k.{l}.weight"], sd[f"proj_k.{l}.bias"]) if l < cfg.decoder_layers else (sd["final_obj_proj.weight"], sd["final_obj_proj.bias"])
+            ws.append((w1o @ wk[0].double()).float())
+            bs.append((w1o @ wk[1].double() + gate_b).float())
+        self.rel_uv = LinStack(ws, bs, dev)  # groups 0..6 -> U_l (subject side), 7..13 -> V_l (object side)
         self.rel_b1 = torch.cat([sd["rel_predictor.layers.0.bias"], sd["connectivity_layer.layers.0.bias"]], 0).contiguous()
         self.rel_w2 = L(sd["rel_predictor.layers.1.weight"], sd["rel_predictor.layers.1.bias"])
         self.con_w2 = L(sd["connectivity_layer.layers.1.weight"], sd["connectivity_layer.layers.1.bias"])
@@ -263,6 +291,26 @@ class Engine:
             call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
         else:
             call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+
+    def gemm_grouped(self, st: "LinStack", M: int, *, a, lda, out, ldo, a2=None, a_col=None, relu: bool = False):
+        G = st.G
+        a_col = a_col or [0] * G
+        a2 = a2 or [None] * G
+        ap = (C.c_void_p * G)(*[_ptr(t, c) for t, c in zip(a, a_col)])
+        a2p = (C.c_void_p * G)(*[_ptr(t, c) for t, c in zip(a2, a_col)])
+        op = (C.c_void_p * G)(*[_ptr(t, c) for t, c in out])
+        ldap = (C.c_int * G)(*lda)
+        ep = Epilogue()
+        ep.bias, ep.res, ep.out, ep.ldo, ep.ldr, ep.relu = _ptr(st.b), None, _ptr(out[0][0], out[0][1]), ldo, ldo, int(relu)
+        if gemm_backend() == "simt":  # debug cross-check path: one CUDA-core launch per group
+            for g in range(G):
+                src, e2 = ASrc(), Epilogue()
+                src.a, src.a2, src.mode, src.lda = ap[g], a2p[g], 0, lda[g]
+                e2.bias, e2.out, e2.ldo, e2.ldr, e2.relu = _ptr(st.b, g * st.Npad), op[g], ldo, ldo, int(relu)
+                call("egtr_gemm_f32", C.byref(src), _ptr(st.w, g * st.Npad * st.K), M, st.N, st.K, C.byref(e2), _stream())
+            return
+        call("egtr_gemm_sbf16_grouped", ap, a2p, op, st.n_base, G, ldap, _ptr(st.planes), st.plane_rows, M, st.N, st.Npad, st.K,
+             C.byref(ep), _stream())
 
     def layernorm(self, x, res, ln, rows, out):
         call("egtr_add_layernorm_f32", _ptr(x), _ptr(res), _ptr(ln[0]), _ptr(ln[1]), rows, 256, _ptr(out), _stream())
@@ -310,8 +358,6 @@ class Engine:
         ws["dffn"] = torch.empty(B * N, 1024, **f32)
         ws["box_h"] = [torch.empty(B * N, 256, **f32) for _ in range(2)]
         Lr = cfg.decoder_layers + 1
-        ws["sub"] = torch.empty(B * N * Lr, 256, **f32)
-        ws["obj"] = torch.empty(B * N * Lr, 256, **f32)
         ws["U"] = torch.empty(B * N * Lr, 516, **f32)
         ws["V"] = torch.empty(B * N * Lr, 516, **f32)
         ws["H1"] = torch.empty(B * N * N, 512, **f32)
@@ -447,8 +493,8 @@ class Engine:
             qkv = torch.empty(Md, 768, **f32)  # captured per layer: q (scaled) | k | v
             qkvs.append(qkv)
             t0, t1, t2 = [b for b in hbuf if b is not hcur][:3]
-            self.gemm(lay["qk"], Md, qkv, a=hcur, a2=qpos, lda=256, ldo=768)
-            self.gemm(lay["v"], Md, qkv, a=hcur, lda=256, ldo=768, out_col=512)
+            self.gemm_grouped(lay["qkv"], Md, a=[hcur, hcur, hcur], a2=[qpos, qpos, None], lda=[256, 256, 256],
+                              out=[(qkv, 0), (qkv, 256), (qkv, 512)], ldo=768)
             call("egtr_mha_core_f32", _ptr(qkv), 768, B, N, 8, 32, _ptr(ws["dattn"]), st)
             self.gemm(lay["o"], Md, t0, a=ws["dattn"], lda=256, res=hcur, ldr=256)
             self.layernorm(t0, None, lay["ln1"], Md, t1)
@@ -481,14 +527,12 @@ class Engine:
         _sp_rel = self.span("stage_relation"); _sp_rel.__enter__()
         Lr = nl + 1
         P = cfg.num_rel_labels
-        sub, obj = ws["sub"], ws["obj"]
-        for l in range(nl):
-            self.gemm(self.rel_sub[l], Md, sub, a=qkvs[l], lda=768, a_col=0, ldo=Lr * 256, out_col=l * 256)
-            self.gemm(self.rel_obj[l], Md, obj, a=qkvs[l], lda=768, a_col=256, ldo=Lr * 256, out_col=l * 256)
-        self.gemm(self.rel_sub[nl], Md, sub, a=h_last, lda=256, ldo=Lr * 256, out_col=nl * 256)
-        self.gemm(self.rel_obj[nl], Md, obj, a=h_last, lda=256, ldo=Lr * 256, out_col=nl * 256)
-        self.gemm(self.rel_u, Md * Lr, ws["U"], a=sub, lda=256, ldo=516)
-        self.gemm(self.rel_v, Md * Lr, ws["V"], a=obj, lda=256, ldo=516)
+        # per-query layer-1 partials U_l(i), V_l(j) (+ gate logits in column 512): one grouped launch of 14 GEMMs
+        a_list = [qkvs[l] for l in range(nl)] + [h_last] + [qkvs[l] for l in range(nl)] + [h_last]
+        a_cols = [0] * nl + [0] + [256] * nl + [0]
+        ldas = [768] * nl + [256] + [768] * nl + [256]
+        outs = [(ws["U"], l * 516) for l in range(Lr)] + [(ws["V"], l * 516) for l in range(Lr)]
+        self.gemm_grouped(self.rel_uv, Md, a=a_list, a_col=a_cols, lda=ldas, out=outs, ldo=Lr * 516)
         pairs = B * N * N
         call("egtr_relation_pair_hidden_f32", _ptr(ws["U"]), _ptr(ws["V"]), 516, _ptr(self.rel_b1), B, N, Lr, _ptr(ws["H1"]), st)
         self.gemm(self.rel_w2, pairs, ws["H2r"], a=ws["H1"], lda=512, a_col=0, relu=True)

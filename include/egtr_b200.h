@@ -78,6 +78,15 @@ int egtr_split_weight_bf16(const float* w, int N, int K, int Npad, void* planes,
 int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M, int N, int Npad, int K,
                     const egtr_epilogue_t* ep, egtr_stream_t s);
 
+/* `groups` (<= 16) independent GEMMs of identical (M, N, K) in ONE launch: group g reads rows a_ptrs[g]
+ * (+ a2_ptrs[g] when non-null; row stride lda[g]), multiplies by weight rows [n_base[g], n_base[g]+Npad) of the
+ * stacked planes [2][plane_rows][K], adds ep->bias[n_base[g] + n] and writes out_ptrs[g] (+ ep->ldo, relu).
+ * The pointer arrays are HOST arrays.  Replaces the 14 proj_q/proj_k/final_* Linear calls of the relation
+ * head (model/egtr.py:336-397) and the decoder's q|k and v projections (model/deformable_detr.py:1166-1168). */
+int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* const* a2_ptrs, float* const* out_ptrs,
+                            const int* n_base, int groups, const int* lda, const void* w_planes, int plane_rows, int M,
+                            int N, int Npad, int K, const egtr_epilogue_t* ep, egtr_stream_t s);
+
 /* Same contract on fp32 CUDA cores with W fp32 [N,K]: the small/odd-shape path (K % 16 == 0). */
 int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N, int K,
                   const egtr_epilogue_t* ep, egtr_stream_t s);

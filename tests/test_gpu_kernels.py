@@ -66,6 +66,42 @@ def test_gemm_plain(cuda, backend, M, N, K):
     assert relerr(out2, ref2) < tol
 
 
+def test_gemm_grouped_launch(cuda):
+    """14 relation-style groups (N=513, mixed row strides) and the decoder's q|k|v triple in one launch each."""
+    from egtr_b200.config import workload_config
+    from egtr_b200.engine import Engine, LinStack
+    import types
+    g = torch.Generator().manual_seed(21)
+    M = 200
+    eng = types.SimpleNamespace()
+    bufs = [torch.randn(M, 768, generator=g).to(cuda) for _ in range(3)] + [torch.randn(M, 256, generator=g).to(cuda)]
+    ws = [torch.randn(513, 256, generator=g) / 16 for _ in range(6)]
+    bs = [torch.randn(513, generator=g) for _ in range(6)]
+    st = LinStack(ws, bs, cuda)
+    a = [bufs[0], bufs[1], bufs[3], bufs[0], bufs[2], bufs[3]]
+    cols = [0, 256, 0, 256, 0, 0]
+    ldas = [768, 768, 256, 768, 768, 256]
+    out = torch.full((M, 6 * 516), float("nan"), device=cuda)
+    Engine.gemm_grouped(eng, st, M, a=a, a_col=cols, lda=ldas, out=[(out, i * 516) for i in range(6)], ldo=6 * 516)
+    torch.cuda.synchronize()
+    for i in range(6):
+        x = a[i][:, cols[i]:cols[i] + 256].double().cpu()
+        want = x @ ws[i].double().t() + bs[i].double()
+        assert relerr(out[:, i * 516:i * 516 + 513], want) < 2e-5, i
+    assert torch.isnan(out[:, 513:516]).all()  # padding columns are never written
+    # q|k|v: a2 (position embedding) only on the first two groups
+    h, pos = torch.randn(M, 256, generator=g).to(cuda), torch.randn(M, 256, generator=g).to(cuda)
+    w3 = [torch.randn(256, 256, generator=g) / 16 for _ in range(3)]
+    b3 = [torch.randn(256, generator=g) for _ in range(3)]
+    st3 = LinStack(w3, b3, cuda)
+    qkv = torch.empty(M, 768, device=cuda)
+    Engine.gemm_grouped(eng, st3, M, a=[h, h, h], a2=[pos, pos, None], lda=[256] * 3, out=[(qkv, 0), (qkv, 256), (qkv, 512)], ldo=768)
+    torch.cuda.synchronize()
+    for i in range(3):
+        x = (h + pos if i < 2 else h).double().cpu()
+        assert relerr(qkv[:, i * 256:(i + 1) * 256], x @ w3[i].double().t() + b3[i].double()) < 2e-5
+
+
 @pytest.mark.parametrize("backend", ["simt", "tc"])
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 13, 17, 64, 64, 3, 1, 1), (1, 20, 31, 128, 256, 3, 2, 1),
                                                   (2, 9, 11, 256, 512, 1, 2, 0), (1, 7, 5, 2048, 256, 3, 2, 1)])
