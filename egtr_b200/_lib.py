@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libegtr_b200.so")
+LIB_PATH = os.environ.get("EGTR_B200_LIB", os.path.join(_HERE, "csrc", "libegtr_b200.so"))  # override: dev A/B builds only
 
 
 class EgtrError(RuntimeError):
@@ -77,6 +77,8 @@ def load():
         )
     lib = C.CDLL(LIB_PATH)
     for name, args in SIGNATURES.items():
+        if "EGTR_B200_LIB" in os.environ and not hasattr(lib, name):
+            continue  # dev A/B builds of older kernels may lack newer entry points
         fn = getattr(lib, name)  # AttributeError here = header/library drift
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, C.c_int)

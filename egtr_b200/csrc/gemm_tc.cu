@@ -210,24 +210,21 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         // All global loads of a batch are issued back to back (predicated, no branches) before anything
         // consumes them, so the 16 (or 2 x 8 with the x+pos addend) 16-byte loads of a thread overlap
         // in the memory system; the stage's empty barrier is only waited for once they are in flight.
-        // fp32 -> bf16 hi/lo happens in registers while the stage's empty barrier is still pending; only the
-        // st.shared of the packed pairs sits behind the wait.
-        auto pack_row = [&](float4& x) {  // in place: (x.x,x.y) <- hi pairs, (x.z,x.w) <- lo pairs
+        auto store_row = [&](int i, const float4& x) {  // split one float4 to bf16 hi/lo and store it (interleaves ALU and LSU work)
+          const int r = p * 32 + 2 * i + rsub;
           __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
           split_bf16(x.x, h0, l0);
           split_bf16(x.y, h1, l1);
           split_bf16(x.z, h2, l2);
           split_bf16(x.w, h3, l3);
-          x.x = __uint_as_float((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16));
-          x.y = __uint_as_float((uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16));
-          x.z = __uint_as_float((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16));
-          x.w = __uint_as_float((uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16));
-        };
-        auto store_row = [&](int i, const float4& x) {
-          const int r = p * 32 + 2 * i + rsub;
           const uint32_t o = ptx::sw128_offset(r, kc >> 1) + (kc & 1) * 8;
-          *(uint2*)(a_hi + o) = make_uint2(__float_as_uint(x.x), __float_as_uint(x.y));
-          *(uint2*)(a_lo + o) = make_uint2(__float_as_uint(x.z), __float_as_uint(x.w));
+          uint2 ph, pl;
+          ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+          pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+          *(uint2*)(a_hi + o) = ph;
+          *(uint2*)(a_lo + o) = pl;
         };
         auto row_off = [&](int i) -> long long {
           const RowSlot rs = rows[p * 32 + 2 * i + rsub];
@@ -247,8 +244,6 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             const RowSlot rs = rows[p * 32 + 2 * i + rsub];
             v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : zero4;
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pack_row(v[i]);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
@@ -264,8 +259,6 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             const long long off = (rs.base + (long long)(rs.iy0 + tky) * src.W + (rs.ix0 + tkx)) * 4;
             v[i] = (tap_ok && rs.base >= 0) ? __ldg((const float4*)(a_ptr + off)) : zero4;
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pack_row(v[i]);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
@@ -276,8 +269,6 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           float4 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pack_row(v[i]);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
@@ -292,14 +283,12 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = off[i] >= 0 ? __ldg((const float4*)(a2_ptr + off[i]) + kc) : zero4;
+            if (half == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v[i].x += w[i].x; v[i].y += w[i].y; v[i].z += w[i].z; v[i].w += w[i].w;
-              pack_row(v[i]);
+              store_row(half * 8 + i, v[i]);
             }
-            if (half == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) store_row(half * 8 + i, v[i]);
           }
         }
         ptx::fence_proxy_async_smem();  // make the st.shared visible to the tensor core's async proxy

@@ -47,10 +47,11 @@ struct MsdaArgs {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   __shared__ float slots[QPB * Q_STRIDE];
   __shared__ int q_of[QPB];
+  __shared__ float2 q_ref[QPB];  // encoder form: pixel centre / (valid_ratio * size) of the query's own level
   __shared__ int lvH[MAX_L], lvW[MAX_L], lvS[MAX_L];
 
   const int tid = threadIdx.x;
@@ -74,7 +75,14 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       const int pid = blockIdx.x - lv_in.patch_start[l];
       const int py = pid / lv_in.patches_x[l], px = pid - py * lv_in.patches_x[l];
       const int y = py * 4 + (tid >> 3), x = px * 8 + (tid & 7);
-      if (y < lv_in.H[l] && x < lv_in.W[l]) q = lv_in.start[l] + y * lv_in.W[l] + x;
+      if (y < lv_in.H[l] && x < lv_in.W[l]) {
+        q = lv_in.start[l] + y * lv_in.W[l] + x;
+        // deformable_detr.py:1642-1644: linspace(0.5, n-0.5, n)[i] / (valid_ratio * n); the per-level
+        // valid-ratio factor of line 1647 is applied per sample below
+        const float* vr = a.valid_ratios + (long long)b * L * 2;
+        q_ref[tid] = make_float2(((float)x + 0.5f) / (vr[l * 2 + 0] * (float)lv_in.W[l]),
+                                 ((float)y + 0.5f) / (vr[l * 2 + 1] * (float)lv_in.H[l]));
+      }
     } else {
       q = blockIdx.x * QPB + tid;
       if (q >= a.Lq) q = -1;
@@ -120,14 +128,11 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       if (FUSED) {
         float rx, ry;
         if (a.enc_patches) {
-          // deformable_detr.py:1616-1648: pixel centre / (valid_ratio * size), then * valid_ratio of level l
-          int lq = 0;
-          while (lq + 1 < L && q >= lvS[lq + 1]) ++lq;
-          const int pix = q - lvS[lq];
-          const int py = pix / lvW[lq], px = pix - py * lvW[lq];
+          // deformable_detr.py:1647: reference_points[:, :, None] * valid_ratios[:, None]
           const float* vr = a.valid_ratios + (long long)b * L * 2;
-          rx = ((float)px + 0.5f) / (vr[lq * 2 + 0] * (float)lvW[lq]) * vr[l * 2 + 0];
-          ry = ((float)py + 0.5f) / (vr[lq * 2 + 1] * (float)lvH[lq]) * vr[l * 2 + 1];
+          const float2 r0 = q_ref[qi];
+          rx = r0.x * vr[l * 2 + 0];
+          ry = r0.y * vr[l * 2 + 1];
         } else {
           // decoder: reference_points[:, :, None] * valid_ratios[:, None] (deformable_detr.py:1865-1867);
           // the sigmoid'ed points are shared by the batch ([Lq,2]) because there is no box refinement.
