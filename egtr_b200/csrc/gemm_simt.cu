@@ -76,10 +76,115 @@ gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny GEMM: a few hundred rows (the decoder's N_q queries, the relation head's per-query tensors).
+// These launches are latency-bound, not throughput-bound, so the goal is many small CTAs and no setup
+// cost: 16x64 output tile per 128-thread CTA, K in chunks of 32 with the next chunk's global loads in
+// flight while the current one is multiplied.  fp32 FMA throughout (exact w.r.t. the reference).
+// blockIdx.z = group (stacked weights / per-group operands), as in the tensor-core grouped launch.
+struct SkinnyGroups {
+  const float* a[16];
+  const float* a2[16];
+  float* out[16];
+  int n_base[16];
+  int lda[16];
+};
+
+__global__ void __launch_bounds__(128)
+gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
+  __shared__ float As[16][33];
+  __shared__ float Ws[64][33];
+  const int g = blockIdx.z;
+  const float* __restrict__ A = gt.a[g];
+  const float* __restrict__ A2 = gt.a2[g];
+  const int lda = gt.lda[g];
+  const float* __restrict__ Wg = w + (long long)gt.n_base[g] * K;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 64;
+  const int r = tid >> 3, c8 = tid & 7;          // compute mapping: row r, columns c8 + 8*j (conflict-free smem rows)
+  const int lr = tid >> 3, lq = tid & 7;         // loader mapping: A row lr, float4 lq of the 32-chunk
+  const bool a_ok = (m0 + lr) < M;
+  float4 an = make_float4(0.f, 0.f, 0.f, 0.f), wn[4];
+  auto load = [&](int k0) {
+    an = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_ok) {
+      an = __ldg((const float4*)(A + (long long)(m0 + lr) * lda + k0) + lq);
+      if (A2) {
+        const float4 p = __ldg((const float4*)(A2 + (long long)(m0 + lr) * lda + k0) + lq);
+        an.x += p.x; an.y += p.y; an.z += p.z; an.w += p.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int wr = n0 + i * 16 + lr;
+      wn[i] = (wr < N) ? __ldg((const float4*)(Wg + (long long)wr * K + k0) + lq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  load(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    __syncthreads();
+    As[lr][lq * 4 + 0] = an.x; As[lr][lq * 4 + 1] = an.y; As[lr][lq * 4 + 2] = an.z; As[lr][lq * 4 + 3] = an.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* d = &Ws[i * 16 + lr][lq * 4];
+      d[0] = wn[i].x; d[1] = wn[i].y; d[2] = wn[i].z; d[3] = wn[i].w;
+    }
+    __syncthreads();
+    if (k0 + 32 < K) load(k0 + 32);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a = As[r][k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, Ws[c8 + 8 * j][k], acc[j]);
+    }
+  }
+  const int m = m0 + r;
+  if (m >= M) return;
+  const long long orow = out_row(ep, m);
+  float* __restrict__ out = gt.out[g];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + c8 + 8 * j;
+    if (n < N) {
+      float o = acc[j];
+      if (ep.bias) o += __ldg(ep.bias + gt.n_base[g] + n);
+      if (ep.res) o += ep.res[orow * ep.ldr + n];
+      if (ep.relu) o = fmaxf(o, 0.f);
+      out[orow * ep.ldo + n] = o;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace egtr
 
 using namespace egtr;
+
+extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* const* a2_ptrs, float* const* out_ptrs,
+                                     const int* n_base, int groups, const int* lda, const float* w, int M, int N, int K,
+                                     const egtr_epilogue_t* ep, egtr_stream_t s) {
+  EGTR_CHECK(a_ptrs && out_ptrs && n_base && lda && w && ep, EGTR_ERR_ARG, "egtr_gemm_f32_grouped: null argument");
+  EGTR_CHECK(groups >= 1 && groups <= 16 && M > 0 && M <= 16 * 65535 && N > 0 && K > 0 && K % 32 == 0, EGTR_ERR_ARG,
+             "egtr_gemm_f32_grouped: bad shape (groups=%d M=%d N=%d K=%d; K %% 32 == 0)", groups, M, N, K);
+  EGTR_CHECK(groups == 1 || (ep->res == nullptr && ep->rows_per_b == 0), EGTR_ERR_ARG, "egtr_gemm_f32_grouped: no residual / remap with groups");
+  SkinnyGroups gt = {};
+  for (int g = 0; g < groups; ++g) {
+    EGTR_CHECK(a_ptrs[g] && out_ptrs[g] && lda[g] % 4 == 0 && lda[g] >= K, EGTR_ERR_ARG, "egtr_gemm_f32_grouped: group %d", g);
+    gt.a[g] = a_ptrs[g];
+    gt.a2[g] = a2_ptrs ? a2_ptrs[g] : nullptr;
+    gt.out[g] = out_ptrs[g];
+    gt.n_base[g] = n_base[g];
+    gt.lda[g] = lda[g];
+  }
+  dim3 grid(cdiv(N, 64), cdiv(M, 16), groups);
+  gemm_skinny_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
 
 extern "C" int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N, int K, const egtr_epilogue_t* ep,
                              egtr_stream_t s) {

@@ -23,6 +23,7 @@ from . import _lib
 from ._lib import ASrc, Epilogue, call
 
 RESNET_BLOCKS = (3, 4, 6, 3)
+SKINNY_M = 512  # GEMMs with at most this many rows take the fp32 skinny kernel (decoder, per-query relation tensors)
 
 
 def _ptr(t: Optional[torch.Tensor], col: int = 0) -> Optional[int]:
@@ -289,6 +290,11 @@ class Engine:
         ep.rows_per_b, ep.bstride, ep.off = remap if remap else (0, 0, 0)
         if gemm_backend() == "simt":
             call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
+        elif conv is None and M <= SKINNY_M and lin.K % 32 == 0:
+            # a few hundred rows: latency-bound -> many small fp32 CTAs beat 128-row tensor-core tiles
+            one = (C.c_void_p * 1)
+            call("egtr_gemm_f32_grouped", one(src.a), one(src.a2), one(ep.out), (C.c_int * 1)(0), 1, (C.c_int * 1)(src.lda),
+                 _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
         else:
             call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
 
@@ -308,6 +314,9 @@ class Engine:
                 src.a, src.a2, src.mode, src.lda = ap[g], a2p[g], 0, lda[g]
                 e2.bias, e2.out, e2.ldo, e2.ldr, e2.relu = _ptr(st.b, g * st.Npad), op[g], ldo, ldo, int(relu)
                 call("egtr_gemm_f32", C.byref(src), _ptr(st.w, g * st.Npad * st.K), M, st.N, st.K, C.byref(e2), _stream())
+            return
+        if M <= SKINNY_M and st.K % 32 == 0:
+            call("egtr_gemm_f32_grouped", ap, a2p, op, st.n_base, G, ldap, _ptr(st.w), M, st.N, st.K, C.byref(ep), _stream())
             return
         call("egtr_gemm_sbf16_grouped", ap, a2p, op, st.n_base, G, ldap, _ptr(st.planes), st.plane_rows, M, st.N, st.Npad, st.K,
              C.byref(ep), _stream())

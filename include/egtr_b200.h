@@ -91,6 +91,14 @@ int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* const* a2_p
 int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N, int K,
                   const egtr_epilogue_t* ep, egtr_stream_t s);
 
+/* Few-hundred-row GEMMs (decoder queries, per-query relation tensors): latency-bound, so many small fp32
+ * CUDA-core CTAs instead of 128-row tensor-core tiles.  Same grouped contract as above with fp32 weights
+ * w [rows,K] (group g uses rows n_base[g] .. n_base[g]+N); groups == 1 additionally allows ep->res and the
+ * row remap.  K % 32 == 0. */
+int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* const* a2_ptrs, float* const* out_ptrs,
+                          const int* n_base, int groups, const int* lda, const float* w, int M, int N, int K,
+                          const egtr_epilogue_t* ep, egtr_stream_t s);
+
 /* ---------------------------------------------------------------- MSDeformAttn ----------- */
 /* Drop-in for ms_deform_attn_forward: value [B,S,M,D], spatial_shapes [L,2] int64 (device),
  * level_start_index [L] int64 (device), sampling_loc [B,Lq,M,L,P,2], attn_weight [B,Lq,M,L,P]

@@ -66,13 +66,32 @@ def test_gemm_plain(cuda, backend, M, N, K):
     assert relerr(out2, ref2) < tol
 
 
-def test_gemm_grouped_launch(cuda):
-    """14 relation-style groups (N=513, mixed row strides) and the decoder's q|k|v triple in one launch each."""
+@pytest.mark.parametrize("M,N,K", [(200, 256, 256), (200, 1024, 256), (200, 256, 1024), (300, 150, 256), (7, 513, 256), (512, 601, 256)])
+def test_gemm_skinny_f32(cuda, M, N, K):
+    from egtr_b200 import _lib
+    from egtr_b200._lib import Epilogue
+    g = torch.Generator().manual_seed(M + N + K)
+    a, a2 = torch.randn(M, K, generator=g).to(cuda), torch.randn(M, K, generator=g).to(cuda)
+    w, b = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda), torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    ep = Epilogue()
+    ep.bias, ep.res, ep.out, ep.ldo, ep.ldr, ep.relu = b.data_ptr(), res.data_ptr(), out.data_ptr(), N, N, 1
+    one = (C.c_void_p * 1)
+    _lib.call("egtr_gemm_f32_grouped", one(a.data_ptr()), one(a2.data_ptr()), one(out.data_ptr()), (C.c_int * 1)(0), 1, (C.c_int * 1)(K),
+              w.data_ptr(), M, N, K, C.byref(ep), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = ((a.double() + a2.double()) @ w.double().t() + b.double() + res.double()).relu()
+    assert relerr(out, want) < 2e-6 * max(1.0, (K / 256) ** 0.5)
+
+
+@pytest.mark.parametrize("M", [200, 700])  # 200 rows -> skinny fp32 kernel, 700 rows -> tcgen05 grouped launch
+def test_gemm_grouped_launch(cuda, M):
+    """Relation-style groups (N=513, mixed row strides) and the decoder's q|k|v triple in one launch each."""
     from egtr_b200.config import workload_config
     from egtr_b200.engine import Engine, LinStack
     import types
     g = torch.Generator().manual_seed(21)
-    M = 200
     eng = types.SimpleNamespace()
     bufs = [torch.randn(M, 768, generator=g).to(cuda) for _ in range(3)] + [torch.randn(M, 256, generator=g).to(cuda)]
     ws = [torch.randn(513, 256, generator=g) / 16 for _ in range(6)]
