@@ -90,56 +90,82 @@ struct SkinnyGroups {
   int lda[16];
 };
 
+constexpr int SK_TM = 16, SK_TN = 64, SK_KC = 256, SK_LD = SK_KC + 4;  // +4 floats: conflict-free float4 rows
+constexpr int SK_STAGE_FLOATS = (2 * SK_TM + SK_TN) * SK_LD;              // A, A2 and W tiles of one K chunk
+constexpr int SK_SMEM_BYTES = 2 * SK_STAGE_FLOATS * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA = 16 x 64 outputs.  A whole 256-wide K chunk of both operands is fetched with cp.async in one burst
+// (40-48 sixteen-byte requests per thread in flight), so a K = 256 GEMM pays global-memory latency once;
+// longer K double-buffers chunks.
 __global__ void __launch_bounds__(128)
 gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
-  __shared__ float As[16][33];
-  __shared__ float Ws[64][33];
+  extern __shared__ __align__(16) float sk_smem[];
   const int g = blockIdx.z;
   const float* __restrict__ A = gt.a[g];
   const float* __restrict__ A2 = gt.a2[g];
   const int lda = gt.lda[g];
   const float* __restrict__ Wg = w + (long long)gt.n_base[g] * K;
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 64;
-  const int r = tid >> 3, c8 = tid & 7;          // compute mapping: row r, columns c8 + 8*j (conflict-free smem rows)
-  const int lr = tid >> 3, lq = tid & 7;         // loader mapping: A row lr, float4 lq of the 32-chunk
-  const bool a_ok = (m0 + lr) < M;
-  float4 an = make_float4(0.f, 0.f, 0.f, 0.f), wn[4];
-  auto load = [&](int k0) {
-    an = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a_ok) {
-      an = __ldg((const float4*)(A + (long long)(m0 + lr) * lda + k0) + lq);
+  const int m0 = blockIdx.y * SK_TM, n0 = blockIdx.x * SK_TN;
+  const int r = tid >> 3, c8 = tid & 7;  // compute mapping: row r, columns c8 + 8*j
+
+  auto issue = [&](int k0, int buf) {
+    float* As = sk_smem + buf * SK_STAGE_FLOATS;
+    float* A2s = As + SK_TM * SK_LD;
+    float* Ws = A2s + SK_TM * SK_LD;
+    const int kc = min(SK_KC, K - k0) >> 2;  // float4 per row in this chunk
+    for (int i = tid; i < SK_TM * (SK_KC / 4); i += 128) {
+      const int row = i / (SK_KC / 4), q = i - row * (SK_KC / 4);
+      const bool ok = (m0 + row) < M && q < kc;
+      float* d = As + row * SK_LD + q * 4;
+      if (ok) cp_async16(d, A + (long long)(m0 + row) * lda + k0 + q * 4);
+      else *(float4*)d = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A2) {
-        const float4 p = __ldg((const float4*)(A2 + (long long)(m0 + lr) * lda + k0) + lq);
-        an.x += p.x; an.y += p.y; an.z += p.z; an.w += p.w;
+        float* d2 = A2s + row * SK_LD + q * 4;
+        if (ok) cp_async16(d2, A2 + (long long)(m0 + row) * lda + k0 + q * 4);
+        else *(float4*)d2 = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int wr = n0 + i * 16 + lr;
-      wn[i] = (wr < N) ? __ldg((const float4*)(Wg + (long long)wr * K + k0) + lq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < SK_TN * (SK_KC / 4); i += 128) {
+      const int row = i / (SK_KC / 4), q = i - row * (SK_KC / 4);
+      float* d = Ws + row * SK_LD + q * 4;
+      if ((n0 + row) < N && q < kc) cp_async16(d, Wg + (long long)(n0 + row) * K + k0 + q * 4);
+      else *(float4*)d = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    cp_async_commit();
   };
+
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  load(0);
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  const int chunks = (K + SK_KC - 1) / SK_KC;
+  issue(0, 0);
+  for (int c = 0; c < chunks; ++c) {
+    if (c + 1 < chunks) { issue((c + 1) * SK_KC, (c + 1) & 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
-    As[lr][lq * 4 + 0] = an.x; As[lr][lq * 4 + 1] = an.y; As[lr][lq * 4 + 2] = an.z; As[lr][lq * 4 + 3] = an.w;
+    const float* As = sk_smem + (c & 1) * SK_STAGE_FLOATS + r * SK_LD;
+    const float* A2s = As + SK_TM * SK_LD;
+    const float* Ws = sk_smem + (c & 1) * SK_STAGE_FLOATS + 2 * SK_TM * SK_LD + c8 * SK_LD;
+#pragma unroll 4
+    for (int k = 0; k < SK_KC; k += 4) {
+      float4 a = *(const float4*)(As + k);
+      if (A2) { const float4 p = *(const float4*)(A2s + k); a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w; }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float* d = &Ws[i * 16 + lr][lq * 4];
-      d[0] = wn[i].x; d[1] = wn[i].y; d[2] = wn[i].z; d[3] = wn[i].w;
+      for (int j = 0; j < 8; ++j) {
+        const float4 wv = *(const float4*)(Ws + j * 8 * SK_LD + k);
+        acc[j] = fmaf(a.x, wv.x, acc[j]); acc[j] = fmaf(a.y, wv.y, acc[j]);
+        acc[j] = fmaf(a.z, wv.z, acc[j]); acc[j] = fmaf(a.w, wv.w, acc[j]);
+      }
     }
-    __syncthreads();
-    if (k0 + 32 < K) load(k0 + 32);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float a = As[r][k];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, Ws[c8 + 8 * j][k], acc[j]);
-    }
+    __syncthreads();  // everyone is done with this buffer before the chunk after next overwrites it
   }
   const int m = m0 + r;
   if (m >= M) return;
@@ -167,8 +193,8 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
                                      const int* n_base, int groups, const int* lda, const float* w, int M, int N, int K,
                                      const egtr_epilogue_t* ep, egtr_stream_t s) {
   EGTR_CHECK(a_ptrs && out_ptrs && n_base && lda && w && ep, EGTR_ERR_ARG, "egtr_gemm_f32_grouped: null argument");
-  EGTR_CHECK(groups >= 1 && groups <= 16 && M > 0 && M <= 16 * 65535 && N > 0 && K > 0 && K % 32 == 0, EGTR_ERR_ARG,
-             "egtr_gemm_f32_grouped: bad shape (groups=%d M=%d N=%d K=%d; K %% 32 == 0)", groups, M, N, K);
+  EGTR_CHECK(groups >= 1 && groups <= 16 && M > 0 && M <= 16 * 65535 && N > 0 && K > 0 && K % 4 == 0, EGTR_ERR_ARG,
+             "egtr_gemm_f32_grouped: bad shape (groups=%d M=%d N=%d K=%d; K %% 4 == 0)", groups, M, N, K);
   EGTR_CHECK(groups == 1 || (ep->res == nullptr && ep->rows_per_b == 0), EGTR_ERR_ARG, "egtr_gemm_f32_grouped: no residual / remap with groups");
   SkinnyGroups gt = {};
   for (int g = 0; g < groups; ++g) {
@@ -179,8 +205,13 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
     gt.n_base[g] = n_base[g];
     gt.lda[g] = lda[g];
   }
-  dim3 grid(cdiv(N, 64), cdiv(M, 16), groups);
-  gemm_skinny_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
+  static bool attr = false;
+  if (!attr) {
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    attr = true;
+  }
+  dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), groups);
+  gemm_skinny_kernel<<<grid, 128, SK_SMEM_BYTES, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
