@@ -25,7 +25,7 @@ class ASrc(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int),
                 ("ldr", C.c_int), ("relu", C.c_int), ("rows_per_b", C.c_int), ("bstride", C.c_int),
-                ("off", C.c_int)]
+                ("off", C.c_int), ("row_keep", C.c_void_p)]
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong

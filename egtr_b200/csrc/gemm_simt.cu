@@ -71,6 +71,7 @@ gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K
       if (ep.bias) o += __ldg(ep.bias + n);
       if (ep.res) o += ep.res[orow * ep.ldr + n];
       if (ep.relu) o = fmaxf(o, 0.f);
+      if (ep.row_keep && !ep.row_keep[orow]) o = 0.f;
       ep.out[orow * ep.ldo + n] = o;
     }
   }
@@ -101,10 +102,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One CTA = 16 x 64 outputs.  A whole 256-wide K chunk of both operands is fetched with cp.async in one burst
+// One CTA (256 threads) = 16 x 64 outputs, 4 per thread.  A whole 256-wide K chunk of both operands is fetched with cp.async in one burst
 // (40-48 sixteen-byte requests per thread in flight), so a K = 256 GEMM pays global-memory latency once;
 // longer K double-buffers chunks.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
   extern __shared__ __align__(16) float sk_smem[];
   const int g = blockIdx.z;
@@ -114,14 +115,14 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
   const float* __restrict__ Wg = w + (long long)gt.n_base[g] * K;
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * SK_TM, n0 = blockIdx.x * SK_TN;
-  const int r = tid >> 3, c8 = tid & 7;  // compute mapping: row r, columns c8 + 8*j
+  const int r = tid >> 4, c16 = tid & 15;  // compute mapping: row r, columns c16 + 16*j (j < 4)
 
   auto issue = [&](int k0, int buf) {
     float* As = sk_smem + buf * SK_STAGE_FLOATS;
     float* A2s = As + SK_TM * SK_LD;
     float* Ws = A2s + SK_TM * SK_LD;
     const int kc = min(SK_KC, K - k0) >> 2;  // float4 per row in this chunk
-    for (int i = tid; i < SK_TM * (SK_KC / 4); i += 128) {
+    for (int i = tid; i < SK_TM * (SK_KC / 4); i += 256) {
       const int row = i / (SK_KC / 4), q = i - row * (SK_KC / 4);
       const bool ok = (m0 + row) < M && q < kc;
       float* d = As + row * SK_LD + q * 4;
@@ -133,7 +134,7 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
         else *(float4*)d2 = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    for (int i = tid; i < SK_TN * (SK_KC / 4); i += 128) {
+    for (int i = tid; i < SK_TN * (SK_KC / 4); i += 256) {
       const int row = i / (SK_KC / 4), q = i - row * (SK_KC / 4);
       float* d = Ws + row * SK_LD + q * 4;
       if ((n0 + row) < N && q < kc) cp_async16(d, Wg + (long long)(n0 + row) * K + k0 + q * 4);
@@ -142,9 +143,9 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
     cp_async_commit();
   };
 
-  float acc[8];
+  float acc[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 4; ++j) acc[j] = 0.f;
   const int chunks = (K + SK_KC - 1) / SK_KC;
   issue(0, 0);
   for (int c = 0; c < chunks; ++c) {
@@ -153,14 +154,14 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
     __syncthreads();
     const float* As = sk_smem + (c & 1) * SK_STAGE_FLOATS + r * SK_LD;
     const float* A2s = As + SK_TM * SK_LD;
-    const float* Ws = sk_smem + (c & 1) * SK_STAGE_FLOATS + 2 * SK_TM * SK_LD + c8 * SK_LD;
+    const float* Ws = sk_smem + (c & 1) * SK_STAGE_FLOATS + 2 * SK_TM * SK_LD + c16 * SK_LD;
 #pragma unroll 4
     for (int k = 0; k < SK_KC; k += 4) {
       float4 a = *(const float4*)(As + k);
       if (A2) { const float4 p = *(const float4*)(A2s + k); a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 wv = *(const float4*)(Ws + j * 8 * SK_LD + k);
+      for (int j = 0; j < 4; ++j) {
+        const float4 wv = *(const float4*)(Ws + j * 16 * SK_LD + k);
         acc[j] = fmaf(a.x, wv.x, acc[j]); acc[j] = fmaf(a.y, wv.y, acc[j]);
         acc[j] = fmaf(a.z, wv.z, acc[j]); acc[j] = fmaf(a.w, wv.w, acc[j]);
       }
@@ -172,13 +173,14 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
   const long long orow = out_row(ep, m);
   float* __restrict__ out = gt.out[g];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = n0 + c8 + 8 * j;
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + c16 + 16 * j;
     if (n < N) {
       float o = acc[j];
       if (ep.bias) o += __ldg(ep.bias + gt.n_base[g] + n);
       if (ep.res) o += ep.res[orow * ep.ldr + n];
       if (ep.relu) o = fmaxf(o, 0.f);
+      if (ep.row_keep && !ep.row_keep[orow]) o = 0.f;
       out[orow * ep.ldo + n] = o;
     }
   }
@@ -211,7 +213,7 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
     attr = true;
   }
   dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), groups);
-  gemm_skinny_kernel<<<grid, 128, SK_SMEM_BYTES, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
+  gemm_skinny_kernel<<<grid, 256, SK_SMEM_BYTES, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

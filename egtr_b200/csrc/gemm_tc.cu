@@ -303,6 +303,17 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       const int g = tg / tiles_per_group, t = tg - g * tiles_per_group;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const int n0 = (t % n_tiles) * BLOCK_N;
+      if (ep.res != nullptr && splits == 1) {
+        // pull this tile's residual rows into L2 while the MMAs are still running: the epilogue's own loads
+        // (8 x 16 B per lane per chunk) are too few bytes in flight to stream them from HBM at speed
+        const long long mr = (long long)(t / n_tiles) * BLOCK_M + warp * 32 + lane;
+        if (mr < M) {
+          const float* rp = ep.res + out_row(ep, mr) * ep.ldr + n0;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 32; ++j)
+            if (n0 + j * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 32));
+        }
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
       ptx::tc_fence_after();
       // Accumulator rows live one per thread in TMEM (lane = row).  Each 32x32 chunk is transposed through a
@@ -316,6 +327,14 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       for (int i = 0; i < 8; ++i) {
         const long long mr = m_base + i * 4 + rsub;
         orow[i] = mr < M ? (splits > 1 ? (long long)sp * M + mr : out_row(ep, mr)) : -1;
+      }
+      // value.masked_fill(~mask, 0) of deformable_detr.py:1050-1052 folded into the store: masked rows write zeros
+      uint32_t keep_bits = 0xffu;
+      if (ep.row_keep != nullptr && splits == 1) {
+        keep_bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (orow[i] >= 0 && ep.row_keep[orow[i]]) keep_bits |= 1u << i;
       }
       float* __restrict__ obase = splits > 1 ? partial : tab.out[g];
       const int ldo = splits > 1 ? Npad : ep.ldo;
@@ -359,6 +378,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           float4 o = *(const float4*)(stg + (i * 4 + rsub) * STG_LD + cc);
           o.x += b4.x + rs[i].x; o.y += b4.y + rs[i].y; o.z += b4.z + rs[i].z; o.w += b4.w + rs[i].w;
           if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (!((keep_bits >> i) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);
           float* op = obase + orow[i] * ldo + n;
           if (full4) *(float4*)op = o;
           else { if (n < ncols) op[0] = o.x; if (n + 1 < ncols) op[1] = o.y; if (n + 2 < ncols) op[2] = o.z; if (n + 3 < ncols) op[3] = o.w; }
@@ -464,6 +484,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
       if (ep.bias) v += __ldg(ep.bias + n + j);
       if (ep.res) v += ep.res[orow * ep.ldr + n + j];
       if (ep.relu) v = fmaxf(v, 0.f);
+      if (ep.row_keep && !ep.row_keep[orow]) v = 0.f;
       ep.out[orow * ep.ldo + n + j] = v;
     }
   }

@@ -121,24 +121,38 @@ groupnorm_partial_kernel(const float* __restrict__ x, int rows_per_b, int bstrid
     p[1] = q;
   }
 }
-__global__ void __launch_bounds__(256)
-groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int off, const double* __restrict__ part,
-                       const float* __restrict__ gamma, const float* __restrict__ beta) {
-  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  __shared__ float mean_s[32], rstd_s[32];
-  if (threadIdx.x < 32) {
-    double a = 0.0, q = 0.0;
-    for (int k = 0; k < nchunks; ++k) {
-      const double* p = part + (((long long)b * nchunks + k) * 32 + threadIdx.x) * 2;
-      a += p[0];
-      q += p[1];
-    }
+// one warp per (image, group): fold the chunk partials into mean / rstd (float2 at the head of the scratch area)
+__global__ void __launch_bounds__(32)
+groupnorm_finalize_kernel(const double* __restrict__ part, int nchunks, int rows_per_b, float2* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  double a = 0.0, q = 0.0;
+  for (int k = lane; k < nchunks; k += 32) {
+    const double* p = part + (((long long)b * nchunks + k) * 32 + g) * 2;
+    a += p[0];
+    q += p[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
     const double n = (double)rows_per_b * 8.0;
     const double mean = a / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    mean_s[threadIdx.x] = (float)mean;
-    rstd_s[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+    stats[b * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+  }
+}
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int off, const float2* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  __shared__ float mean_s[32], rstd_s[32];
+  if (threadIdx.x < 32) {
+    const float2 st = stats[b * 32 + threadIdx.x];
+    mean_s[threadIdx.x] = st.x;
+    rstd_s[threadIdx.x] = st.y;
   }
   __syncthreads();
   const int c = threadIdx.x & 63, r8 = threadIdx.x >> 6;
@@ -155,6 +169,7 @@ groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int o
 }
 
 // ------------------------------------------------------------------ masks, cumulative sums, valid ratios
+constexpr int LEVEL_MASK_SMEM = 64 * 1024;
 struct GeoLevels {
   int L;
   int h[8], w[8], start[8];
@@ -170,24 +185,30 @@ level_masks_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLeve
   float* xc = xcum + (long long)b * S + lv.start[l];
   const int64_t* pm = pixel_mask + (long long)b * H * W;
   const float sy = (float)H / (float)h, sx = (float)W / (float)w;  // legacy 'nearest': src = floor(dst * in/out)
+  // the level's mask is staged in shared memory when it fits, so the serial scans below run at smem latency
+  extern __shared__ uint8_t mk_s[];
+  const bool in_smem = (h * w) <= LEVEL_MASK_SMEM;
+  const uint8_t* msrc = in_smem ? mk_s : mk;
   for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
     const int yy = min((int)floorf((float)y * sy), H - 1), xx = min((int)floorf((float)x * sx), W - 1);
-    mk[i] = pm[(long long)yy * W + xx] != 0;
+    const uint8_t v = pm[(long long)yy * W + xx] != 0;
+    mk[i] = v;
+    if (in_smem) mk_s[i] = v;
   }
   __syncthreads();
   for (int x = threadIdx.x; x < w; x += blockDim.x) {  // y_embed = cumsum over rows (deformable_detr.py:853)
     float c = 0.f;
-    for (int y = 0; y < h; ++y) { c += (float)mk[y * w + x]; yc[y * w + x] = c; }
+    for (int y = 0; y < h; ++y) { c += (float)msrc[y * w + x]; yc[y * w + x] = c; }
   }
   for (int y = threadIdx.x; y < h; y += blockDim.x) {  // x_embed = cumsum over columns (854)
     float c = 0.f;
-    for (int x = 0; x < w; ++x) { c += (float)mk[y * w + x]; xc[y * w + x] = c; }
+    for (int x = 0; x < w; ++x) { c += (float)msrc[y * w + x]; xc[y * w + x] = c; }
   }
   if (threadIdx.x == 0) {  // get_valid_ratio (2064-2073): first column / first row
     int vh = 0, vw = 0;
-    for (int y = 0; y < h; ++y) vh += mk[y * w];
-    for (int x = 0; x < w; ++x) vw += mk[x];
+    for (int y = 0; y < h; ++y) vh += msrc[y * w];
+    for (int x = 0; x < w; ++x) vw += msrc[x];
     valid_ratios[((long long)b * lv.L + l) * 2 + 0] = (float)vw / (float)w;
     valid_ratios[((long long)b * lv.L + l) * 2 + 1] = (float)vh / (float)h;
   }
@@ -347,8 +368,12 @@ extern "C" int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, 
   EGTR_CHECK(x && gamma && beta && scratch && B > 0 && rows_per_b > 0, EGTR_ERR_ARG, "egtr_groupnorm_f32: bad arguments");
   EGTR_CHECK(C == 256 && groups == 32, EGTR_ERR_UNSUPPORTED, "egtr_groupnorm_f32: built for GroupNorm(32, 256)");
   dim3 grid(cdiv(rows_per_b, GN_ROWS), B);
-  groupnorm_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, scratch);
-  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, scratch, gamma, beta);
+  double* part = scratch + B * 32;  // first B*32 doubles hold the float2 (mean, rstd) table
+  float2* stats = (float2*)scratch;
+  groupnorm_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, part);
+  groupnorm_finalize_kernel<<<dim3(32, B), 32, 0, (cudaStream_t)s>>>(part, grid.x, rows_per_b, stats);
+  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, stats, gamma, beta);
+  count_launch();
   count_launch();
   count_launch();
   EGTR_CUDA(cudaGetLastError());
@@ -356,7 +381,7 @@ extern "C" int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, 
 }
 
 extern "C" long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b) {
-  return (long long)B * cdiv(rows_per_b, GN_ROWS) * 32 * 2;
+  return (long long)B * 32 + (long long)B * cdiv(rows_per_b, GN_ROWS) * 32 * 2;
 }
 
 extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H, int W, const int* shapes_hw, int L,
@@ -376,7 +401,12 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
   }
   float* ycum = scratch;
   float* xcum = scratch + (long long)B * S;
-  level_masks_kernel<<<dim3(L, B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat, ycum, xcum, valid_ratios);
+  static bool attr = false;
+  if (!attr) {
+    EGTR_CUDA(cudaFuncSetAttribute(level_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_MASK_SMEM));
+    attr = true;
+  }
+  level_masks_kernel<<<dim3(L, B), 256, LEVEL_MASK_SMEM, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat, ycum, xcum, valid_ratios);
   pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
   count_launch();
   count_launch();

@@ -23,7 +23,12 @@ from . import _lib
 from ._lib import ASrc, Epilogue, call
 
 RESNET_BLOCKS = (3, 4, 6, 3)
-SKINNY_M = 512  # GEMMs with at most this many rows take the fp32 skinny kernel (decoder, per-query relation tensors)
+SKINNY_M = 512  # GEMMs with at most this many rows may take the fp32 skinny kernel (decoder, detection heads)
+
+
+def _skinny(M: int, N: int, groups: int) -> bool:
+    """Latency-bound shapes: few rows AND few enough 16x64 tiles to fit about two waves of the 148 SMs."""
+    return M <= SKINNY_M and groups * ((M + 15) // 16) * ((N + 63) // 64) <= 2 * 148
 
 
 def _ptr(t: Optional[torch.Tensor], col: int = 0) -> Optional[int]:
@@ -273,7 +278,7 @@ class Engine:
     def gemm(self, lin: Lin, M: int, out: torch.Tensor, *, a: Optional[torch.Tensor] = None, lda: Optional[int] = None,
              a_col: int = 0, a2: Optional[torch.Tensor] = None, conv: Optional[dict] = None, relu: bool = False,
              res: Optional[torch.Tensor] = None, ldr: int = 0, ldo: Optional[int] = None, out_col: int = 0,
-             remap: Optional[Tuple[int, int, int]] = None):
+             remap: Optional[Tuple[int, int, int]] = None, row_keep: Optional[torch.Tensor] = None):
         src = ASrc()
         if conv is None:
             src.a, src.a2, src.mode = _ptr(a, a_col), _ptr(a2, a_col), 0
@@ -288,9 +293,10 @@ class Engine:
         ep.ldr = ldr if ldr else ep.ldo
         ep.relu = int(relu)
         ep.rows_per_b, ep.bstride, ep.off = remap if remap else (0, 0, 0)
+        ep.row_keep = _ptr(row_keep)
         if gemm_backend() == "simt":
             call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
-        elif conv is None and M <= SKINNY_M and lin.K % 32 == 0:
+        elif conv is None and _skinny(M, lin.N, 1):
             # a few hundred rows: latency-bound -> many small fp32 CTAs beat 128-row tensor-core tiles
             one = (C.c_void_p * 1)
             call("egtr_gemm_f32_grouped", one(src.a), one(src.a2), one(ep.out), (C.c_int * 1)(0), 1, (C.c_int * 1)(src.lda),
@@ -315,7 +321,7 @@ class Engine:
                 e2.bias, e2.out, e2.ldo, e2.ldr, e2.relu = _ptr(st.b, g * st.Npad), op[g], ldo, ldo, int(relu)
                 call("egtr_gemm_f32", C.byref(src), _ptr(st.w, g * st.Npad * st.K), M, st.N, st.K, C.byref(e2), _stream())
             return
-        if M <= SKINNY_M and st.K % 32 == 0:
+        if _skinny(M, st.N, G):
             call("egtr_gemm_f32_grouped", ap, a2p, op, st.n_base, G, ldap, _ptr(st.w), M, st.N, st.K, C.byref(ep), _stream())
             return
         call("egtr_gemm_sbf16_grouped", ap, a2p, op, st.n_base, G, ldap, _ptr(st.planes), st.plane_rows, M, st.N, st.Npad, st.K,
@@ -468,8 +474,7 @@ class Engine:
         vr = ws["valid_ratios"]
         for i, lay in enumerate(self.enc):
             self.gemm(lay["offaw"], M, offaw, a=xa, a2=pos, lda=256)
-            self.gemm(lay["value"], M, value, a=xa, lda=256)
-            call("egtr_mask_rows_f32", _ptr(value), 256, 256, _ptr(ws["mask_flat"]), M, st)
+            self.gemm(lay["value"], M, value, a=xa, lda=256, row_keep=ws["mask_flat"])
             with self.span("msda_enc"):
                 call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
                      B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
@@ -488,8 +493,7 @@ class Engine:
         # ---- decoder (deformable_detr.py:1390-1489, 1774-1968)
         nl = cfg.decoder_layers
         dv = ws["dec_value"]
-        self.gemm(self.dec_value, M, dv, a=enc, lda=256)
-        call("egtr_mask_rows_f32", _ptr(dv), 256 * nl, 256 * nl, _ptr(ws["mask_flat"]), M, st)
+        self.gemm(self.dec_value, M, dv, a=enc, lda=256, row_keep=ws["mask_flat"])
         call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
              None, 0, 0, _ptr(ws["ref"]), 2, st)
         Md = B * N

@@ -59,8 +59,9 @@ typedef struct {
   int H, W, C, OH, OW, KH, KW, stride, pad;
 } egtr_asrc_t;
 
-/* out[orow(m)*ldo + n] = act(acc + bias[n] + res[orow(m)*ldr + n]);
- * orow(m) = (m / rows_per_b)*bstride + off + m % rows_per_b when rows_per_b > 0, else m. */
+/* out[orow(m)*ldo + n] = keep(act(acc + bias[n] + res[orow(m)*ldr + n]));
+ * orow(m) = (m / rows_per_b)*bstride + off + m % rows_per_b when rows_per_b > 0, else m;
+ * keep(x) = row_keep[orow(m)] ? x : 0 when row_keep is non-null (value.masked_fill, deformable_detr.py:1050-1052). */
 typedef struct {
   const float* bias;
   const float* res;
@@ -68,6 +69,7 @@ typedef struct {
   int ldo, ldr;
   int relu;
   int rows_per_b, bstride, off;
+  const uint8_t* row_keep;
 } egtr_epilogue_t;
 
 /* fp32 weight [N,K] -> split-bf16 planes [2][Npad][K] (hi, lo; rows >= N zero). Npad % 64 == 0. */
