@@ -91,7 +91,7 @@ struct SkinnyGroups {
   int lda[16];
 };
 
-constexpr int SK_TM = 16, SK_TN = 64, SK_KC = 256, SK_LD = SK_KC + 4;  // +4 floats: conflict-free float4 rows
+constexpr int SK_TM = 16, SK_TN = 64, SK_KC = 128, SK_LD = SK_KC + 4;  // +4 floats: conflict-free float4 rows
 constexpr int SK_STAGE_FLOATS = (2 * SK_TM + SK_TN) * SK_LD;              // A, A2 and W tiles of one K chunk
 constexpr int SK_SMEM_BYTES = 2 * SK_STAGE_FLOATS * 4;
 
@@ -102,9 +102,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One CTA (256 threads) = 16 x 64 outputs, 4 per thread.  A whole 256-wide K chunk of both operands is fetched with cp.async in one burst
-// (40-48 sixteen-byte requests per thread in flight), so a K = 256 GEMM pays global-memory latency once;
-// longer K double-buffers chunks.
+// One CTA (256 threads) = 16 x 64 outputs, 4 per thread.  A whole 128-wide K chunk of both operands is fetched with
+// cp.async in one burst and the next chunk is already in flight while the current one is multiplied; 100 KB of smem
+// per CTA keeps two CTAs resident per SM.
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
   extern __shared__ __align__(16) float sk_smem[];

@@ -34,6 +34,16 @@ void count_launch();
 
 namespace {
 
+#ifdef EGTR_GEMM_PROF
+// dev-only cycle accounting per role (tools/gemm_bench.py --prof): [cta][slot]
+__device__ unsigned long long g_prof[148][16];
+#define PROF_T0(var) long long var = clock64()
+#define PROF_ADD(slot, var) do { if (lane == 0) g_prof_local[slot] += clock64() - (var); } while (0)
+#else
+#define PROF_T0(var)
+#define PROF_ADD(slot, var)
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
@@ -87,6 +97,10 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef EGTR_GEMM_PROF
+  long long g_prof_local[4] = {0, 0, 0, 0};
+  const long long prof_start = clock64();
+#endif
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = Npad / BLOCK_N;
   // work item = (output tile, K split): few-tile GEMMs with a long K (3x3 convs on C5, decoder FFN) are
@@ -123,7 +137,9 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         const int n0 = tab.n_base[g] + (t % n_tiles) * BLOCK_N;
         const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          PROF_T0(t_a);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 101);
+          PROF_ADD(0, t_a);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_TILE_BYTES);
           ptx::tma_load_2d(st + 2 * A_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
@@ -140,11 +156,15 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       const int sp = w % splits;
       const int kb_lo = sp * kb_per_split, kb_hi = min(k_blocks_all, kb_lo + kb_per_split);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      PROF_T0(t_b);
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, err, 102);
+      PROF_ADD(0, t_b);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        PROF_T0(t_c);
         ptx::mbar_wait(&full_bar[stage], phase, err, 103);
+        PROF_ADD(1, t_c);
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
@@ -175,6 +195,16 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     const int kc = lane & 15;   // which float4 of the 64-float run
     const int rsub = lane >> 4; // 0/1: two rows per warp-wide load
     RowSlot* rows = rows_all + grp * 128;
+    const uint32_t rows_s = ptx::smem_u32(rows);
+    auto ld_rowslot = [](uint32_t addr) {  // explicit 16-byte shared load of one RowSlot
+      uint32_t a, b, c, d;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+      RowSlot r;
+      r.base = (long long)(((unsigned long long)b << 32) | a);
+      r.iy0 = (int)c;
+      r.ix0 = (int)d;
+      return r;
+    };
     int seq = 0;  // k-blocks issued so far by this CTA (all work items)
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
       const int tg = w / splits, sp = w - tg * splits;
@@ -205,8 +235,8 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           ky = tap / src.KW;
           kx = tap - ky * src.KW;
         }
-        uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
-        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t a_hi_s = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t a_lo_s = a_hi_s + A_TILE_BYTES;
         // All global loads of a batch are issued back to back (predicated, no branches) before anything
         // consumes them, so the 16 (or 2 x 8 with the x+pos addend) 16-byte loads of a thread overlap
         // in the memory system; the stage's empty barrier is only waited for once they are in flight.
@@ -223,11 +253,12 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
           pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
           pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-          *(uint2*)(a_hi + o) = ph;
-          *(uint2*)(a_lo + o) = pl;
+          // explicit shared-space stores (the realigned dynamic-smem pointer is generic to the compiler)
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi_s + o), "r"(ph.x), "r"(ph.y) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo_s + o), "r"(pl.x), "r"(pl.y) : "memory");
         };
         auto row_off = [&](int i) -> long long {
-          const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+          const RowSlot rs = ld_rowslot(rows_s + (p * 32 + 2 * i + rsub) * 16);
           long long off = rs.base + k0;  // plain rows
           if (src.mode == 1) {
             const int iy = rs.iy0 + ky, ix = rs.ix0 + kx;
@@ -241,7 +272,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           float4 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+            const RowSlot rs = ld_rowslot(rows_s + (p * 32 + 2 * i + rsub) * 16);
             v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : zero4;
           }
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
@@ -255,7 +286,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           float4 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const RowSlot rs = rows[p * 32 + 2 * i + rsub];
+            const RowSlot rs = ld_rowslot(rows_s + (p * 32 + 2 * i + rsub) * 16);
             const long long off = (rs.base + (long long)(rs.iy0 + tky) * src.W + (rs.ix0 + tkx)) * 4;
             v[i] = (tap_ok && rs.base >= 0) ? __ldg((const float4*)(a_ptr + off)) : zero4;
           }
@@ -269,9 +300,13 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           float4 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
+          PROF_T0(t_d);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
+          PROF_ADD(0, t_d);
+          PROF_T0(t_e);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
+          PROF_ADD(1, t_e);
         } else {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -314,8 +349,11 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             if (n0 + j * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 32));
         }
       }
+      PROF_T0(t_f);
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 105);
+      PROF_ADD(0, t_f);
       ptx::tc_fence_after();
+      PROF_T0(t_g);
       // Accumulator rows live one per thread in TMEM (lane = row).  Each 32x32 chunk is transposed through a
       // padded smem tile so that global traffic is row-contiguous: 8 lanes x float4 cover 128 B of one output
       // row (4 rows per warp instruction) for the stores and for the residual loads alike.
@@ -342,52 +380,89 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       const float* __restrict__ bias = (splits > 1 || !ep.bias) ? nullptr : ep.bias + tab.n_base[g];
       const int relu = splits > 1 ? 0 : ep.relu;
       const int ncols = splits > 1 ? Npad : N;
+      const uint32_t stg_w = ptx::smem_u32(stg) + lane * (STG_LD * 4);               // this lane's row (TMEM order)
+      const uint32_t stg_r = ptx::smem_u32(stg) + (rsub * STG_LD + cc) * 4;           // this lane's float4 column (row order)
+      const bool aligned = ((ldo & 3) == 0) && (!rbase || (ep.ldr & 3) == 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         const int n = n0 + c0 + cc;  // first of this lane's 4 columns
-        const bool full4 = (n + 4 <= ncols) && ((ldo & 3) == 0) && (!rbase || (ep.ldr & 3) == 0);
-        float4 rs[8];
+        if (n0 + c0 >= ncols) break;  // whole chunk beyond N (padded weight rows)
+        const bool chunk_full = aligned && (n0 + c0 + 32 <= ncols);  // warp-uniform fast path
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) {
-          if (full4) b4 = __ldg((const float4*)(bias + n));
+          if (chunk_full) b4 = __ldg((const float4*)(bias + n));
           else { if (n < ncols) b4.x = __ldg(bias + n); if (n + 1 < ncols) b4.y = __ldg(bias + n + 1);
                  if (n + 2 < ncols) b4.z = __ldg(bias + n + 2); if (n + 3 < ncols) b4.w = __ldg(bias + n + 3); }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rbase && orow[i] >= 0) {
-            const float* rp = rbase + orow[i] * ep.ldr + n;
-            if (full4) rs[i] = *(const float4*)rp;
-            else { if (n < ncols) rs[i].x = rp[0]; if (n + 1 < ncols) rs[i].y = rp[1];
-                   if (n + 2 < ncols) rs[i].z = rp[2]; if (n + 3 < ncols) rs[i].w = rp[3]; }
-          }
-        }
         uint32_t r[32];
+        PROF_T0(t_h);
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BLOCK_N + c0, r);
         ptx::tmem_ld_wait();
+        PROF_ADD(2, t_h);
+        PROF_T0(t_i);
         __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *(float4*)(stg + lane * STG_LD + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + 16 * j), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
         __syncwarp();
+        float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (orow[i] < 0) continue;
-          float4 o = *(const float4*)(stg + (i * 4 + rsub) * STG_LD + cc);
-          o.x += b4.x + rs[i].x; o.y += b4.y + rs[i].y; o.z += b4.z + rs[i].z; o.w += b4.w + rs[i].w;
-          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (!((keep_bits >> i) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          float* op = obase + orow[i] * ldo + n;
-          if (full4) *(float4*)op = o;
-          else { if (n < ncols) op[0] = o.x; if (n + 1 < ncols) op[1] = o.y; if (n + 2 < ncols) op[2] = o.z; if (n + 3 < ncols) op[3] = o.w; }
+        for (int i = 0; i < 8; ++i)  // all eight row reads are issued together (no control flow in between)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w)
+                       : "r"(stg_r + i * 4 * STG_LD * 4) : "memory");
+        if (chunk_full) {
+          float4 rs[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rs[i] = (rbase && orow[i] >= 0) ? *(const float4*)(rbase + orow[i] * ep.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = o[i];
+            v.x += b4.x + rs[i].x; v.y += b4.y + rs[i].y; v.z += b4.z + rs[i].z; v.w += b4.w + rs[i].w;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (!((keep_bits >> i) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (orow[i] >= 0) *(float4*)(obase + orow[i] * ldo + n) = v;
+          }
+        } else {  // N tail or unaligned leading dimension: per-element, still fully unrolled (registers only)
+          auto put = [&](long long row, int col, float v, float bv, bool keep) {
+            if (col < ncols) {
+              v += bv;
+              if (rbase) v += rbase[row * ep.ldr + col];
+              if (relu) v = fmaxf(v, 0.f);
+              obase[row * ldo + col] = keep ? v : 0.f;
+            }
+          };
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (orow[i] >= 0) {
+              const bool keep = (keep_bits >> i) & 1u;
+              put(orow[i], n, o[i].x, b4.x, keep);
+              put(orow[i], n + 1, o[i].y, b4.y, keep);
+              put(orow[i], n + 2, o[i].z, b4.z, keep);
+              put(orow[i], n + 3, o[i].w, b4.w, keep);
+            }
+          }
         }
+        PROF_ADD(3, t_i);
       }
+      PROF_ADD(1, t_g);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
   }
+#ifdef EGTR_GEMM_PROF
+  if (lane == 0 && blockIdx.x < 148) {
+    // slots: role*4 + {0: first wait, 1: second counter, 2: role total}; roles: 0 TMA(warp4) 1 MMA(warp5) 2 producer(warp6) 3 epilogue(warp0)
+    const int role = warp == 4 ? 0 : warp == 5 ? 1 : warp == 6 ? 2 : warp == 0 ? 3 : -1;
+    if (role >= 0) {
+      g_prof[blockIdx.x][role * 4 + 0] = g_prof_local[0];
+      g_prof[blockIdx.x][role * 4 + 1] = g_prof_local[1];
+      g_prof[blockIdx.x][role * 4 + 2] = clock64() - prof_start;
+      if (role == 3) { g_prof[blockIdx.x][14] = g_prof_local[2]; g_prof[blockIdx.x][15] = g_prof_local[3]; }
+    }
+  }
+#endif
 
   ptx::tc_fence_before();
   __syncthreads();
@@ -628,3 +703,10 @@ extern "C" int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* 
   if (Npad % 128 == 0) return launch<128>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
   return launch<64>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
 }
+
+#ifdef EGTR_GEMM_PROF
+extern "C" int egtr_debug_gemm_prof(unsigned long long* host_out) {
+  EGTR_CUDA(cudaMemcpyFromSymbol(host_out, egtr::g_prof, sizeof(unsigned long long) * 148 * 16));
+  return EGTR_OK;
+}
+#endif

@@ -174,28 +174,34 @@ struct GeoLevels {
   int L;
   int h[8], w[8], start[8];
 };
-// one CTA per (level, image): nearest-neighbour mask, then column/row inclusive scans.
+// nearest-neighbour level masks: one thread per token (legacy 'nearest': src = floor(dst * in/out), fp32 scale)
 __global__ void __launch_bounds__(256)
-level_masks_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLevels lv, int S, uint8_t* __restrict__ mask_flat,
-                   float* __restrict__ ycum, float* __restrict__ xcum, float* __restrict__ valid_ratios) {
+level_mask_gather_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLevels lv, int S, uint8_t* __restrict__ mask_flat) {
+  const int tok = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (tok >= S) return;
+  int l = 0;
+  while (l + 1 < lv.L && tok >= lv.start[l + 1]) ++l;
+  const int h = lv.h[l], w = lv.w[l];
+  const int i = tok - lv.start[l];
+  const int y = i / w, x = i - y * w;
+  const float sy = (float)H / (float)h, sx = (float)W / (float)w;
+  const int yy = min((int)floorf((float)y * sy), H - 1), xx = min((int)floorf((float)x * sx), W - 1);
+  mask_flat[(long long)b * S + tok] = pixel_mask[((long long)b * H + yy) * W + xx] != 0;
+}
+// one CTA per (level, image): column/row inclusive scans of the level mask (staged in smem) and valid ratios
+__global__ void __launch_bounds__(256)
+level_scans_kernel(GeoLevels lv, int S, const uint8_t* __restrict__ mask_flat, float* __restrict__ ycum, float* __restrict__ xcum,
+                   float* __restrict__ valid_ratios) {
   const int l = blockIdx.x, b = blockIdx.y;
   const int h = lv.h[l], w = lv.w[l];
-  uint8_t* mk = mask_flat + (long long)b * S + lv.start[l];
+  const uint8_t* mk = mask_flat + (long long)b * S + lv.start[l];
   float* yc = ycum + (long long)b * S + lv.start[l];
   float* xc = xcum + (long long)b * S + lv.start[l];
-  const int64_t* pm = pixel_mask + (long long)b * H * W;
-  const float sy = (float)H / (float)h, sx = (float)W / (float)w;  // legacy 'nearest': src = floor(dst * in/out)
-  // the level's mask is staged in shared memory when it fits, so the serial scans below run at smem latency
   extern __shared__ uint8_t mk_s[];
   const bool in_smem = (h * w) <= LEVEL_MASK_SMEM;
+  if (in_smem)
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) mk_s[i] = mk[i];
   const uint8_t* msrc = in_smem ? mk_s : mk;
-  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
-    const int y = i / w, x = i - y * w;
-    const int yy = min((int)floorf((float)y * sy), H - 1), xx = min((int)floorf((float)x * sx), W - 1);
-    const uint8_t v = pm[(long long)yy * W + xx] != 0;
-    mk[i] = v;
-    if (in_smem) mk_s[i] = v;
-  }
   __syncthreads();
   for (int x = threadIdx.x; x < w; x += blockDim.x) {  // y_embed = cumsum over rows (deformable_detr.py:853)
     float c = 0.f;
@@ -403,10 +409,12 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
   float* xcum = scratch + (long long)B * S;
   static bool attr = false;
   if (!attr) {
-    EGTR_CUDA(cudaFuncSetAttribute(level_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_MASK_SMEM));
+    EGTR_CUDA(cudaFuncSetAttribute(level_scans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_MASK_SMEM));
     attr = true;
   }
-  level_masks_kernel<<<dim3(L, B), 256, LEVEL_MASK_SMEM, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat, ycum, xcum, valid_ratios);
+  level_mask_gather_kernel<<<dim3(cdiv(S, 256), B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat);
+  level_scans_kernel<<<dim3(L, B), 256, LEVEL_MASK_SMEM, (cudaStream_t)s>>>(lv, S, mask_flat, ycum, xcum, valid_ratios);
+  count_launch();
   pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
   count_launch();
   count_launch();

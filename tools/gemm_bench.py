@@ -34,6 +34,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--profile", type=int, default=-1)
 ap.add_argument("--only", type=str, default="")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--prof", action="store_true", help="with an EGTR_GEMM_PROF build: print per-role cycle accounting")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 _lib.load()
@@ -94,4 +95,16 @@ for idx, (name, M, N, K, kind) in enumerate(SHAPES):
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
     us = ts[len(ts) // 2]
+    if args.prof:
+        import numpy as np
+        buf = (C.c_ulonglong * (148 * 16))()
+        lib = _lib.load()
+        lib.egtr_debug_gemm_prof.argtypes = [C.c_void_p]
+        run(); torch.cuda.synchronize()
+        lib.egtr_debug_gemm_prof(buf)
+        a = np.array(buf[:], dtype=np.float64).reshape(148, 16)
+        a = a[a[:, 6] > 0]  # CTAs that ran
+        m = a.mean(0)
+        print(f"   cycles/CTA: total {m[6]:9.0f} | TMA wait_empty {m[0]:8.0f} | MMA wait_tmem {m[4]:8.0f} wait_full {m[5]:8.0f} | "
+              f"producer(w6) wait_empty {m[8]:8.0f} store {m[9]:8.0f} | epilogue wait_full {m[12]:8.0f} work {m[13]:8.0f} (tmem_ld {m[14]:8.0f} stage+store {m[15]:8.0f})")
     print(f"{name:16s} M={M:6d} N={N:5d} K={K:5d}  {us:8.1f} us  {2 * M * N * K / us / 1e6:7.1f} TFLOP/s (x3 bf16 = {6 * M * N * K / us / 1e6:7.1f})  BN={os.environ.get('EGTR_GEMM_BLOCK_N', 'auto')}")
