@@ -19,13 +19,15 @@ class EgtrError(RuntimeError):
 class ASrc(C.Structure):
     _fields_ = [("a", C.c_void_p), ("a2", C.c_void_p), ("mode", C.c_int), ("lda", C.c_int),
                 ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
-                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int)]
+                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("aux", C.c_void_p)]
 
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int),
                 ("ldr", C.c_int), ("relu", C.c_int), ("rows_per_b", C.c_int), ("bstride", C.c_int),
-                ("off", C.c_int), ("row_keep", C.c_void_p)]
+                ("off", C.c_int), ("row_keep", C.c_void_p),
+                ("pair_n", C.c_int), ("dot_w", C.c_void_p), ("dot_out", C.c_void_p), ("dot_b", C.c_float), ("dot_col0", C.c_int),
+                ("fin", C.c_int), ("fin_n", C.c_int), ("cls", C.c_void_p), ("triplet", C.c_void_p), ("adj", C.c_void_p), ("k1", C.c_int)]
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -53,6 +55,7 @@ SIGNATURES = {
     "egtr_mha_core_f32": [_p, _i, _i, _i, _i, _i, _p, _p],
     "egtr_small_linear_f32": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p],
     "egtr_relation_pair_hidden_f32": [_p, _p, _i, _p, _i, _i, _i, _p, _p],
+    "egtr_argmax_rows_f32": [_p, _i, _i, _p, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {

@@ -118,7 +118,26 @@ __device__ __forceinline__ float4 gather4_nchw(const ASrc& s, long long img, int
 //   orow(m) = (m / rows_per_b) * bstride + off + m % rows_per_b   (level slices of [B,S,C] buffers)
 using Epilogue = egtr_epilogue_t;
 
+// Relation pair tiles: 128 consecutive rows = 8 subjects x 16 objects of one image.
+__device__ __forceinline__ bool pair_decode(long long m, int n_q, int& b, int& i, int& j) {
+  const int ti_n = (n_q + 7) >> 3, tj_n = (n_q + 15) >> 4;
+  const long long per_img = (long long)ti_n * tj_n * 128;
+  b = (int)(m / per_img);
+  const int rem = (int)(m - b * per_img);
+  const int tile = rem >> 7, r = rem & 127;
+  const int ti = tile / tj_n, tj = tile - ti * tj_n;
+  i = ti * 8 + (r >> 4);
+  j = tj * 16 + (r & 15);
+  return i < n_q && j < n_q;
+}
+
+// Output row of GEMM row m, or -1 when the row has no output (padding rows of pair tiles).
 __device__ __forceinline__ long long out_row(const Epilogue& e, long long m) {
+  if (e.pair_n > 0) {
+    int b, i, j;
+    if (!pair_decode(m, e.pair_n, b, i, j)) return -1;
+    return ((long long)b * e.pair_n + i) * e.pair_n + j;
+  }
   if (e.rows_per_b <= 0) return m;
   long long b = m / e.rows_per_b;
   return b * e.bstride + e.off + (m - b * e.rows_per_b);

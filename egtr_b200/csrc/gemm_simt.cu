@@ -63,6 +63,7 @@ gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K
     const long long m = m0 + ty * 4 + i;
     if (m >= M) continue;
     const long long orow = out_row(ep, m);
+    if (orow < 0) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -171,6 +172,7 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
   const int m = m0 + r;
   if (m >= M) return;
   const long long orow = out_row(ep, m);
+  if (orow < 0) return;
   float* __restrict__ out = gt.out[g];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {

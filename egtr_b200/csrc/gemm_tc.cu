@@ -58,7 +58,7 @@ struct Cfg {
   static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4608 /*barriers, row info*/ +
-                                    4 * 32 * 36 * 4 /*epilogue transpose tiles*/;
+                                    4 * 32 * 36 * 4 /*epilogue transpose tiles*/ + 2 * 128 * 8 * 4 /*pair-stage gate tables*/;
 };
 
 // Grouped launch: `groups` independent GEMMs of identical (M, N, K) in one grid — different left operands,
@@ -78,7 +78,9 @@ struct RowSlot {  // RowInfo packed for shared memory
   int iy0, ix0;
 };
 
-template <int BLOCK_N>
+// REL = true compiles in the relation-head extras (pair-gating producer, dot / finish epilogues); the generic
+// instantiation carries none of their registers.
+template <int BLOCK_N, bool REL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
                   int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int groups, int plane_rows,
@@ -94,6 +96,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   uint32_t* tmem_holder = (uint32_t*)(tmem_empty + 2);
   RowSlot* rows_all = (RowSlot*)(ctrl + 256);     // [2 groups][128] x 16 B
   float* stage_out = (float*)(ctrl + 4608);       // [4 warps][32][STG_LD]
+  float* gates_all = (float*)(ctrl + 4608 + 4 * 32 * STG_LD * 4);  // [2 groups][128 rows][8] relation gate values
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,12 +218,27 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       const long long m0 = (long long)(t / n_tiles) * BLOCK_M;
       ptx::named_bar_sync(1 + grp, 128);  // previous tile's readers are done with `rows`
       {
-        RowInfo ri = decode_row(src, m0 + ptid, M);
-        if (src.mode == 0) ri.base = (m0 + ptid) * (long long)tab.lda[g];
         RowSlot rs;
-        rs.base = ri.valid ? ri.base : -1;
-        rs.iy0 = ri.iy0;
-        rs.ix0 = ri.ix0;
+        if (REL && src.mode == 4) {
+          // relation pair tile: this thread's row is the pair (subject i, object j) of image b
+          int pb, pi, pj;
+          const bool ok = pair_decode(m0 + ptid, src.H, pb, pi, pj) && (m0 + ptid) < M;
+          rs.base = ok ? pb : -1;
+          rs.iy0 = min(pi, src.H - 1);
+          rs.ix0 = min(pj, src.H - 1);
+          // gate_l(i,j) = sigmoid(a_l(i) + b_l(j) + bias): separable logit, columns 2C of U and V (egtr.py:400)
+          const float* ug = src.a + ((long long)pb * src.H + rs.iy0) * src.W * src.lda + 2 * src.C;
+          const float* vg = src.a2 + ((long long)pb * src.H + rs.ix0) * src.W * src.lda + 2 * src.C;
+          float* gt = gates_all + (grp * 128 + ptid) * 8;
+#pragma unroll
+          for (int l = 0; l < 8; ++l) gt[l] = (l < src.W) ? sigmoidf_(__ldg(ug + l * src.lda) + __ldg(vg + l * src.lda)) : 0.f;
+        } else {
+          RowInfo ri = decode_row(src, m0 + ptid, M);
+          if (src.mode == 0) ri.base = (m0 + ptid) * (long long)tab.lda[g];
+          rs.base = ri.valid ? ri.base : -1;
+          rs.iy0 = ri.iy0;
+          rs.ix0 = ri.ix0;
+        }
         rows[ptid] = rs;
       }
       ptx::named_bar_sync(1 + grp, 128);
@@ -268,7 +286,52 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           return rs.base >= 0 ? off : -1;
         };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src.mode == 2) {
+        if (REL && src.mode == 4) {
+          // h1 = relu(b1 + sum_l gate_l(i,j) * (U_l(i) + V_l(j))) for this thread's 16 pairs x 4 channels.
+          // The thread's rows are 2 subjects (halves) x 8 objects, so each U vector is read once per half and
+          // each V vector once per (half, object): 9 L1/L2-resident float4 loads per layer and half.
+          const int cbase = (t % n_tiles) * src.C + k0 + kc * 4;  // channel inside [rel 0..C) | conn C..2C)
+          const float4 b1v = __ldg((const float4*)(src.aux + cbase));
+          const float* gt = gates_all + grp * 128 * 8;
+          int img, ti0, tj0;
+          pair_decode(m0, src.H, img, ti0, tj0);  // every row of a tile belongs to the same image
+          const long long qstride = (long long)src.W * src.lda;
+          bool waited = false;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const RowSlot rh = ld_rowslot(rows_s + (p * 32 + 16 * half + rsub) * 16);
+            const float* up = src.a + ((long long)img * src.H + rh.iy0) * qstride + cbase;
+            const float* vp[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const RowSlot rq = ld_rowslot(rows_s + (p * 32 + 16 * half + 2 * q + rsub) * 16);
+              vp[q] = src.a2 + ((long long)img * src.H + rq.ix0) * qstride + cbase;
+            }
+            float4 acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = b1v;
+#pragma unroll 1
+            for (int l = 0; l < src.W; ++l) {
+              const float4 u = __ldg((const float4*)(up + l * src.lda));
+              float4 v[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = __ldg((const float4*)(vp[q] + l * src.lda));
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float gv = gt[(p * 32 + 16 * half + 2 * q + rsub) * 8 + l];
+                acc[q].x = fmaf(gv, u.x + v[q].x, acc[q].x); acc[q].y = fmaf(gv, u.y + v[q].y, acc[q].y);
+                acc[q].z = fmaf(gv, u.z + v[q].z, acc[q].z); acc[q].w = fmaf(gv, u.w + v[q].w, acc[q].w);
+              }
+            }
+            if (!waited) { ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104); waited = true; }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              acc[q].x = fmaxf(acc[q].x, 0.f); acc[q].y = fmaxf(acc[q].y, 0.f);
+              acc[q].z = fmaxf(acc[q].z, 0.f); acc[q].w = fmaxf(acc[q].w, 0.f);
+              store_row(8 * half + q, acc[q]);
+            }
+          }
+        } else if (src.mode == 2) {
           float4 v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -342,8 +405,9 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         // pull this tile's residual rows into L2 while the MMAs are still running: the epilogue's own loads
         // (8 x 16 B per lane per chunk) are too few bytes in flight to stream them from HBM at speed
         const long long mr = (long long)(t / n_tiles) * BLOCK_M + warp * 32 + lane;
-        if (mr < M) {
-          const float* rp = ep.res + out_row(ep, mr) * ep.ldr + n0;
+        const long long pr = mr < M ? out_row(ep, mr) : -1;
+        if (pr >= 0) {
+          const float* rp = ep.res + pr * ep.ldr + n0;
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 32; ++j)
             if (n0 + j * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 32));
@@ -380,6 +444,27 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       const float* __restrict__ bias = (splits > 1 || !ep.bias) ? nullptr : ep.bias + tab.n_base[g];
       const int relu = splits > 1 ? 0 : ep.relu;
       const int ncols = splits > 1 ? Npad : N;
+      // relation-head epilogues: the connectivity MLP's 256->1 last layer as a row dot product (dot tile), and the
+      // frequency-bias / logit-adjustment / sigmoid finish of pred_rel (fin)
+      const bool dot_tile = REL && (ep.dot_w != nullptr) && (splits == 1) && (n0 >= ep.dot_col0);
+      const bool fin = REL && ep.fin && (splits == 1);
+      float dpart[REL ? 8 : 1];
+#pragma unroll
+      for (int i = 0; i < (REL ? 8 : 1); ++i) dpart[i] = 0.f;
+      const float* trip[REL ? 8 : 1];
+      if (fin) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          trip[i] = nullptr;
+          if (orow[i] >= 0 && ep.triplet != nullptr) {
+            const long long pr = orow[i];               // pair index (b*N + s)*N + o
+            const long long bs = pr / ep.fin_n;         // b*N + s
+            const int o = (int)(pr - bs * ep.fin_n);
+            const long long bb = bs / ep.fin_n;
+            trip[i] = ep.triplet + ((long long)ep.cls[bs] * ep.k1 + ep.cls[bb * ep.fin_n + o]) * N;
+          }
+        }
+      }
       const uint32_t stg_w = ptx::smem_u32(stg) + lane * (STG_LD * 4);               // this lane's row (TMEM order)
       const uint32_t stg_r = ptx::smem_u32(stg) + (rsub * STG_LD + cc) * 4;           // this lane's float4 column (row order)
       const bool aligned = ((ldo & 3) == 0) && (!rbase || (ep.ldr & 3) == 0);
@@ -422,14 +507,31 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
             v.x += b4.x + rs[i].x; v.y += b4.y + rs[i].y; v.z += b4.z + rs[i].z; v.w += b4.w + rs[i].w;
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             if (!((keep_bits >> i) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (REL) {
+            if (dot_tile) {
+              const float4 w4 = __ldg((const float4*)(ep.dot_w + (n - ep.dot_col0)));
+              dpart[i] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, dpart[i]))));
+              continue;
+            }
+            if (fin && orow[i] >= 0) {
+              if (trip[i]) { v.x += __ldg(trip[i] + n); v.y += __ldg(trip[i] + n + 1); v.z += __ldg(trip[i] + n + 2); v.w += __ldg(trip[i] + n + 3); }
+              if (ep.adj) { v.x -= __ldg(ep.adj + n); v.y -= __ldg(ep.adj + n + 1); v.z -= __ldg(ep.adj + n + 2); v.w -= __ldg(ep.adj + n + 3); }
+              v.x = sigmoidf_(v.x); v.y = sigmoidf_(v.y); v.z = sigmoidf_(v.z); v.w = sigmoidf_(v.w);
+            }
+            }
             if (orow[i] >= 0) *(float4*)(obase + orow[i] * ldo + n) = v;
           }
         } else {  // N tail or unaligned leading dimension: per-element, still fully unrolled (registers only)
-          auto put = [&](long long row, int col, float v, float bv, bool keep) {
+          auto put = [&](long long row, int col, float v, float bv, bool keep, const float* tp) {
             if (col < ncols) {
               v += bv;
               if (rbase) v += rbase[row * ep.ldr + col];
               if (relu) v = fmaxf(v, 0.f);
+              if (fin) {
+                if (tp) v += __ldg(tp + col);
+                if (ep.adj) v -= __ldg(ep.adj + col);
+                v = sigmoidf_(v);
+              }
               obase[row * ldo + col] = keep ? v : 0.f;
             }
           };
@@ -437,14 +539,25 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           for (int i = 0; i < 8; ++i) {
             if (orow[i] >= 0) {
               const bool keep = (keep_bits >> i) & 1u;
-              put(orow[i], n, o[i].x, b4.x, keep);
-              put(orow[i], n + 1, o[i].y, b4.y, keep);
-              put(orow[i], n + 2, o[i].z, b4.z, keep);
-              put(orow[i], n + 3, o[i].w, b4.w, keep);
+              const float* tp = fin ? trip[REL ? i : 0] : nullptr;
+              put(orow[i], n, o[i].x, b4.x, keep, tp);
+              put(orow[i], n + 1, o[i].y, b4.y, keep, tp);
+              put(orow[i], n + 2, o[i].z, b4.z, keep, tp);
+              put(orow[i], n + 3, o[i].w, b4.w, keep, tp);
             }
           }
         }
         PROF_ADD(3, t_i);
+      }
+      if (dot_tile) {
+#pragma unroll
+        for (int i = 0; i < (REL ? 8 : 1); ++i) {  // the 8 lanes that share a row hold its partial sums
+          float d = dpart[i];
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (cc == 0 && orow[i] >= 0) ep.dot_out[orow[i]] = sigmoidf_(d + ep.dot_b);
+        }
       }
       PROF_ADD(1, t_g);
       ptx::tc_fence_before();
@@ -551,6 +664,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   const long long orow = out_row(ep, m);
+  if (orow < 0) return;
   const float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -580,7 +694,7 @@ float* partial_buffer(size_t floats) {
   return buf;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool REL = false>
 int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st,
            int groups = 1, int plane_rows = 0, const GroupTab* gtab = nullptr) {
   using C = Cfg<BLOCK_N>;
@@ -593,7 +707,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   if (rc != EGTR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = groups * cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
@@ -613,7 +727,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   }
   const int work = tiles * splits;
   const int grid = work < num_sms() ? work : num_sms();
-  gemm_sbf16_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
+  gemm_sbf16_kernel<BLOCK_N, REL><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long n = (long long)M * ((N + 3) / 4);
@@ -660,7 +774,8 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   EGTR_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0 && Npad % 64 == 0 && Npad >= N, EGTR_ERR_ARG,
              "egtr_gemm_sbf16: need K %% 64 == 0 and Npad %% 64 == 0 (M=%d N=%d Npad=%d K=%d)", M, N, Npad, K);
   EGTR_CHECK(a->mode == 0 || (a->mode == 1 && a->C % 64 == 0 && K == a->KH * a->KW * a->C) ||
-                 (a->mode == 2 && K >= a->KH * a->KW * a->C) || (a->mode == 3 && a->C == 4 && a->pad == 0 && K >= a->KH * a->KW * 4),
+                 (a->mode == 2 && K >= a->KH * a->KW * a->C) || (a->mode == 3 && a->C == 4 && a->pad == 0 && K >= a->KH * a->KW * 4) ||
+                 (a->mode == 4 && a->a2 && a->aux && K == a->C && a->C % 64 == 0 && a->W <= 8 && ep->pair_n == a->H && Npad % 256 == 0),
              EGTR_ERR_ARG, "egtr_gemm_sbf16: conv source needs C %% 64 == 0 and K == KH*KW*C (mode=%d C=%d K=%d)", a->mode, a->C, K);
   EGTR_CHECK(a->mode != 0 || (a->lda % 4 == 0 && a->lda >= K), EGTR_ERR_ARG, "egtr_gemm_sbf16: lda=%d", a->lda);
   EGTR_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)w_planes & 127) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16: alignment");
@@ -669,6 +784,11 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   if (forced_bn == 128 && Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
   if (forced_bn == 64) return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);
+  if (a->mode == 4 || ep->fin || ep->dot_w || ep->pair_n > 0) {  // relation-head instantiations
+    if (Npad % 256 == 0) return launch<256, true>(*a, w_planes, M, N, Npad, K, *ep, st);
+    if (Npad % 128 == 0) return launch<128, true>(*a, w_planes, M, N, Npad, K, *ep, st);
+    return launch<64, true>(*a, w_planes, M, N, Npad, K, *ep, st);
+  }
   if (Npad % 256 == 0) return launch<256>(*a, w_planes, M, N, Npad, K, *ep, st);
   if (Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
   return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);

@@ -169,7 +169,6 @@ groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int o
 }
 
 // ------------------------------------------------------------------ masks, cumulative sums, valid ratios
-constexpr int LEVEL_MASK_SMEM = 64 * 1024;
 struct GeoLevels {
   int L;
   int h[8], w[8], start[8];
@@ -197,19 +196,17 @@ level_scans_kernel(GeoLevels lv, int S, const uint8_t* __restrict__ mask_flat, f
   const uint8_t* mk = mask_flat + (long long)b * S + lv.start[l];
   float* yc = ycum + (long long)b * S + lv.start[l];
   float* xc = xcum + (long long)b * S + lv.start[l];
-  extern __shared__ uint8_t mk_s[];
-  const bool in_smem = (h * w) <= LEVEL_MASK_SMEM;
-  if (in_smem)
-    for (int i = threadIdx.x; i < h * w; i += blockDim.x) mk_s[i] = mk[i];
-  const uint8_t* msrc = in_smem ? mk_s : mk;
-  __syncthreads();
+  const uint8_t* msrc = mk;
+  // the loads of a scan are independent of the running sum: unrolling lets 8 of them be in flight per thread
   for (int x = threadIdx.x; x < w; x += blockDim.x) {  // y_embed = cumsum over rows (deformable_detr.py:853)
     float c = 0.f;
-    for (int y = 0; y < h; ++y) { c += (float)msrc[y * w + x]; yc[y * w + x] = c; }
+#pragma unroll 8
+    for (int y = 0; y < h; ++y) { c += (float)__ldg(msrc + y * w + x); yc[y * w + x] = c; }
   }
   for (int y = threadIdx.x; y < h; y += blockDim.x) {  // x_embed = cumsum over columns (854)
     float c = 0.f;
-    for (int x = 0; x < w; ++x) { c += (float)msrc[y * w + x]; xc[y * w + x] = c; }
+#pragma unroll 8
+    for (int x = 0; x < w; ++x) { c += (float)__ldg(msrc + y * w + x); xc[y * w + x] = c; }
   }
   if (threadIdx.x == 0) {  // get_valid_ratio (2064-2073): first column / first row
     int vh = 0, vw = 0;
@@ -223,24 +220,29 @@ level_scans_kernel(GeoLevels lv, int S, const uint8_t* __restrict__ mask_flat, f
 __global__ void __launch_bounds__(256)
 pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum, GeoLevels lv, int S, const float* __restrict__ level_embed,
                  const float* __restrict__ dim_t_tab, float* __restrict__ pos) {
-  const int tok = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+  // 2 tokens per CTA; thread = one (sin, cos) channel pair: channels 2j, 2j+1 share dim_t (860-865), so one sincosf serves both
+  const int tok = blockIdx.x * 2 + (threadIdx.x >> 7), b = blockIdx.y, j = threadIdx.x & 127;
+  if (tok >= S) return;
   int l = 0;
   while (l + 1 < lv.L && tok >= lv.start[l + 1]) ++l;
   const int w = lv.w[l], h = lv.h[l];
   const int pix = tok - lv.start[l];
   const int y = pix / w, x = pix - y * w;
   const long long base = (long long)b * S + lv.start[l];
-  const bool is_y = c < 128;
-  const int i = is_y ? c : c - 128;
+  const bool is_y = j < 64;
+  const int i = (is_y ? j : j - 64) * 2;  // even channel index inside the y (or x) half
   float e, last;
   if (is_y) { e = ycum[base + pix]; last = ycum[base + (h - 1) * w + x]; }
   else      { e = xcum[base + pix]; last = xcum[base + y * w + (w - 1)]; }
   const float v = (e - 0.5f) / (last + 1e-6f) * 6.283185307179586f;
-  // dim_t = 10000^(2*(i//2)/128) comes from a host-made table so that fully padded columns, whose
-  // normalised coordinate is -0.5/1e-6 (the reference divides by last+eps, 857-858), see bit-identical arguments.
-  const float dim_t = dim_t_tab[i];
-  const float a = v / dim_t;
-  pos[((long long)b * S + tok) * 256 + c] = ((i & 1) ? cosf(a) : sinf(a)) + level_embed[l * 256 + c];
+  // dim_t = 10000^(2*(i//2)/128) comes from a host-made table so that fully padded columns, whose normalised
+  // coordinate is -0.5/1e-6 (the reference divides by last+eps, 857-858), see bit-identical arguments.
+  const float a = v / dim_t_tab[i];
+  float sn, cs;
+  sincosf(a, &sn, &cs);
+  const int c = (is_y ? 0 : 128) + i;
+  const float2 le = *(const float2*)(level_embed + l * 256 + c);
+  *(float2*)(pos + ((long long)b * S + tok) * 256 + c) = make_float2(sn + le.x, cs + le.y);
 }
 
 // ------------------------------------------------------------------ decoder self-attention core
@@ -407,15 +409,10 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
   }
   float* ycum = scratch;
   float* xcum = scratch + (long long)B * S;
-  static bool attr = false;
-  if (!attr) {
-    EGTR_CUDA(cudaFuncSetAttribute(level_scans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_MASK_SMEM));
-    attr = true;
-  }
   level_mask_gather_kernel<<<dim3(cdiv(S, 256), B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat);
-  level_scans_kernel<<<dim3(L, B), 256, LEVEL_MASK_SMEM, (cudaStream_t)s>>>(lv, S, mask_flat, ycum, xcum, valid_ratios);
+  level_scans_kernel<<<dim3(L, B), 256, 0, (cudaStream_t)s>>>(lv, S, mask_flat, ycum, xcum, valid_ratios);
   count_launch();
-  pos_embed_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
+  pos_embed_kernel<<<dim3(cdiv(S, 2), B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
   count_launch();
   count_launch();
   EGTR_CUDA(cudaGetLastError());

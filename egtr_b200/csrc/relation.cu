@@ -129,3 +129,11 @@ extern "C" int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, con
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
 }
+
+extern "C" int egtr_argmax_rows_f32(const float* x, int cols, int rows, int* out, egtr_stream_t s) {
+  EGTR_CHECK(x && out && cols > 0 && rows > 0, EGTR_ERR_ARG, "egtr_argmax_rows_f32: bad arguments");
+  argmax_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, cols, rows, out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}

@@ -256,6 +256,10 @@ class Engine:
             bs.append((w1o @ wk[1].double() + gate_b).float())
         self.rel_uv = LinStack(ws, bs, dev)  # groups 0..6 -> U_l (subject side), 7..13 -> V_l (object side)
         self.rel_b1 = torch.cat([sd["rel_predictor.layers.0.bias"], sd["connectivity_layer.layers.0.bias"]], 0).contiguous()
+        # layer 2 of both MLPs as one block-diagonal [512,256] weight: output columns 0..255 = relation MLP (reads
+        # hidden channels 0..255), columns 256..511 = connectivity MLP (reads channels 256..511)
+        self.rel_w2both = L(torch.cat([sd["rel_predictor.layers.1.weight"], sd["connectivity_layer.layers.1.weight"]], 0),
+                            torch.cat([sd["rel_predictor.layers.1.bias"], sd["connectivity_layer.layers.1.bias"]], 0))
         self.rel_w2 = L(sd["rel_predictor.layers.1.weight"], sd["rel_predictor.layers.1.bias"])
         self.con_w2 = L(sd["connectivity_layer.layers.1.weight"], sd["connectivity_layer.layers.1.bias"])
         self.rel_w3 = L(sd["rel_predictor.layers.2.weight"], sd["rel_predictor.layers.2.bias"])
@@ -263,6 +267,8 @@ class Engine:
         self.con_w3_b = sd["connectivity_layer.layers.2.bias"].contiguous()
         self.triplet = sd["triplet_dist"].contiguous()
         self.rel_dist = sd["rel_dist"].contiguous()
+        self.rel_adj = (float(getattr(cfg, "logit_adj_tau", 0.3)) * self.rel_dist.log()).contiguous()  # egtr.py:509-512
+        self.con_w3_b_host = float(sd["connectivity_layer.layers.2.bias"].item())
         torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------ CUDA-graph replay
@@ -547,18 +553,41 @@ class Engine:
         outs = [(ws["U"], l * 516) for l in range(Lr)] + [(ws["V"], l * 516) for l in range(Lr)]
         self.gemm_grouped(self.rel_uv, Md, a=a_list, a_col=a_cols, lda=ldas, out=outs, ldo=Lr * 516)
         pairs = B * N * N
-        call("egtr_relation_pair_hidden_f32", _ptr(ws["U"]), _ptr(ws["V"]), 516, _ptr(self.rel_b1), B, N, Lr, _ptr(ws["H1"]), st)
-        self.gemm(self.rel_w2, pairs, ws["H2r"], a=ws["H1"], lda=512, a_col=0, relu=True)
-        self.gemm(self.con_w2, pairs, ws["H2c"], a=ws["H1"], lda=512, a_col=256, relu=True)
-        self.gemm(self.rel_w3, pairs, ws["rel_logits"], a=ws["H2r"], lda=256, ldo=P)
-        call("egtr_small_linear_f32", _ptr(ws["H2c"]), 256, _ptr(self.con_w3_w), _ptr(self.con_w3_b), pairs, 256, 1, 0,
-             None, 0, 0, _ptr(ws["con_logits"]), 1, st)
         pred_rel = torch.empty(B, N, N, P, **f32)
         pred_con = torch.empty(B, N, N, 1, **f32)
-        call("egtr_relation_finish_f32", _ptr(ws["rel_logits"]), P, _ptr(ws["con_logits"]), 1, _ptr(logits), K,
-             _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
-             int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), _ptr(pred_con), st)
-
+        if gemm_backend() == "simt":
+            # unfused cross-check path: pair kernel -> H1 -> two layer-2 GEMMs -> layer 3 -> finish kernel
+            call("egtr_relation_pair_hidden_f32", _ptr(ws["U"]), _ptr(ws["V"]), 516, _ptr(self.rel_b1), B, N, Lr, _ptr(ws["H1"]), st)
+            self.gemm(self.rel_w2, pairs, ws["H2r"], a=ws["H1"], lda=512, a_col=0, relu=True)
+            self.gemm(self.con_w2, pairs, ws["H2c"], a=ws["H1"], lda=512, a_col=256, relu=True)
+            self.gemm(self.rel_w3, pairs, ws["rel_logits"], a=ws["H2r"], lda=256, ldo=P)
+            call("egtr_small_linear_f32", _ptr(ws["H2c"]), 256, _ptr(self.con_w3_w), _ptr(self.con_w3_b), pairs, 256, 1, 0,
+                 None, 0, 0, _ptr(ws["con_logits"]), 1, st)
+            call("egtr_relation_finish_f32", _ptr(ws["rel_logits"]), P, _ptr(ws["con_logits"]), 1, _ptr(logits), K,
+                 _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
+                 int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), _ptr(pred_con), st)
+        else:
+            # fused pair stage: the gating + layer 1 is the GEMM's operand producer (never in HBM), layer 2 of both MLPs is
+            # one block-diagonal tcgen05 GEMM, the connectivity head's last layer + sigmoid is its epilogue; only the
+            # relation MLP's 256-wide hidden goes to HBM for the layer-3 GEMM whose epilogue finishes pred_rel.
+            TI, TJ = (N + 7) // 8, (N + 15) // 16
+            src, ep = ASrc(), Epilogue()
+            src.a, src.a2, src.aux, src.mode, src.lda = _ptr(ws["U"]), _ptr(ws["V"]), _ptr(self.rel_b1), 4, 516
+            src.H, src.W, src.C, src.OH, src.OW = N, Lr, 256, TI, TJ
+            ep.bias, ep.out, ep.ldo, ep.ldr, ep.relu = _ptr(self.rel_w2both.b), _ptr(ws["H2r"]), 256, 256, 1
+            ep.pair_n = N
+            ep.dot_w, ep.dot_out, ep.dot_b, ep.dot_col0 = _ptr(self.con_w3_w), _ptr(pred_con), self.con_w3_b_host, 256
+            lin = self.rel_w2both
+            call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), B * TI * TJ * 128, lin.N, lin.Npad, lin.K, C.byref(ep), st)
+            call("egtr_argmax_rows_f32", _ptr(logits), K, B * N, _ptr(ws["cls_idx"]), st)
+            src2, ep2 = ASrc(), Epilogue()
+            src2.a, src2.mode, src2.lda = _ptr(ws["H2r"]), 0, 256
+            ep2.bias, ep2.out, ep2.ldo, ep2.ldr = _ptr(self.rel_w3.b), _ptr(pred_rel), P, P
+            ep2.fin, ep2.fin_n, ep2.cls, ep2.k1 = 1, N, _ptr(ws["cls_idx"]), K + 1
+            ep2.triplet = _ptr(self.triplet) if cfg.use_freq_bias else None
+            ep2.adj = _ptr(self.rel_adj) if cfg.logit_adjustment else None
+            lin3 = self.rel_w3
+            call("egtr_gemm_sbf16", C.byref(src2), _ptr(lin3.planes), pairs, lin3.N, lin3.Npad, lin3.K, C.byref(ep2), st)
         _sp_rel.__exit__()
         # captured decoder self-attention states as [B, heads, N, 32] views (deformable_detr.py:1179-1185)
         qs = tuple(q.view(B, N, 3, 8, 32)[:, :, 0].permute(0, 2, 1, 3) for q in qkvs)

@@ -50,13 +50,19 @@ void egtr_launch_count_reset(void);
  * same gather over an NCHW image with few channels (the 7x7/2 stem on pixel_values [B,3,H,W]):
  * k = (ky*KW + kx)*C + c for k < KH*KW*C, zero for the padding columns up to K.  mode 3: the stem on
  * the zero-padded NHWC4 copy of the image made by egtr_pad_nchw3_to_nhwc4_f32 (C = 4, pad = 0, H/W the
- * padded sizes): k = (ky*KW + kx)*4 + c, every tap one aligned float4 and no bounds checks. */
+ * padded sizes): k = (ky*KW + kx)*4 + c, every tap one aligned float4 and no bounds checks.  mode 4: the
+ * relation head's pair stage (model/egtr.py:366-401 + layer 1 of both MLPs, factorised — DESIGN.md §4.3):
+ * rows enumerate subject x object pairs in tiles of 8 x 16, a = U, a2 = V ([B*H, W*lda] per-query layer-1
+ * partials with the gate logit in column 2*C; H = N_q, W = 7 "layers", C = 256, OH/OW = tiles per image side),
+ * and the operand row is  relu(aux + sum_l sigmoid(U_l[i,2C] + V_l[j,2C]) * (U_l[i,c] + V_l[j,c]))  for the
+ * c-range of the n-tile (block-diagonal layer 2: columns >= C of the output read channels C..2C-1). */
 typedef struct {
   const float* a;
   const float* a2;
   int mode;
   int lda;
   int H, W, C, OH, OW, KH, KW, stride, pad;
+  const float* aux; /* mode 4: b1 [2*C] (layer-1 bias of the relation and connectivity MLPs) */
 } egtr_asrc_t;
 
 /* out[orow(m)*ldo + n] = keep(act(acc + bias[n] + res[orow(m)*ldr + n]));
@@ -70,6 +76,18 @@ typedef struct {
   int relu;
   int rows_per_b, bstride, off;
   const uint8_t* row_keep;
+  /* relation-head extensions (all zero / NULL elsewhere) */
+  int pair_n;           /* > 0: rows are padded 8x16 pair tiles of N_q = pair_n queries; output row = pair index */
+  const float* dot_w;   /* non-NULL: output columns >= dot_col0 are not stored; the row's */
+  float* dot_out;       /*   sigmoid(sum_n act(..)[n] * dot_w[n - dot_col0] + dot_b) goes to dot_out[pair] */
+  float dot_b;          /*   (the connectivity MLP's last layer, model/egtr.py:416, 516) */
+  int dot_col0;
+  int fin;              /* 1: out = sigmoid(acc + bias + triplet[cls[s], cls[o], n] - adj[n]) (model/egtr.py:405-413, 509-515) */
+  int fin_n;            /*    N_q of the finishing GEMM whose rows are pair indices (b*N + i)*N + j */
+  const int* cls;       /*    argmax class per query [B*N] */
+  const float* triplet; /*    [K1, K1, P] or NULL */
+  const float* adj;     /*    tau * log(rel_dist) [P] or NULL */
+  int k1;
 } egtr_epilogue_t;
 
 /* fp32 weight [N,K] -> split-bf16 planes [2][Npad][K] (hi, lo; rows >= N zero). Npad % 64 == 0. */
@@ -167,6 +185,9 @@ int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, const float* c
                              const float* logits, int K, const float* triplet_dist, const float* rel_dist,
                              float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
                              int* cls_scratch /* B*N ints */, float* pred_rel, float* pred_conn, egtr_stream_t s);
+
+/* out[r] = argmax over x[r, :cols], first maximum wins (torch.argmax; model/egtr.py:406). */
+int egtr_argmax_rows_f32(const float* x, int cols, int rows, int* out, egtr_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -111,3 +111,23 @@ def test_pipelined_runner_matches_direct_forward(cuda):
     model.use_cuda_graph = True  # the single-call graph option of the model API gives the same answers too
     o = model(batches[0][0].cuda(), batches[0][1].cuda())
     assert torch.equal(o.pred_rel.cpu(), want[0]["pred_rel"])
+
+
+@pytest.mark.parametrize("wl,batch", [("tiny", 2), ("small", 1), ("A", 1)])
+def test_fused_relation_stage_matches_unfused_kernels(cuda, wl, batch, monkeypatch):
+    """tc backend (pair-gating producer + dot/finish epilogues) vs the simt cross-check path (separate kernels)."""
+    from egtr_b200.config import WORKLOADS, workload_config
+    from egtr_b200.engine import Engine
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from tests.util import relerr
+    cfg = workload_config(wl, logit_adjustment=(wl == "small"))
+    H, W = WORKLOADS[wl]["image"]
+    sd = synth_state_dict(cfg, 77)
+    px, mask = synth_images(batch, H, W, seed=78)
+    monkeypatch.setenv("EGTR_B200_GEMM", "tc")
+    got = Engine(cfg, sd, cuda).forward(px.to(cuda), mask.to(cuda))
+    monkeypatch.setenv("EGTR_B200_GEMM", "simt")
+    want = Engine(cfg, sd, cuda).forward(px.to(cuda), mask.to(cuda))
+    torch.cuda.synchronize()
+    for k in ("pred_rel", "pred_connectivity", "logits"):
+        assert relerr(got[k], want[k]) < 2e-4, k
