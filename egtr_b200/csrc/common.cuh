@@ -118,16 +118,26 @@ __device__ __forceinline__ float4 gather4_nchw(const ASrc& s, long long img, int
 //   orow(m) = (m / rows_per_b) * bstride + off + m % rows_per_b   (level slices of [B,S,C] buffers)
 using Epilogue = egtr_epilogue_t;
 
-// Relation pair tiles: 128 consecutive rows = 8 subjects x 16 objects of one image.
+// Relation pair tiles: 128 consecutive rows = 8 subjects x 16 objects of one image.  Inside a tile the rows are
+// ordered so that the 16 rows one producer thread of the GEMM owns (r = 32*p + 2*i + rsub, i = 0..15) form a
+// 4 subjects x 4 objects block: every U/V vector it loads is then used four times.
+//   r = 32*p + 2*(4*a + c) + rsub   ->   subject = 4*(p & 1) + a,   object = 8*(p >> 1) + 4*rsub + c
+__device__ __forceinline__ void pair_local(int r, int& s_loc, int& o_loc) {
+  const int p = r >> 5, i = (r & 31) >> 1, rsub = r & 1;
+  s_loc = 4 * (p & 1) + (i >> 2);
+  o_loc = 8 * (p >> 1) + 4 * rsub + (i & 3);
+}
 __device__ __forceinline__ bool pair_decode(long long m, int n_q, int& b, int& i, int& j) {
   const int ti_n = (n_q + 7) >> 3, tj_n = (n_q + 15) >> 4;
   const long long per_img = (long long)ti_n * tj_n * 128;
   b = (int)(m / per_img);
   const int rem = (int)(m - b * per_img);
-  const int tile = rem >> 7, r = rem & 127;
+  const int tile = rem >> 7;
   const int ti = tile / tj_n, tj = tile - ti * tj_n;
-  i = ti * 8 + (r >> 4);
-  j = tj * 16 + (r & 15);
+  int s_loc, o_loc;
+  pair_local(rem & 127, s_loc, o_loc);
+  i = ti * 8 + s_loc;
+  j = tj * 16 + o_loc;
   return i < n_q && j < n_q;
 }
 

@@ -287,48 +287,63 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (REL && src.mode == 4) {
-          // h1 = relu(b1 + sum_l gate_l(i,j) * (U_l(i) + V_l(j))) for this thread's 16 pairs x 4 channels.
-          // The thread's rows are 2 subjects (halves) x 8 objects, so each U vector is read once per half and
-          // each V vector once per (half, object): 9 L1/L2-resident float4 loads per layer and half.
+          // h1 = relu(b1 + sum_l gate_l(s,o) * (U_l(s) + V_l(o))) for this thread's 16 pairs x 4 channels.  The rows
+          // of a thread are a 4 x 4 block of (subject, object) (pair_local), processed as two passes of 2 subjects
+          // x 4 objects: 6 L1/L2-resident float4 loads feed 8 pairs per layer; two layers are in flight at a time.
           const int cbase = (t % n_tiles) * src.C + k0 + kc * 4;  // channel inside [rel 0..C) | conn C..2C)
           const float4 b1v = __ldg((const float4*)(src.aux + cbase));
-          const float* gt = gates_all + grp * 128 * 8;
           int img, ti0, tj0;
-          pair_decode(m0, src.H, img, ti0, tj0);  // every row of a tile belongs to the same image
+          pair_decode(m0, src.H, img, ti0, tj0);  // (image, first subject, first object) of the tile: row 0 is (s 0, o 0)
+          const int nq1 = src.H - 1;
           const long long qstride = (long long)src.W * src.lda;
+          const float* ubase = src.a + (long long)img * src.H * qstride + cbase;
+          const float* vbase = src.a2 + (long long)img * src.H * qstride + cbase;
+          const uint32_t gts = ptx::smem_u32(gates_all + grp * 128 * 8);
+          const int s_first = ti0 + 4 * (p & 1), o_first = tj0 + 8 * (p >> 1) + 4 * rsub;
+          int vo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) vo[c] = (int)(min(o_first + c, nq1) * qstride);
           bool waited = false;
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            const RowSlot rh = ld_rowslot(rows_s + (p * 32 + 16 * half + rsub) * 16);
-            const float* up = src.a + ((long long)img * src.H + rh.iy0) * qstride + cbase;
-            const float* vp[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const RowSlot rq = ld_rowslot(rows_s + (p * 32 + 16 * half + 2 * q + rsub) * 16);
-              vp[q] = src.a2 + ((long long)img * src.H + rq.ix0) * qstride + cbase;
-            }
-            float4 acc[8];
+          for (int pass = 0; pass < 2; ++pass) {  // subjects a = 2*pass, 2*pass + 1
+            const int uo0 = (int)(min(s_first + 2 * pass, nq1) * qstride), uo1 = (int)(min(s_first + 2 * pass + 1, nq1) * qstride);
+            float4 acc[8];  // [a_local (2)][c (4)]
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = b1v;
+            auto fma_layer = [&](int l, const float4 (&u)[2], const float4 (&v)[4]) {
+#pragma unroll
+              for (int al = 0; al < 2; ++al)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int r = p * 32 + 2 * (4 * (2 * pass + al) + c) + rsub;
+                  float gv;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gv) : "r"(gts + (r * 8 + l) * 4));
+                  float4& a4 = acc[al * 4 + c];
+                  a4.x = fmaf(gv, u[al].x + v[c].x, a4.x); a4.y = fmaf(gv, u[al].y + v[c].y, a4.y);
+                  a4.z = fmaf(gv, u[al].z + v[c].z, a4.z); a4.w = fmaf(gv, u[al].w + v[c].w, a4.w);
+                }
+            };
+            auto load_layer = [&](int l, float4 (&u)[2], float4 (&v)[4]) {
+              u[0] = __ldg((const float4*)(ubase + uo0 + l * src.lda));
+              u[1] = __ldg((const float4*)(ubase + uo1 + l * src.lda));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) v[c] = __ldg((const float4*)(vbase + vo[c] + l * src.lda));
+            };
+            float4 ua[2], va[4], ub[2], vb[4];
+            load_layer(0, ua, va);
 #pragma unroll 1
-            for (int l = 0; l < src.W; ++l) {
-              const float4 u = __ldg((const float4*)(up + l * src.lda));
-              float4 v[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __ldg((const float4*)(vp[q] + l * src.lda));
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float gv = gt[(p * 32 + 16 * half + 2 * q + rsub) * 8 + l];
-                acc[q].x = fmaf(gv, u.x + v[q].x, acc[q].x); acc[q].y = fmaf(gv, u.y + v[q].y, acc[q].y);
-                acc[q].z = fmaf(gv, u.z + v[q].z, acc[q].z); acc[q].w = fmaf(gv, u.w + v[q].w, acc[q].w);
-              }
+            for (int l = 0; l < src.W; l += 2) {
+              if (l + 1 < src.W) load_layer(l + 1, ub, vb);
+              fma_layer(l, ua, va);
+              if (l + 2 < src.W) load_layer(l + 2, ua, va);
+              if (l + 1 < src.W) fma_layer(l + 1, ub, vb);
             }
             if (!waited) { ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104); waited = true; }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               acc[q].x = fmaxf(acc[q].x, 0.f); acc[q].y = fmaxf(acc[q].y, 0.f);
               acc[q].z = fmaxf(acc[q].z, 0.f); acc[q].w = fmaxf(acc[q].w, 0.f);
-              store_row(8 * half + q, acc[q]);
+              store_row(4 * (2 * pass + (q >> 2)) + (q & 3), acc[q]);
             }
           }
         } else if (src.mode == 2) {
