@@ -78,9 +78,10 @@ struct RowSlot {  // RowInfo packed for shared memory
   int iy0, ix0;
 };
 
-// REL = true compiles in the relation-head extras (pair-gating producer, dot / finish epilogues); the generic
-// instantiation carries none of their registers.
-template <int BLOCK_N, bool REL>
+// MODE selects the one operand-producer path that is compiled in (0 plain rows, 5 plain rows + addend, 1 implicit
+// im2col, 3 stem taps, 4 relation pair gating); REL = true adds the relation-head epilogues (dot / finish).  One
+// path per instantiation keeps each kernel's code — and its instruction-cache footprint — small.
+template <int BLOCK_N, int MODE, bool REL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
                   int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int groups, int plane_rows,
@@ -201,7 +202,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
     const uint32_t rows_s = ptx::smem_u32(rows);
     auto ld_rowslot = [](uint32_t addr) {  // explicit 16-byte shared load of one RowSlot
       uint32_t a, b, c, d;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
       RowSlot r;
       r.base = (long long)(((unsigned long long)b << 32) | a);
       r.iy0 = (int)c;
@@ -219,7 +220,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
       ptx::named_bar_sync(1 + grp, 128);  // previous tile's readers are done with `rows`
       {
         RowSlot rs;
-        if (REL && src.mode == 4) {
+        if (MODE == 4) {
           // relation pair tile: this thread's row is the pair (subject i, object j) of image b
           int pb, pi, pj;
           const bool ok = pair_decode(m0 + ptid, src.H, pb, pi, pj) && (m0 + ptid) < M;
@@ -234,7 +235,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           for (int l = 0; l < 8; ++l) gt[l] = (l < src.W) ? sigmoidf_(__ldg(ug + l * src.lda) + __ldg(vg + l * src.lda)) : 0.f;
         } else {
           RowInfo ri = decode_row(src, m0 + ptid, M);
-          if (src.mode == 0) ri.base = (m0 + ptid) * (long long)tab.lda[g];
+          if (MODE == 0 || MODE == 5) ri.base = (m0 + ptid) * (long long)tab.lda[g];
           rs.base = ri.valid ? ri.base : -1;
           rs.iy0 = ri.iy0;
           rs.ix0 = ri.ix0;
@@ -247,7 +248,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
         const int stage = seq % C::STAGES, phase = (seq / C::STAGES) & 1;
         const int k0 = kb * BLOCK_K;
         int ky = 0, kx = 0, c0 = k0;
-        if (src.mode == 1) {
+        if (MODE == 1) {
           const int tap = k0 / src.C;
           c0 = k0 - tap * src.C;
           ky = tap / src.KW;
@@ -272,13 +273,13 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
           pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
           // explicit shared-space stores (the realigned dynamic-smem pointer is generic to the compiler)
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi_s + o), "r"(ph.x), "r"(ph.y) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo_s + o), "r"(pl.x), "r"(pl.y) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi_s + o), "r"(ph.x), "r"(ph.y));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo_s + o), "r"(pl.x), "r"(pl.y));
         };
         auto row_off = [&](int i) -> long long {
           const RowSlot rs = ld_rowslot(rows_s + (p * 32 + 2 * i + rsub) * 16);
           long long off = rs.base + k0;  // plain rows
-          if (src.mode == 1) {
+          if (MODE == 1) {
             const int iy = rs.iy0 + ky, ix = rs.ix0 + kx;
             const bool in = (unsigned)iy < (unsigned)src.H && (unsigned)ix < (unsigned)src.W;
             off = in ? (rs.base + (long long)iy * src.W + ix) * src.C + c0 : -1;
@@ -286,7 +287,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           return rs.base >= 0 ? off : -1;
         };
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (REL && src.mode == 4) {
+        if constexpr (MODE == 4) {
           // h1 = relu(b1 + sum_l gate_l(s,o) * (U_l(s) + V_l(o))) for this thread's 16 pairs x 4 channels.  The rows
           // of a thread are a 4 x 4 block of (subject, object) (pair_local), processed as two passes of 2 subjects
           // x 4 objects: 6 L1/L2-resident float4 loads feed 8 pairs per layer; two layers are in flight at a time.
@@ -346,17 +347,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
               store_row(4 * (2 * pass + (q >> 2)) + (q & 3), acc[q]);
             }
           }
-        } else if (src.mode == 2) {
-          float4 v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const RowSlot rs = ld_rowslot(rows_s + (p * 32 + 2 * i + rsub) * 16);
-            v[i] = rs.base >= 0 ? gather4_nchw(src, rs.base, rs.iy0, rs.ix0, k0 + kc * 4) : zero4;
-          }
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) store_row(i, v[i]);
-        } else if (src.mode == 3) {
+        } else if constexpr (MODE == 3) {
           // stem on the zero-padded NHWC4 image: this thread's float4 of the run is filter tap k0/4 + kc
           const int tap = (k0 >> 2) + kc;
           const int tky = tap / src.KW, tkx = tap - tky * src.KW;
@@ -371,7 +362,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
           for (int i = 0; i < 16; ++i) store_row(i, v[i]);
-        } else if (a2_ptr == nullptr) {
+        } else if constexpr (MODE != 5) {
           long long off[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) off[i] = row_off(i);
@@ -395,7 +386,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? __ldg((const float4*)(a_ptr + off[i]) + kc) : zero4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = off[i] >= 0 ? __ldg((const float4*)(a2_ptr + off[i]) + kc) : zero4;
+            for (int i = 0; i < 8; ++i) w[i] = (off[i] >= 0 && a2_ptr != nullptr) ? __ldg((const float4*)(a2_ptr + off[i]) + kc) : zero4;
             if (half == 0) ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 104);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -709,7 +700,7 @@ float* partial_buffer(size_t floats) {
   return buf;
 }
 
-template <int BLOCK_N, bool REL = false>
+template <int BLOCK_N, int MODE, bool REL>
 int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st,
            int groups = 1, int plane_rows = 0, const GroupTab* gtab = nullptr) {
   using C = Cfg<BLOCK_N>;
@@ -720,9 +711,9 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   CUtensorMap tmap;
   int rc = weight_tensor_map(planes, plane_rows, K, BLOCK_N, &tmap);
   if (rc != EGTR_OK) return rc;
-  static bool attr_set = false;
+  static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_sbf16_kernel<BLOCK_N, MODE, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = groups * cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
@@ -742,7 +733,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   }
   const int work = tiles * splits;
   const int grid = work < num_sms() ? work : num_sms();
-  gemm_sbf16_kernel<BLOCK_N, REL><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
+  gemm_sbf16_kernel<BLOCK_N, MODE, REL><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long n = (long long)M * ((N + 3) / 4);
@@ -763,6 +754,30 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, i
     planes[i] = h;
     planes[total + i] = l;
   }
+}
+
+
+// Picks the instantiation: tile width from the padded N, producer path from the operand source, relation epilogues
+// only where the epilogue descriptor asks for them.
+int dispatch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st, int groups,
+             int plane_rows, const GroupTab* gtab) {
+  static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
+  int bn = (Npad % 256 == 0) ? 256 : (Npad % 128 == 0 ? 128 : 64);
+  if (forced_bn == 64 || (forced_bn == 128 && Npad % 128 == 0)) bn = forced_bn;
+  const bool rel = ep.fin || ep.dot_w || ep.pair_n > 0;
+  const int mode = (a.mode == 0 && a.a2) ? 5 : a.mode;
+#define EGTR_GO(BN, MD, RL) return launch<BN, MD, RL>(a, planes, M, N, Npad, K, ep, st, groups, plane_rows, gtab)
+#define EGTR_BN(MD, RL) do { if (bn == 256) EGTR_GO(256, MD, RL); if (bn == 128) EGTR_GO(128, MD, RL); EGTR_GO(64, MD, RL); } while (0)
+  if (mode == 4) { if (bn == 256) EGTR_GO(256, 4, true); set_last_error("pair stage needs Npad %% 256 == 0"); return EGTR_ERR_ARG; }
+  if (rel) { if (mode == 0) EGTR_BN(0, true); set_last_error("relation epilogues are built for plain rows"); return EGTR_ERR_UNSUPPORTED; }
+  if (mode == 0) EGTR_BN(0, false);
+  if (mode == 5) EGTR_BN(5, false);
+  if (mode == 1) EGTR_BN(1, false);
+  if (mode == 3) EGTR_BN(3, false);
+#undef EGTR_BN
+#undef EGTR_GO
+  set_last_error("egtr_gemm_sbf16: operand mode %d has no tensor-core producer (use egtr_gemm_f32)", a.mode);
+  return EGTR_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -796,17 +811,7 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   EGTR_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)w_planes & 127) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16: alignment");
   count_launch();
   cudaStream_t st = (cudaStream_t)s;
-  static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
-  if (forced_bn == 128 && Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
-  if (forced_bn == 64) return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);
-  if (a->mode == 4 || ep->fin || ep->dot_w || ep->pair_n > 0) {  // relation-head instantiations
-    if (Npad % 256 == 0) return launch<256, true>(*a, w_planes, M, N, Npad, K, *ep, st);
-    if (Npad % 128 == 0) return launch<128, true>(*a, w_planes, M, N, Npad, K, *ep, st);
-    return launch<64, true>(*a, w_planes, M, N, Npad, K, *ep, st);
-  }
-  if (Npad % 256 == 0) return launch<256>(*a, w_planes, M, N, Npad, K, *ep, st);
-  if (Npad % 128 == 0) return launch<128>(*a, w_planes, M, N, Npad, K, *ep, st);
-  return launch<64>(*a, w_planes, M, N, Npad, K, *ep, st);
+  return dispatch(*a, w_planes, M, N, Npad, K, *ep, st, 1, 0, nullptr);
 }
 
 extern "C" int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* const* a2_ptrs, float* const* out_ptrs,
@@ -834,9 +839,9 @@ extern "C" int egtr_gemm_sbf16_grouped(const float* const* a_ptrs, const float* 
   a.lda = lda[0];
   count_launch();
   cudaStream_t st = (cudaStream_t)s;
-  if (Npad % 256 == 0) return launch<256>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
-  if (Npad % 128 == 0) return launch<128>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
-  return launch<64>(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
+  for (int g = 0; g < groups; ++g)
+    if (tab.a2[g]) a.a2 = tab.a2[g];  // any addend -> the addend-capable producer (groups without one skip it at run time)
+  return dispatch(a, w_planes, M, N, Npad, K, *ep, st, groups, plane_rows, &tab);
 }
 
 #ifdef EGTR_GEMM_PROF
