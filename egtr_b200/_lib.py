@@ -55,6 +55,8 @@ SIGNATURES = {
     "egtr_mha_core_f32": [_p, _i, _i, _i, _i, _i, _p, _p],
     "egtr_small_linear_f32": [_p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p],
     "egtr_relation_pair_hidden_f32": [_p, _p, _i, _p, _i, _i, _i, _p, _p],
+    "egtr_triplets_scratch_bytes": [_i, _i, _i, _i, _i],
+    "egtr_triplets_f32": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "egtr_argmax_rows_f32": [_p, _i, _i, _p, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }
@@ -63,6 +65,7 @@ _RESTYPES = {
     "egtr_launch_count": _ll,
     "egtr_launch_count_reset": None,
     "egtr_groupnorm_scratch_doubles": _ll,
+    "egtr_triplets_scratch_bytes": _ll,
 }
 _NO_STATUS = set(_RESTYPES) | {"egtr_abi_version"}
 

@@ -116,11 +116,13 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       float mx = logit;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float e = expf(logit - mx);
+      // softmax over 16 logits: ex2.approx + fast divide are within 2 ulp — far inside the 1e-3 parity bar and cheap
+      // enough that phase 1 stops being a third of the kernel's instruction count
+      const float e = __expf(logit - mx);
       float sum = e;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      wgt = e / sum;
+      wgt = __fdividef(e, sum);
     }
     if (q >= 0) {
       const int H = lvH[l], W = lvW[l];
@@ -140,8 +142,8 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
           const float* vr = a.valid_ratios + (long long)b * L * 2;
           rx = r.x * vr[l * 2 + 0]; ry = r.y * vr[l * 2 + 1];
         }
-        lx = rx + off.x / (float)W;  // deformable_detr.py:1066-1073
-        ly = ry + off.y / (float)H;
+        lx = rx + __fdividef(off.x, (float)W);  // deformable_detr.py:1066-1073 (offset / (W_l, H_l))
+        ly = ry + __fdividef(off.y, (float)H);
       } else {
         const long long base = (((long long)b * a.Lq + q) * a.M + m) * 16 + s;
         const float2 lc = *(const float2*)(a.loc + base * 2);

@@ -186,6 +186,18 @@ int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, const float* c
                              float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
                              int* cls_scratch /* B*N ints */, float* pred_rel, float* pred_conn, egtr_stream_t s);
 
+/* ---------------------------------------------------------------- triplet extraction */
+/* Device-side equivalent of the model-output post-processing in train_egtr.py:56-94 (multiple predicates per pair,
+ * single == 0) and 56-69 + 120-128 (one entry per pair, single == 1): object scores/classes from softmax(logits)
+ * [:, :num_labels], sub_ob = outer(obj, obj) without diagonal, rel = clamp(pred_rel) * clamp(pred_conn) (pred_conn
+ * may be NULL), top-k of rel * sub_ob (resp. max_p rel * sub_ob) by a radix select instead of a full argsort.
+ * Outputs: obj_scores [B,N], pred_classes [B,N] int32, rel_inds [B,k,3] (s,o,p) or [B,k,2] (s,o) int32 sorted by
+ * descending score, rel_scores [B,k] or [B,k,P].  scratch: egtr_triplets_scratch_bytes() bytes of device memory. */
+long long egtr_triplets_scratch_bytes(int B, int N, int P, int single, int k);
+int egtr_triplets_f32(const float* logits, const float* pred_rel, const float* pred_conn, int B, int N, int K,
+                      int num_labels, int P, int single, int k, void* scratch, float* obj_scores, int* pred_classes,
+                      int* rel_inds, float* rel_scores, egtr_stream_t s);
+
 /* out[r] = argmax over x[r, :cols], first maximum wins (torch.argmax; model/egtr.py:406). */
 int egtr_argmax_rows_f32(const float* x, int cols, int rows, int* out, egtr_stream_t s);
 
