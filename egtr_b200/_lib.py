@@ -19,7 +19,7 @@ class EgtrError(RuntimeError):
 class ASrc(C.Structure):
     _fields_ = [("a", C.c_void_p), ("a2", C.c_void_p), ("mode", C.c_int), ("lda", C.c_int),
                 ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
-                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("aux", C.c_void_p)]
+                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("aux", C.c_void_p), ("fmt", C.c_int)]
 
 
 class Epilogue(C.Structure):
@@ -27,7 +27,11 @@ class Epilogue(C.Structure):
                 ("ldr", C.c_int), ("relu", C.c_int), ("rows_per_b", C.c_int), ("bstride", C.c_int),
                 ("off", C.c_int), ("row_keep", C.c_void_p),
                 ("pair_n", C.c_int), ("dot_w", C.c_void_p), ("dot_out", C.c_void_p), ("dot_b", C.c_float), ("dot_col0", C.c_int),
-                ("fin", C.c_int), ("fin_n", C.c_int), ("cls", C.c_void_p), ("triplet", C.c_void_p), ("adj", C.c_void_p), ("k1", C.c_int)]
+                ("fin", C.c_int), ("fin_n", C.c_int), ("cls", C.c_void_p), ("triplet", C.c_void_p), ("adj", C.c_void_p), ("k1", C.c_int),
+                ("out_fmt", C.c_int), ("res_fmt", C.c_int)]
+
+
+FMT_F32, FMT_P32 = 0, 1
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -46,6 +50,10 @@ SIGNATURES = {
     "egtr_msda_fwd_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "egtr_msda_fused_fwd_f32": [_p, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "egtr_add_layernorm_f32": [_p, _p, _p, _p, _i, _i, _p, _p],
+    "egtr_add_layernorm_p32": [_p, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "egtr_rows_to_p32": [_p, _p, _i, _i, _i, _p, _p],
+    "egtr_p32_to_rows": [_p, _i, _i, _p, _i, _p],
+    "egtr_msda_fused_fwd_ex": [_p, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "egtr_mask_rows_f32": [_p, _i, _i, _p, _i, _p],
     "egtr_pad_nchw3_to_nhwc4_f32": [_p, _i, _i, _i, _i, _p, _p],
     "egtr_maxpool3x3s2_nhwc_f32": [_p, _i, _i, _i, _i, _p, _p],

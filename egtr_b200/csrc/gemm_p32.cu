@@ -1,0 +1,559 @@
+// D[M,N] = A[M,K] * W[N,K]^T (+bias, +residual, ReLU, row mask) on tcgen05 with BOTH operands fed by TMA.
+//
+// Activations between GEMM-class kernels live in HBM in the "P32" row format: an fp32 [rows, C] matrix
+// stored with the same 4*C-byte row pitch, every group of 32 channels = 128 bytes = 32 bf16 hi values
+// followed by 32 bf16 lo values (x ~= hi + lo to 2^-17, exactly the split the bf16x3 product scheme of
+// gemm_tc.cu performs in registers).  Writing the split once in the producing kernel's epilogue means the
+// consuming GEMM needs no operand-producer warps at all: one 128 x 128-byte SW128 TMA box per channel
+// group lands hi in 16-byte chunks 0-3 and lo in chunks 4-7 of each smem row, and the UMMA descriptors of
+// the hi / lo operands are the same tile at byte offsets 0 / 64 (+32 for the second 16-wide k-step).
+//
+// Roles (persistent, one CTA per SM, 320 threads):
+//   warps 0-7  epilogue : two warps per TMEM lane quadrant, each owns half of the tile's columns;
+//                         tcgen05.ld 32x32 -> bias / residual / ReLU / mask -> fp32 or P32 packing ->
+//                         st.shared into a 4 KB SW128 staging box -> TMA store (clips the M tail);
+//                         residual boxes are TMA-loaded into the same staging box beforehand.
+//   warp  8    TMA      : per k-block 2 activation boxes + weight hi/lo boxes into the stage ring.
+//   warp  9    MMA      : one lane issues 12 tcgen05.mma per k-block; owns the TMEM allocation
+//                         (two accumulator stages so the epilogue of tile t overlaps the MMAs of t+1).
+#include <cuda.h>
+
+#include <mutex>
+#include <string.h>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace egtr {
+
+void count_launch();
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int TMA_WARP = 8, MMA_WARP = 9;
+constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
+constexpr int A_GROUP_BYTES = BLOCK_M * 128;  // one 32-channel group of 128 rows: hi 64 B | lo 64 B per row
+constexpr int STG_BYTES = 32 * 128;           // one epilogue box: 32 rows x 32 channels
+
+template <int BLOCK_N>
+struct PCfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * A_GROUP_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int CTRL_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + 1024 /*align slack*/;
+  static constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per epilogue warp (half of the tile's columns)
+};
+
+struct PArgs {
+  const float* bias;
+  const uint8_t* row_keep;
+  int M, N, K;
+  int rows_per_b, nb;     // rows are nb batches of rows_per_b (tiles never straddle a batch)
+  int keep_bstride, keep_off;
+  int relu, out_fmt, res_fmt, has_res;
+  int splits, kb_per_split, plane_rows;
+  int ncols;              // columns that exist in the output map (N, or Npad for split-K partial sums)
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(ptx::smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {  // low 16 bits = first element
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const PArgs p,
+                int* __restrict__ err) {
+  using C = PCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stg_all = smem + C::STAGES * C::STAGE_BYTES;         // [EPI_WARPS][4096], 1024-aligned
+  uint8_t* ctrl = stg_all + EPI_WARPS * STG_BYTES;
+  uint64_t* full_bar = (uint64_t*)ctrl;          // [STAGES]
+  uint64_t* empty_bar = full_bar + 4;            // [STAGES]
+  uint64_t* tmem_full = empty_bar + 4;           // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* res_bar = tmem_empty + 2;            // [EPI_WARPS]
+  uint32_t* tmem_holder = (uint32_t*)(res_bar + EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtiles_per_b = (p.rows_per_b + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = mtiles_per_b * p.nb;
+  const int n_tiles = (p.ncols + BLOCK_N - 1) / BLOCK_N;
+  const int total = m_tiles * n_tiles * p.splits;
+  const int k_blocks_all = p.K / BLOCK_K;
+
+  if (warp == TMA_WARP && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_w);
+    ptx::prefetch_tensormap(&tmap_out);
+    if (p.has_res) ptx::prefetch_tensormap(&tmap_res);
+    for (int i = 0; i < C::STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);   // the TMA thread's expect_tx arrive
+      ptx::mbar_init(&empty_bar[i], 1);  // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], EPI_WARPS * 32);
+    }
+    for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == MMA_WARP) ptx::tmem_alloc<C::TMEM_COLS>(tmem_holder);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------------ TMA: activation groups + weight tiles
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tg = w / p.splits, sp = w - tg * p.splits;
+        const int mt = tg / n_tiles, nt = tg - mt * n_tiles;
+        const int b = mt / mtiles_per_b, m0 = (mt - b * mtiles_per_b) * BLOCK_M;
+        const int n0 = nt * BLOCK_N;
+        const int kb_lo = sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 201);
+          const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_3d(st, &tmap_a, &full_bar[stage], kb * 128, m0, b);
+          tma_load_3d(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], kb * 128 + 64, m0, b);
+          ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
+          ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage],
+                           kb * BLOCK_K, p.plane_rows + n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0, phase = 0, it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int sp = w % p.splits;
+      const int kb_lo = sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, err, 202);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase, err, 203);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_hi = a0 + 2 * A_GROUP_BYTES;
+          const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 16-wide k-steps: channel group ks>>1, half (ks&1) of its 32 channels
+            const uint32_t at = a0 + (ks >> 1) * A_GROUP_BYTES + (ks & 1) * 32;
+            const uint64_t dah = ptx::umma_desc_sw128(at), dal = ptx::umma_desc_sw128(at + 64);
+            const uint64_t dbh = ptx::umma_desc_sw128(b_hi + ks * 32), dbl = ptx::umma_desc_sw128(b_lo + ks * 32);
+            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb != kb_lo) || (ks != 0));  // small terms first
+            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (kb == kb_hi - 1) ptx::umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;    // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
+    const int hf = warp >> 2;  // column half
+    uint8_t* stg = stg_all + warp * STG_BYTES;
+    const uint32_t stg_s = ptx::smem_u32(stg);
+    const uint32_t my_row_s = stg_s + lane * 128;
+    const int sw = lane & 7;
+    uint64_t* rbar = &res_bar[warp];
+    uint32_t res_phase = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tg = w / p.splits, sp = w - tg * p.splits;
+      const int mt = tg / n_tiles, nt = tg - mt * n_tiles;
+      const int b = mt / mtiles_per_b, m0 = (mt - b * mtiles_per_b) * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int row0 = m0 + q * 32;        // first row (inside batch b) of this warp's slab
+      const int zc = p.splits > 1 ? sp : b;  // third output coordinate
+      const int col_base = n0 + hf * (BLOCK_N / 2);
+      int nch = (p.ncols - col_base + 31) / 32;
+      nch = nch < 0 ? 0 : (nch > C::CHUNKS ? C::CHUNKS : nch);
+      if (row0 >= p.rows_per_b) nch = 0;  // slab entirely in the M tail: nothing to store
+      bool keep = true;
+      if (p.row_keep != nullptr && nch > 0 && row0 + lane < p.rows_per_b)
+        keep = p.row_keep[(long long)b * p.keep_bstride + p.keep_off + row0 + lane] != 0;
+      if (p.has_res && nch > 0 && lane == 0) {  // first residual box of the tile, in flight while the MMAs run
+        ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
+        tma_load_3d(stg_s, &tmap_res, rbar, col_base, row0, zc);
+      }
+      ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 205);
+      ptx::tc_fence_after();
+      if (nch == 0) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * (BLOCK_N / 2), r);
+#pragma unroll 1
+      for (int ci = 0; ci < nch; ++ci) {
+        const int n = col_base + ci * 32;
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r[j]));  // uses of r must not be scheduled above the wait
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ci + 1 < nch) {  // next chunk's accumulator read overlaps this chunk's arithmetic and store
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * (BLOCK_N / 2) + (ci + 1) * 32, r);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg((const float4*)(p.bias + n) + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+        if (p.has_res) {
+          ptx::mbar_wait(rbar, res_phase, err, 206);
+          res_phase ^= 1;
+          uint32_t x[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                         : "r"(my_row_s + ((c ^ sw) << 4)) : "memory");
+          if (p.res_fmt == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(x[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] += __uint_as_float(x[j] << 16) + __uint_as_float(x[16 + j] << 16);
+              v[2 * j + 1] += __uint_as_float(x[j] & 0xffff0000u) + __uint_as_float(x[16 + j] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (!keep) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        uint32_t o[32];
+        if (p.out_fmt == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t h = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            const float l0 = v[2 * j] - __uint_as_float(h << 16), l1 = v[2 * j + 1] - __uint_as_float(h & 0xffff0000u);
+            o[j] = h;
+            o[16 + j] = pack_bf16x2(l0, l1);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_s + ((c ^ sw) << 4)), "r"(o[4 * c]), "r"(o[4 * c + 1]),
+                       "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_out, stg_s, n, row0, zc);
+          bulk_commit();
+          bulk_wait_read0();  // the staging box may be overwritten once TMA has read it
+          if (p.has_res && ci + 1 < nch) {
+            ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
+            tma_load_3d(stg_s, &tmap_res, rbar, n + 32, row0, zc);
+          }
+        }
+        __syncwarp();
+        if (ci + 1 == nch) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait0();  // all stores of this warp have left shared memory and are complete
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// --------------------------------------------------------------------------- split-K reduction
+// out = epilogue(sum over splits of partial[s][m][n]); one warp per (row, 32-channel group), lane = channel.
+struct ReduceArgs {
+  const float* partial;
+  int splits, M, N, Npad;
+  const float* bias;
+  const void* res;
+  void* out;
+  int ldo, ldr, relu, out_fmt, res_fmt;
+  const uint8_t* row_keep;
+};
+
+__device__ __forceinline__ float p32_load(const void* base, long long row, int ld, int col) {
+  const __nv_bfloat16* g = (const __nv_bfloat16*)((const uint8_t*)base + (row * ld + (col & ~31)) * 4);
+  return __bfloat162float(g[col & 31]) + __bfloat162float(g[32 + (col & 31)]);
+}
+
+__global__ void __launch_bounds__(256)
+p32_reduce_kernel(const ReduceArgs a) {
+  const int groups = a.N / 32;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)a.M * groups) return;
+  const long long m = wid / groups;
+  const int n = (int)(wid - m * groups) * 32 + lane;
+  float acc = 0.f;
+  for (int s = 0; s < a.splits; ++s) acc += a.partial[((long long)s * a.M + m) * a.Npad + n];
+  if (a.bias) acc += __ldg(a.bias + n);
+  if (a.res) acc += a.res_fmt ? p32_load(a.res, m, a.ldr, n) : ((const float*)a.res)[m * a.ldr + n];
+  if (a.relu) acc = fmaxf(acc, 0.f);
+  if (a.row_keep && !a.row_keep[m]) acc = 0.f;
+  if (a.out_fmt == 0) {
+    ((float*)a.out)[m * a.ldo + n] = acc;
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+    const __nv_bfloat16 l = __float2bfloat16_rn(acc - __bfloat162float(h));
+    __nv_bfloat16* g = (__nv_bfloat16*)((uint8_t*)a.out + (m * a.ldo + (n & ~31)) * 4);
+    g[lane] = h;
+    g[32 + lane] = l;
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  });
+  return fn;
+}
+
+struct MapDesc {  // everything that determines a tensor map (POD, zero-initialised, compared bytewise)
+  const void* ptr;
+  unsigned long long dim[3], stride[2];
+  unsigned box[3];
+  int dtype, rank;
+};
+struct MapDescHash {
+  size_t operator()(const MapDesc& d) const {
+    const unsigned char* b = (const unsigned char*)&d;
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapDesc); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+  }
+};
+struct MapDescEq {
+  bool operator()(const MapDesc& a, const MapDesc& b) const { return memcmp(&a, &b, sizeof(MapDesc)) == 0; }
+};
+
+// Tensor maps are immutable per (pointer, geometry): encode once, reuse for every launch (workspaces are persistent).
+int cached_map(const MapDesc& d, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapDesc, CUtensorMap, MapDescHash, MapDescEq> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(d);
+  if (it != cache.end()) {
+    *out = it->second;
+    return EGTR_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  EGTR_CHECK(enc != nullptr, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {d.dim[0], d.dim[1], d.dim[2]};
+  cuuint64_t gstride[2] = {d.stride[0], d.stride[1]};
+  cuuint32_t box[3] = {d.box[0], d.box[1], d.box[2]};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, (CUtensorMapDataType)d.dtype, (cuuint32_t)d.rank, const_cast<void*>(d.ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA,
+             "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
+             d.rank, d.dim[0], d.dim[1], d.dim[2], d.stride[0], d.stride[1], d.box[0], d.box[1], d.box[2]);
+  cache.emplace(d, m);
+  *out = m;
+  return EGTR_OK;
+}
+
+MapDesc make_desc(const void* ptr, int dtype, int rank, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                  unsigned long long s0, unsigned long long s1, unsigned b0, unsigned b1) {
+  MapDesc d;
+  memset(&d, 0, sizeof(d));
+  d.ptr = ptr; d.dtype = dtype; d.rank = rank;
+  d.dim[0] = d0; d.dim[1] = d1; d.dim[2] = d2;
+  d.stride[0] = s0; d.stride[1] = s1;
+  d.box[0] = b0; d.box[1] = b1; d.box[2] = 1;
+  return d;
+}
+
+int* device_error_flag_p32() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+float* partial_buffer_p32(size_t floats) {  // grow-only; older buffers stay alive for captured graphs
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    float* nb = nullptr;
+    const size_t want = floats + floats / 2;
+    if (cudaMalloc(&nb, want * sizeof(float)) != cudaSuccess) return nullptr;
+    buf = nb;
+    cap = want;
+  }
+  return buf;
+}
+
+template <int BLOCK_N>
+int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
+               cudaStream_t st) {
+  using C = PCfg<BLOCK_N>;
+  const int rows_per_b = ep.rows_per_b > 0 ? ep.rows_per_b : M;
+  const int nb = M / rows_per_b;
+  const int m_tiles = cdiv(rows_per_b, BLOCK_M) * nb;
+  const int n_tiles = cdiv(N, BLOCK_N);
+  const int k_blocks = K / BLOCK_K;
+  int splits = 1;
+  if (nb == 1 && m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
+    splits = num_sms() / (m_tiles * n_tiles);
+    if (splits > k_blocks / 4) splits = k_blocks / 4;
+    if (splits < 1) splits = 1;
+  }
+  const int kbps = cdiv(k_blocks, splits);
+  splits = cdiv(k_blocks, kbps);
+
+  PArgs p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.rows_per_b = rows_per_b; p.nb = nb;
+  p.splits = splits; p.kb_per_split = kbps; p.plane_rows = plane_rows;
+  CUtensorMap ta, tw, to, tr;
+  int rc = cached_map(make_desc(a.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, 2ull * K, rows_per_b, nb, 4ull * a.lda,
+                                4ull * a.lda * rows_per_b, 64, BLOCK_M), &ta);
+  if (rc != EGTR_OK) return rc;
+  rc = cached_map(make_desc(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, 2ull * plane_rows, 1, 2ull * K, 0, BLOCK_K, BLOCK_N), &tw);
+  if (rc != EGTR_OK) return rc;
+  const int n_cols32 = cdiv(N, 32) * 32;
+  float* partial = nullptr;
+  if (splits > 1) {
+    partial = partial_buffer_p32((size_t)splits * M * Npad);
+    EGTR_CHECK(partial != nullptr, EGTR_ERR_CUDA, "split-K scratch allocation failed");
+    rc = cached_map(make_desc(partial, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, Npad, M, splits, 4ull * Npad, 4ull * Npad * M, 32, 32), &to);
+    if (rc != EGTR_OK) return rc;
+    tr = to;
+    p.ncols = Npad;
+  } else {
+    const unsigned long long bstride = ep.rows_per_b > 0 ? (unsigned long long)ep.bstride : (unsigned long long)rows_per_b;
+    const uint8_t* obase = (const uint8_t*)ep.out + 4ll * ep.off * ep.ldo;
+    rc = cached_map(make_desc(obase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, n_cols32, rows_per_b, nb, 4ull * ep.ldo, 4ull * ep.ldo * bstride, 32, 32), &to);
+    if (rc != EGTR_OK) return rc;
+    tr = to;
+    if (ep.res != nullptr) {
+      const uint8_t* rbase = (const uint8_t*)ep.res + 4ll * ep.off * ep.ldr;
+      rc = cached_map(make_desc(rbase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, n_cols32, rows_per_b, nb, 4ull * ep.ldr, 4ull * ep.ldr * bstride, 32, 32), &tr);
+      if (rc != EGTR_OK) return rc;
+      p.has_res = 1;
+      p.res_fmt = ep.res_fmt;
+    }
+    p.bias = ep.bias;
+    p.row_keep = ep.row_keep;
+    p.keep_bstride = (int)bstride;
+    p.keep_off = ep.off;
+    p.relu = ep.relu;
+    p.out_fmt = ep.out_fmt;
+    p.ncols = N;
+  }
+  static bool attr_set = false;  // one flag per instantiation
+  if (!attr_set) {
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int work = m_tiles * cdiv(p.ncols, BLOCK_N) * splits;
+  const int grid = work < num_sms() ? work : num_sms();
+  gemm_p32_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tw, to, tr, p, device_error_flag_p32());
+  EGTR_CUDA(cudaGetLastError());
+  if (splits > 1) {
+    ReduceArgs r = {};
+    r.partial = partial; r.splits = splits; r.M = M; r.N = N; r.Npad = Npad;
+    r.bias = ep.bias; r.res = ep.res; r.out = ep.out; r.ldo = ep.ldo; r.ldr = ep.ldr; r.relu = ep.relu;
+    r.out_fmt = ep.out_fmt; r.res_fmt = ep.res_fmt; r.row_keep = ep.row_keep;
+    const long long threads = (long long)M * (N / 32) * 32;
+    p32_reduce_kernel<<<cdiv(threads, 256), 256, 0, st>>>(r);
+    count_launch();
+    EGTR_CUDA(cudaGetLastError());
+  }
+  return EGTR_OK;
+}
+
+}  // namespace
+
+// Entry used by egtr_gemm_sbf16 when the operand source is P32 rows (a.fmt == 1, mode 0).
+int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
+                      cudaStream_t st) {
+  EGTR_CHECK(a.a2 == nullptr && a.mode == 0, EGTR_ERR_UNSUPPORTED, "P32 operand rows: plain rows only (fold addends into the producer)");
+  EGTR_CHECK(N % 32 == 0 && K % 64 == 0 && a.lda % 4 == 0 && a.lda >= K && ep.ldo % 4 == 0 && ep.ldo >= N, EGTR_ERR_ARG,
+             "egtr_gemm_sbf16 (P32 rows): need N %% 32 == 0, K %% 64 == 0, 16-byte row pitches (N=%d K=%d lda=%d ldo=%d)", N, K, a.lda, ep.ldo);
+  EGTR_CHECK(((uintptr_t)a.a & 127) == 0 && ((uintptr_t)ep.out & 127) == 0 && (!ep.res || ((uintptr_t)ep.res & 127) == 0) && ((uintptr_t)planes & 127) == 0,
+             EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): 128-byte aligned buffers required");
+  EGTR_CHECK(!ep.res || (ep.ldr % 4 == 0 && ep.ldr >= N), EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): ldr=%d", ep.ldr);
+  EGTR_CHECK(ep.pair_n == 0 && !ep.fin && !ep.dot_w, EGTR_ERR_UNSUPPORTED, "egtr_gemm_sbf16 (P32 rows): relation epilogues are not built here");
+  EGTR_CHECK(ep.rows_per_b <= 0 || M % ep.rows_per_b == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): M %% rows_per_b != 0");
+  static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
+  int bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N >= 192 ? 128 : 64));
+  if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
+  if (bn == 256) return launch_p32<256>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  if (bn == 128) return launch_p32<128>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  return launch_p32<64>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+}
+
+}  // namespace egtr

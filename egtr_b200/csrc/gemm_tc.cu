@@ -31,6 +31,8 @@
 namespace egtr {
 
 void count_launch();
+int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
+                      cudaStream_t st);  // gemm_p32.cu: TMA-fed operand rows
 
 namespace {
 
@@ -811,6 +813,9 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   EGTR_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)w_planes & 127) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16: alignment");
   count_launch();
   cudaStream_t st = (cudaStream_t)s;
+  if (a->fmt == EGTR_FMT_P32) return gemm_p32_dispatch(*a, w_planes, Npad, M, N, Npad, K, *ep, st);
+  EGTR_CHECK(ep->out_fmt == EGTR_FMT_F32 && ep->res_fmt == EGTR_FMT_F32, EGTR_ERR_UNSUPPORTED,
+             "egtr_gemm_sbf16: P32 outputs / residuals are written by the P32-operand kernel only");
   return dispatch(*a, w_planes, M, N, Npad, K, *ep, st, 1, 0, nullptr);
 }
 

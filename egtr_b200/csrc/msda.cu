@@ -42,6 +42,7 @@ struct MsdaArgs {
   const int64_t* dev_shapes;              // drop-in: [L,2] int64 on device
   const int64_t* dev_start;               // drop-in: [L] int64 on device
   float* out;                             // [B,Lq,M*32]
+  int out_fmt;                            // 1: P32 rows (one head = one 32-channel group: hi 64 B | lo 64 B)
   int B, S, M, Lq;
   int enc_patches;                        // 1: queries are the S tokens, enumerated in 8x4 patches
 };
@@ -189,7 +190,21 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
     acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y); acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
   }
-  *(float4*)(a.out + ((long long)b * a.Lq + q) * (a.M * 32) + m * 32 + c4) = acc;
+  float* orow = a.out + ((long long)b * a.Lq + q) * (a.M * 32) + m * 32;
+  if (a.out_fmt == 0) {
+    *(float4*)(orow + c4) = acc;
+  } else {
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    split_bf16(acc.x, h0, l0); split_bf16(acc.y, h1, l1); split_bf16(acc.z, h2, l2); split_bf16(acc.w, h3, l3);
+    uint2 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+    uint8_t* g = (uint8_t*)orow + c4 * 2;
+    *(uint2*)g = ph;
+    *(uint2*)(g + 64) = pl;
+  }
 }
 
 int fill_levels(const int* shapes_hw, int L, Levels* lv, int* S_out) {
@@ -241,6 +256,14 @@ extern "C" int egtr_msda_fwd_f32(const float* value, const int64_t* spatial_shap
 extern "C" int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
                                        int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
                                        int B, int S, int M, int D, int L, int Lq, int P, float* out, egtr_stream_t s) {
+  return egtr_msda_fused_fwd_ex(value, ld_value, shapes_hw, offaw, ld_offaw, ref_points, valid_ratios, enc_ref, B, S, M, D, L, Lq,
+                                P, out, EGTR_FMT_F32, s);
+}
+
+extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
+                                      int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                                      int B, int S, int M, int D, int L, int Lq, int P, void* out_v, int out_fmt, egtr_stream_t s) {
+  float* out = (float*)out_v;
   EGTR_CHECK(value && shapes_hw && offaw && out, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: null pointer");
   EGTR_CHECK(valid_ratios != nullptr && (enc_ref || ref_points != nullptr), EGTR_ERR_ARG,
              "egtr_msda_fused_fwd_f32: reference points missing");
@@ -258,7 +281,7 @@ extern "C" int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const i
   a.value = value; a.ld_value = ld_value;
   a.offaw = offaw; a.ld_offaw = ld_offaw;
   a.ref_points = ref_points; a.valid_ratios = valid_ratios;
-  a.out = out; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
+  a.out = out; a.out_fmt = out_fmt; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
   dim3 grid(enc_ref ? patches : cdiv(Lq, QPB), M, B);
   msda_kernel<true><<<grid, 256, 0, (cudaStream_t)s>>>(a, lv);
   count_launch();

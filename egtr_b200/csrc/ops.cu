@@ -37,6 +37,106 @@ add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ r
   op[lane + 32] = o1;
 }
 
+// ------------------------------------------------------------------ P32 rows (include/egtr_b200.h)
+// four consecutive channels c..c+3 (c % 4 == 0) of a row: hi at byte (c/32)*128 + (c%32)*2, lo 64 bytes further
+__device__ __forceinline__ void p32_store4(uint8_t* row, int c, const float4& v) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  uint2 ph, pl;
+  ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  uint8_t* g = row + (c >> 5) * 128 + (c & 31) * 2;
+  *(uint2*)g = ph;
+  *(uint2*)(g + 64) = pl;
+}
+__device__ __forceinline__ float4 p32_load4(const uint8_t* row, int c) {
+  const uint8_t* g = row + (c >> 5) * 128 + (c & 31) * 2;
+  const uint2 ph = *(const uint2*)g, pl = *(const uint2*)(g + 64);
+  float4 v;
+  v.x = __uint_as_float(ph.x << 16) + __uint_as_float(pl.x << 16);
+  v.y = __uint_as_float(ph.x & 0xffff0000u) + __uint_as_float(pl.x & 0xffff0000u);
+  v.z = __uint_as_float(ph.y << 16) + __uint_as_float(pl.y << 16);
+  v.w = __uint_as_float(ph.y & 0xffff0000u) + __uint_as_float(pl.y & 0xffff0000u);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+rows_to_p32_kernel(const float* __restrict__ x, const float* __restrict__ addend, long long rows, int C4, int ldx, uint8_t* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = i / C4;
+  if (row >= rows) return;
+  const int c = (int)(i - row * C4) * 4;
+  float4 v = *(const float4*)(x + row * ldx + c);
+  if (addend) {
+    const float4 a = *(const float4*)(addend + row * ldx + c);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  p32_store4(out + row * (long long)C4 * 16, c, v);
+}
+
+__global__ void __launch_bounds__(256)
+p32_to_rows_kernel(const uint8_t* __restrict__ p32, long long rows, int C4, float* __restrict__ out, int ldo) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long row = i / C4;
+  if (row >= rows) return;
+  const int c = (int)(i - row * C4) * 4;
+  *(float4*)(out + row * ldo + c) = p32_load4(p32 + row * (long long)C4 * 16, c);
+}
+
+// LayerNorm(x + res) with P32 / fp32 outputs and the optional "+ addend" second P32 output (next layer's x + pos)
+__global__ void __launch_bounds__(256)
+add_layernorm256_p32_kernel(const float* __restrict__ x, const uint8_t* __restrict__ res, int res_fmt, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, int rows, uint8_t* __restrict__ out_p32, float* __restrict__ out_f32,
+                            const float* __restrict__ addend, uint8_t* __restrict__ out_plus) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  const float4* xp = (const float4*)(x + (long long)row * 256);
+  float4 a = xp[lane], b = xp[lane + 32];
+  if (res) {
+    float4 c, d;
+    if (res_fmt) {
+      c = p32_load4(res + (long long)row * 1024, c0);
+      d = p32_load4(res + (long long)row * 1024, c1);
+    } else {
+      const float4* rp = (const float4*)(res + (long long)row * 1024);
+      c = rp[lane]; d = rp[lane + 32];
+    }
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+  const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / 256.f);
+  a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+  b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+  const float var = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w) * (1.f / 256.f);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  const float4 g0 = ((const float4*)gamma)[lane], g1 = ((const float4*)gamma)[lane + 32];
+  const float4 b0 = ((const float4*)beta)[lane], b1 = ((const float4*)beta)[lane + 32];
+  float4 o0, o1;
+  o0.x = a.x * rstd * g0.x + b0.x; o0.y = a.y * rstd * g0.y + b0.y; o0.z = a.z * rstd * g0.z + b0.z; o0.w = a.w * rstd * g0.w + b0.w;
+  o1.x = b.x * rstd * g1.x + b1.x; o1.y = b.y * rstd * g1.y + b1.y; o1.z = b.z * rstd * g1.z + b1.z; o1.w = b.w * rstd * g1.w + b1.w;
+  if (out_f32) {
+    float4* op = (float4*)(out_f32 + (long long)row * 256);
+    op[lane] = o0;
+    op[lane + 32] = o1;
+  }
+  if (out_p32) {
+    p32_store4(out_p32 + (long long)row * 1024, c0, o0);
+    p32_store4(out_p32 + (long long)row * 1024, c1, o1);
+  }
+  if (out_plus) {
+    const float4* ap = (const float4*)(addend + (long long)row * 256);
+    const float4 p0 = ap[lane], p1 = ap[lane + 32];
+    o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+    o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+    p32_store4(out_plus + (long long)row * 1024, c0, o0);
+    p32_store4(out_plus + (long long)row * 1024, c1, o1);
+  }
+}
+
 // ------------------------------------------------------------------ zero masked rows
 __global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const uint8_t* __restrict__ keep, long long rows) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -338,6 +438,36 @@ extern "C" int egtr_add_layernorm_f32(const float* x, const float* res, const fl
   EGTR_CHECK(x && gamma && beta && out && rows > 0, EGTR_ERR_ARG, "egtr_add_layernorm_f32: bad arguments");
   EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_f32: built for d_model 256 (got %d)", C);
   add_layernorm256_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, res, gamma, beta, rows, out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_add_layernorm_p32(const float* x, const void* res, int res_fmt, const float* gamma, const float* beta, int rows,
+                                      int C, void* out_p32, float* out_f32, const float* addend, void* out_plus_p32, egtr_stream_t s) {
+  EGTR_CHECK(x && gamma && beta && rows > 0 && (out_p32 || out_f32 || out_plus_p32), EGTR_ERR_ARG, "egtr_add_layernorm_p32: bad arguments");
+  EGTR_CHECK(!out_plus_p32 || addend, EGTR_ERR_ARG, "egtr_add_layernorm_p32: out_plus_p32 needs an addend");
+  EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_p32: built for d_model 256 (got %d)", C);
+  add_layernorm256_p32_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, (const uint8_t*)res, res_fmt, gamma, beta, rows,
+                                                                         (uint8_t*)out_p32, out_f32, addend, (uint8_t*)out_plus_p32);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_rows_to_p32(const float* x, const float* addend, int rows, int C, int ldx, void* out, egtr_stream_t s) {
+  EGTR_CHECK(x && out && rows > 0 && C > 0 && C % 32 == 0 && ldx % 4 == 0 && ldx >= C, EGTR_ERR_ARG, "egtr_rows_to_p32: bad arguments (C=%d ldx=%d)", C, ldx);
+  const long long total = (long long)rows * (C / 4);
+  rows_to_p32_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, addend, rows, C / 4, ldx, (uint8_t*)out);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_p32_to_rows(const void* p32, int rows, int C, float* out, int ldo, egtr_stream_t s) {
+  EGTR_CHECK(p32 && out && rows > 0 && C > 0 && C % 32 == 0 && ldo % 4 == 0 && ldo >= C, EGTR_ERR_ARG, "egtr_p32_to_rows: bad arguments (C=%d ldo=%d)", C, ldo);
+  const long long total = (long long)rows * (C / 4);
+  p32_to_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>((const uint8_t*)p32, rows, C / 4, out, ldo);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

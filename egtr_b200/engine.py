@@ -284,7 +284,10 @@ class Engine:
     def gemm(self, lin: Lin, M: int, out: torch.Tensor, *, a: Optional[torch.Tensor] = None, lda: Optional[int] = None,
              a_col: int = 0, a2: Optional[torch.Tensor] = None, conv: Optional[dict] = None, relu: bool = False,
              res: Optional[torch.Tensor] = None, ldr: int = 0, ldo: Optional[int] = None, out_col: int = 0,
-             remap: Optional[Tuple[int, int, int]] = None, row_keep: Optional[torch.Tensor] = None):
+             remap: Optional[Tuple[int, int, int]] = None, row_keep: Optional[torch.Tensor] = None,
+             a_fmt: int = 0, out_fmt: int = 0, res_fmt: int = 0):
+        """`a_fmt`/`out_fmt`/`res_fmt` = 1: the tensor is stored as P32 rows (include/egtr_b200.h); a P32 operand takes the
+        TMA-fed tcgen05 kernel (gemm_p32.cu)."""
         src = ASrc()
         if conv is None:
             src.a, src.a2, src.mode = _ptr(a, a_col), _ptr(a2, a_col), 0
@@ -300,6 +303,11 @@ class Engine:
         ep.relu = int(relu)
         ep.rows_per_b, ep.bstride, ep.off = remap if remap else (0, 0, 0)
         ep.row_keep = _ptr(row_keep)
+        src.fmt, ep.out_fmt, ep.res_fmt = a_fmt, out_fmt, res_fmt
+        if a_fmt == 1:
+            assert conv is None and a2 is None
+            call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+            return
         if gemm_backend() == "simt":
             call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
         elif conv is None and _skinny(M, lin.N, 1):
@@ -364,7 +372,7 @@ class Engine:
         ws["geo_scratch"] = torch.empty(2 * B * S, **f32)
         gn = max(call("egtr_groupnorm_scratch_doubles", B, h * w) for h, w in shapes)
         ws["gn_scratch"] = torch.empty(int(gn), dtype=torch.float64, device=dev)
-        ws["x"] = [torch.empty(B * S, 256, **f32) for _ in range(3)]
+        ws["x"] = [torch.empty(B * S, 256, **f32) for _ in range(5)]
         ws["offaw"] = torch.empty(B * S, 384, **f32)
         ws["value"] = torch.empty(B * S, 256, **f32)
         ws["attn"] = torch.empty(B * S, 256, **f32)
@@ -475,23 +483,53 @@ class Engine:
         # ---- encoder (deformable_detr.py:1283-1358)
         _sp_enc = self.span("stage_encoder"); _sp_enc.__enter__()
         M = B * S
-        xa, xb, xc = ws["x"]
         pos, offaw, value, attn, ffn = ws["pos"], ws["offaw"], ws["value"], ws["attn"], ws["ffn"]
         vr = ws["valid_ratios"]
-        for i, lay in enumerate(self.enc):
-            self.gemm(lay["offaw"], M, offaw, a=xa, a2=pos, lda=256)
-            self.gemm(lay["value"], M, value, a=xa, lda=256, row_keep=ws["mask_flat"])
-            with self.span("msda_enc"):
-                call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
-                     B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
-            self.gemm(lay["out"], M, xb, a=attn, lda=256, res=xa, ldr=256)
-            self.layernorm(xb, None, lay["ln1"], M, xc)
-            self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, relu=True)
-            self.gemm(lay["fc2"], M, xb, a=ffn, lda=1024, res=xc, ldr=256)
-            self.layernorm(xb, None, lay["ln2"], M, xa)
-            if taps is not None and i == 0:
-                taps["enc0_out"] = xa.view(B, S, 256).clone()
-        enc = xa
+        if gemm_backend() == "simt":
+            xa, xb, xc = ws["x"][:3]
+            for i, lay in enumerate(self.enc):
+                self.gemm(lay["offaw"], M, offaw, a=xa, a2=pos, lda=256)
+                self.gemm(lay["value"], M, value, a=xa, lda=256, row_keep=ws["mask_flat"])
+                with self.span("msda_enc"):
+                    call("egtr_msda_fused_fwd_f32", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
+                         B, S, 8, 32, Lv, S, 4, _ptr(attn), st)
+                self.gemm(lay["out"], M, xb, a=attn, lda=256, res=xa, ldr=256)
+                self.layernorm(xb, None, lay["ln1"], M, xc)
+                self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, relu=True)
+                self.gemm(lay["fc2"], M, xb, a=ffn, lda=1024, res=xc, ldr=256)
+                self.layernorm(xb, None, lay["ln2"], M, xa)
+                if taps is not None and i == 0:
+                    taps["enc0_out"] = xa.view(B, S, 256).clone()
+            enc_f32, enc_p32 = xa, None
+        else:
+            # Product path: every tensor that feeds a GEMM lives in HBM as P32 rows (split-bf16 at fp32 pitch), written by
+            # the kernel that produces it; the GEMMs stream both operands with TMA.  x: layer input, xp: x + pos (operand of
+            # the sampling_offsets / attention_weights projections, deformable_detr.py:1040), xc: post-attention LayerNorm.
+            x0, x, xp, xc, xb = ws["x"]
+            call("egtr_rows_to_p32", _ptr(x0), None, M, 256, 256, _ptr(x), st)
+            call("egtr_rows_to_p32", _ptr(x0), _ptr(pos), M, 256, 256, _ptr(xp), st)
+            enc_f32 = x0
+            nl_enc = len(self.enc)
+            for i, lay in enumerate(self.enc):
+                self.gemm(lay["offaw"], M, offaw, a=xp, lda=256, a_fmt=1)
+                self.gemm(lay["value"], M, value, a=x, lda=256, a_fmt=1, row_keep=ws["mask_flat"])
+                with self.span("msda_enc"):
+                    call("egtr_msda_fused_fwd_ex", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
+                         B, S, 8, 32, Lv, S, 4, _ptr(attn), 1, st)
+                self.gemm(lay["out"], M, xb, a=attn, lda=256, a_fmt=1)
+                # residual adds ride in the LayerNorm kernels (same bytes as a GEMM-epilogue residual, one less format)
+                call("egtr_add_layernorm_p32", _ptr(xb), _ptr(x), 1, _ptr(lay["ln1"][0]), _ptr(lay["ln1"][1]), M, 256,
+                     _ptr(xc), None, None, None, st)
+                self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, a_fmt=1, relu=True, out_fmt=1)
+                self.gemm(lay["fc2"], M, xb, a=ffn, lda=1024, a_fmt=1)
+                last = i == nl_enc - 1
+                want_f32 = last or (taps is not None and i == 0)
+                call("egtr_add_layernorm_p32", _ptr(xb), _ptr(xc), 1, _ptr(lay["ln2"][0]), _ptr(lay["ln2"][1]), M, 256,
+                     _ptr(x), _ptr(enc_f32) if want_f32 else None, None if last else _ptr(pos), None if last else _ptr(xp), st)
+                if taps is not None and i == 0:
+                    taps["enc0_out"] = enc_f32.view(B, S, 256).clone()
+            enc_p32 = x
+        enc = enc_f32
         enc_out = enc.view(B, S, 256).clone()
         _sp_enc.__exit__()
         _sp_dec = self.span("stage_decoder"); _sp_dec.__enter__()
@@ -499,7 +537,10 @@ class Engine:
         # ---- decoder (deformable_detr.py:1390-1489, 1774-1968)
         nl = cfg.decoder_layers
         dv = ws["dec_value"]
-        self.gemm(self.dec_value, M, dv, a=enc, lda=256, row_keep=ws["mask_flat"])
+        if enc_p32 is not None:
+            self.gemm(self.dec_value, M, dv, a=enc_p32, lda=256, a_fmt=1, row_keep=ws["mask_flat"])
+        else:
+            self.gemm(self.dec_value, M, dv, a=enc, lda=256, row_keep=ws["mask_flat"])
         call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
              None, 0, 0, _ptr(ws["ref"]), 2, st)
         Md = B * N

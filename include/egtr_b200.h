@@ -63,7 +63,15 @@ typedef struct {
   int lda;
   int H, W, C, OH, OW, KH, KW, stride, pad;
   const float* aux; /* mode 4: b1 [2*C] (layer-1 bias of the relation and connectivity MLPs) */
+  int fmt;          /* 0: fp32 rows.  1: P32 rows (see below) — mode 0 rows are then streamed by TMA with no operand-
+                     * producer warps; a2 must be NULL (fold addends into the kernel that wrote the rows) */
 } egtr_asrc_t;
+
+/* P32 row format ("split-bf16 planes at fp32 pitch"): an fp32 [rows, C] matrix (C % 32 == 0) stored with the same
+ * 4*C-byte row pitch; every group of 32 channels occupies 128 bytes = 32 bf16 `hi` values then 32 bf16 `lo` values with
+ * hi = bf16_rn(x), lo = bf16_rn(x - hi), i.e. x == hi + lo to 2^-17 relative.  It is what the bf16x3 tensor-core product
+ * consumes, written once by the producing kernel instead of being re-split by every consumer. */
+enum { EGTR_FMT_F32 = 0, EGTR_FMT_P32 = 1 };
 
 /* out[orow(m)*ldo + n] = keep(act(acc + bias[n] + res[orow(m)*ldr + n]));
  * orow(m) = (m / rows_per_b)*bstride + off + m % rows_per_b when rows_per_b > 0, else m;
@@ -88,6 +96,8 @@ typedef struct {
   const float* triplet; /*    [K1, K1, P] or NULL */
   const float* adj;     /*    tau * log(rel_dist) [P] or NULL */
   int k1;
+  int out_fmt;          /* EGTR_FMT_F32 / EGTR_FMT_P32: storage of `out` (P32 needs N % 32 == 0) */
+  int res_fmt;          /* storage of `res` */
 } egtr_epilogue_t;
 
 /* fp32 weight [N,K] -> split-bf16 planes [2][Npad][K] (hi, lo; rows >= N zero). Npad % 64 == 0. */
@@ -119,6 +129,11 @@ int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* const* a2_ptr
                           const int* n_base, int groups, const int* lda, const float* w, int M, int N, int K,
                           const egtr_epilogue_t* ep, egtr_stream_t s);
 
+/* x (+ addend) [rows, C] fp32 (row stride ldx floats) -> P32 rows [rows, C] (pitch 4*C bytes).  C % 32 == 0. */
+int egtr_rows_to_p32(const float* x, const float* addend, int rows, int C, int ldx, void* out, egtr_stream_t s);
+/* P32 rows -> fp32 (debug / tests / handing a P32 tensor back to the caller). */
+int egtr_p32_to_rows(const void* p32, int rows, int C, float* out, int ldo, egtr_stream_t s);
+
 /* ---------------------------------------------------------------- MSDeformAttn ----------- */
 /* Drop-in for ms_deform_attn_forward: value [B,S,M,D], spatial_shapes [L,2] int64 (device),
  * level_start_index [L] int64 (device), sampling_loc [B,Lq,M,L,P,2], attn_weight [B,Lq,M,L,P]
@@ -138,10 +153,20 @@ int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const int* shapes_
                             int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
                             int B, int S, int M, int D, int L, int Lq, int P, float* out, egtr_stream_t s);
 
+/* Same with the output written as P32 rows when out_fmt == EGTR_FMT_P32 (one head = one 32-channel group). */
+int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
+                           int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                           int B, int S, int M, int D, int L, int Lq, int P, void* out, int out_fmt, egtr_stream_t s);
+
 /* ---------------------------------------------------------------- row-wise / image ops --- */
 /* out = LayerNorm(x + res) over the last dim C (== 256), eps 1e-5; res may be NULL. */
 int egtr_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
                            int rows, int C, float* out, egtr_stream_t s);
+/* y = LayerNorm(x + res), C == 256; x fp32, res fp32 or P32 (res_fmt) or NULL.  Any of the three outputs may be NULL:
+ * out_p32 (y as P32 rows), out_f32 (y as fp32), out_plus_p32 (y + addend as P32 rows: the `x + pos` operand of the next
+ * layer's sampling_offsets / attention_weights projections, deformable_detr.py:1040). */
+int egtr_add_layernorm_p32(const float* x, const void* res, int res_fmt, const float* gamma, const float* beta, int rows,
+                           int C, void* out_p32, float* out_f32, const float* addend, void* out_plus_p32, egtr_stream_t s);
 /* zero rows of x[rows, C] where keep[row] == 0 (value.masked_fill, deformable_detr.py:1050-1052). */
 int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s);
 /* pixel_values [B,3,H,W] -> zero-bordered NHWC4 [B,H+2*pad,W+2*pad,4] (4th channel zero). */

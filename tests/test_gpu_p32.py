@@ -1,0 +1,145 @@
+"""GPU: the P32 (split-bf16 rows) data path — conversions, the TMA-fed tcgen05 GEMM, LayerNorm and MSDA writers."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.util import p32_decode, p32_encode, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_p32_encode_decode_host():
+    x = torch.randn(7, 96)
+    assert relerr(p32_decode(p32_encode(x)), x) < 2 ** -16
+
+
+@pytest.mark.parametrize("rows,Cn", [(1, 32), (333, 256), (1000, 1024)])
+def test_rows_to_p32_roundtrip(cuda, rows, Cn):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(rows + Cn)
+    x, add = torch.randn(rows, Cn, generator=g).to(cuda), torch.randn(rows, Cn, generator=g).to(cuda)
+    out = torch.empty(rows, Cn, device=cuda)
+    _lib.call("egtr_rows_to_p32", x.data_ptr(), None, rows, Cn, Cn, out.data_ptr(), _st())
+    assert torch.equal(out.view(torch.int32), p32_encode(x).view(torch.int32))  # bit-exact split
+    _lib.call("egtr_rows_to_p32", x.data_ptr(), add.data_ptr(), rows, Cn, Cn, out.data_ptr(), _st())
+    assert torch.equal(out.view(torch.int32), p32_encode(x + add).view(torch.int32))
+    back = torch.empty(rows, Cn, device=cuda)
+    _lib.call("egtr_p32_to_rows", out.data_ptr(), rows, Cn, back.data_ptr(), Cn, _st())
+    assert torch.equal(back, p32_decode(out))
+
+
+def _gemm_p32(a_p32, w, bias, *, relu=False, res=None, res_fmt=0, out_fmt=0, keep=None, remap=None, out=None, ldo=None):
+    from egtr_b200 import _lib
+    from egtr_b200._lib import ASrc, Epilogue
+    from egtr_b200.engine import Lin
+    dev = w.device
+    lin = Lin(w, bias, dev)
+    M, K = a_p32.shape
+    src, ep = ASrc(), Epilogue()
+    src.a, src.mode, src.lda, src.fmt = a_p32.data_ptr(), 0, K, 1
+    if out is None:
+        out = torch.full((M, lin.N), float("nan"), device=dev)
+    ep.bias, ep.res, ep.out = (lin.b.data_ptr() if bias is not None else None), (res.data_ptr() if res is not None else None), out.data_ptr()
+    ep.ldo = ldo or lin.N
+    ep.ldr = ep.ldo
+    ep.relu, ep.out_fmt, ep.res_fmt = int(relu), out_fmt, res_fmt
+    ep.rows_per_b, ep.bstride, ep.off = remap or (0, 0, 0)
+    ep.row_keep = keep.data_ptr() if keep is not None else None
+    _lib.call("egtr_gemm_sbf16", C.byref(src), lin.planes.data_ptr(), M, lin.N, lin.Npad, lin.K, C.byref(ep), _st())
+    torch.cuda.synchronize()
+    return out
+
+
+P32_SHAPES = [(128, 64, 64), (200, 256, 256), (1000, 384, 256), (4100, 1024, 256), (2500, 256, 1024), (77, 512, 256),
+              (129, 64, 256), (22223, 256, 256), (5, 64, 128), (333, 1536, 256), (66800, 64, 256), (1030, 96, 128), (500, 32, 64),
+              (200, 256, 1024), (273, 256, 2048), (130, 1024, 512), (1050, 512, 2048)]  # the last four take the split-K path
+
+
+@pytest.mark.parametrize("M,N,K", P32_SHAPES)
+def test_gemm_p32_plain(cuda, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = p32_encode(torch.randn(M, K, generator=g)).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    ad = p32_decode(a).double()
+    tol = 2e-5 * max(1.0, (K / 1024) ** 0.5)
+    out = _gemm_p32(a, w, None)
+    assert relerr(out, ad @ w.double().t()) < tol
+    out = _gemm_p32(a, w, b, relu=True)
+    assert relerr(out, (ad @ w.double().t() + b.double()).relu()) < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 256, 256), (1000, 384, 256), (4100, 1024, 256), (2500, 256, 1024), (333, 64, 64), (273, 256, 2048)])
+@pytest.mark.parametrize("res_fmt", [0, 1])
+@pytest.mark.parametrize("out_fmt", [0, 1])
+def test_gemm_p32_formats(cuda, M, N, K, res_fmt, out_fmt):
+    g = torch.Generator().manual_seed(M + N + K + res_fmt * 2 + out_fmt)
+    a = p32_encode(torch.randn(M, K, generator=g)).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g)
+    res_dev = (p32_encode(res) if res_fmt else res).to(cuda)
+    res_val = p32_decode(res_dev) if res_fmt else res_dev
+    keep = (torch.rand(M, generator=g) > 0.3).to(torch.uint8).to(cuda)
+    ref = (p32_decode(a).double() @ w.double().t() + b.double() + res_val.double()).relu() * keep.double().unsqueeze(1)
+    out = _gemm_p32(a, w, b, relu=True, res=res_dev, res_fmt=res_fmt, out_fmt=out_fmt, keep=keep)
+    got = p32_decode(out) if out_fmt else out
+    assert relerr(got, ref) < 2e-5 * max(1.0, (K / 1024) ** 0.5)
+
+
+def test_gemm_p32_remap_levels(cuda):
+    """input_proj style: per-image level slices of a [B, S, 256] buffer (rows_per_b / bstride / off)."""
+    g = torch.Generator().manual_seed(5)
+    B, hw, S, off, K = 3, 300, 1000, 450, 512
+    a = p32_encode(torch.randn(B * hw, K, generator=g)).to(cuda)
+    w = (torch.randn(256, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(256, generator=g).to(cuda)
+    out = torch.full((B * S, 256), 7.0, device=cuda)
+    _gemm_p32(a, w, b, remap=(hw, S, off), out=out, ldo=256)
+    ref = (p32_decode(a).double() @ w.double().t() + b.double()).view(B, hw, 256)
+    o3 = out.view(B, S, 256)
+    assert relerr(o3[:, off:off + hw], ref) < 2e-5
+    assert (o3[:, :off] == 7.0).all() and (o3[:, off + hw:] == 7.0).all()  # nothing outside the slice is touched
+
+
+@pytest.mark.parametrize("res_fmt", [None, 0, 1])
+def test_add_layernorm_p32(cuda, res_fmt):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    rows = 1237
+    x, res, pos = (torch.randn(rows, 256, generator=g) for _ in range(3))
+    gamma, beta = torch.randn(256, generator=g).to(cuda), torch.randn(256, generator=g).to(cuda)
+    res_dev = None if res_fmt is None else (p32_encode(res) if res_fmt else res).to(cuda)
+    res_val = 0 if res_fmt is None else (p32_decode(res_dev) if res_fmt else res_dev).double().cpu()
+    want = torch.nn.functional.layer_norm(x.double() + res_val, (256,), gamma.double().cpu(), beta.double().cpu(), 1e-5)
+    o_p, o_f, o_plus = (torch.empty(rows, 256, device=cuda) for _ in range(3))
+    xd, pd = x.to(cuda), pos.to(cuda)
+    _lib.call("egtr_add_layernorm_p32", xd.data_ptr(), res_dev.data_ptr() if res_dev is not None else None, res_fmt or 0,
+              gamma.data_ptr(), beta.data_ptr(), rows, 256, o_p.data_ptr(), o_f.data_ptr(), pd.data_ptr(), o_plus.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert relerr(o_f, want) < 5e-6
+    assert torch.equal(o_p.view(torch.int32), p32_encode(o_f.cpu()).to(cuda).view(torch.int32))
+    assert torch.equal(o_plus.view(torch.int32), p32_encode((o_f + pd).cpu()).to(cuda).view(torch.int32))
+
+
+def test_msda_fused_p32_out(cuda):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    shapes = [(12, 17), (6, 9), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in shapes)
+    B = 2
+    value = torch.randn(B * S, 256, generator=g).to(cuda)
+    offaw = torch.randn(B * S, 384, generator=g).to(cuda)
+    vr = (0.5 + 0.5 * torch.rand(B, 4, 2, generator=g)).to(cuda)
+    sh = (C.c_int * 8)(*[v for hw in shapes for v in hw])
+    o_f, o_p = torch.empty(B * S, 256, device=cuda), torch.empty(B * S, 256, device=cuda)
+    for out, fmt in ((o_f, 0), (o_p, 1)):
+        _lib.call("egtr_msda_fused_fwd_ex", value.data_ptr(), 256, sh, offaw.data_ptr(), 384, None, vr.data_ptr(), 1,
+                  B, S, 8, 32, 4, S, 4, out.data_ptr(), fmt, _st())
+    torch.cuda.synchronize()
+    assert torch.equal(o_p.view(torch.int32), p32_encode(o_f.cpu()).to(cuda).view(torch.int32))

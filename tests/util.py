@@ -54,3 +54,21 @@ def compare_forward(out, ref, tol=TOL, argmax_guard=None):
         errs["pred_rel_sum_p"] = relerr(rel.sum(-1), ref["pred_rel_sum_p"])
         errs["pred_rel_sum_ij"] = relerr(rel.sum((1, 2)), ref["pred_rel_sum_ij"])
     return errs
+
+
+def p32_encode(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, C] -> the P32 row format of include/egtr_b200.h, returned as a float32-typed [rows, C] tensor
+    (same bytes): per 32-channel group 32 bf16 hi then 32 bf16 lo, hi = bf16_rn(x), lo = bf16_rn(x - hi)."""
+    rows, C = x.shape
+    assert C % 32 == 0
+    x = x.float()
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    st = torch.stack([hi.view(rows, C // 32, 32), lo.view(rows, C // 32, 32)], 2).contiguous()  # [rows, G, 2, 32]
+    return st.view(rows, 2 * C).view(torch.float32)
+
+
+def p32_decode(p: torch.Tensor) -> torch.Tensor:
+    rows, C = p.shape
+    u = p.contiguous().view(torch.bfloat16).view(rows, C // 32, 2, 32).float()
+    return (u[:, :, 0] + u[:, :, 1]).reshape(rows, C)

@@ -34,6 +34,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--profile", type=int, default=-1)
 ap.add_argument("--only", type=str, default="")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--p32", action="store_true", help="feed plain-row shapes as P32 rows (TMA-fed kernel); --p32out also writes P32")
+ap.add_argument("--p32out", action="store_true")
 ap.add_argument("--prof", action="store_true", help="with an EGTR_GEMM_PROF build: print per-role cycle accounting")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -58,7 +60,13 @@ for idx, (name, M, N, K, kind) in enumerate(SHAPES):
         src.H, src.W, src.C, src.OH, src.OW, src.KH, src.KW, src.stride, src.pad = h, wd, c, h, wd, 3, 3, 1, 1
         assert h * wd == M and 9 * c == K
     else:
-        a = torch.randn(M, K, generator=g).to(dev)
+        a = torch.randn(M, K, generator=g)
+        if args.p32 and kind != "a2":
+            from tests.util import p32_encode
+            a = p32_encode(a)
+            src.fmt = 1
+            ep.out_fmt = int(args.p32out and N % 32 == 0)
+        a = a.to(dev)
         keep.append(a)
         src.a, src.mode, src.lda = _ptr(a), 0, K
         if kind == "a2":
