@@ -8,6 +8,11 @@
 // group lands hi in 16-byte chunks 0-3 and lo in chunks 4-7 of each smem row, and the UMMA descriptors of
 // the hi / lo operands are the same tile at byte offsets 0 / 64 (+32 for the second 16-wide k-step).
 //
+// Convolutions use the same kernel: the activation map is 4-D {channels, W, H, B} over the NHWC P32 tensor and an M tile is
+// a BW x BH patch of output pixels (BW * BH = 128), so filter tap (ky, kx) of a 64-channel slab is ONE tiled TMA box at
+// pixel offset (w0*stride + kx - pad, h0*stride + ky - pad): the zero padding is TMA's out-of-bounds fill, the stride is
+// the map's element stride, and there is no im2col buffer and no gather code.  Plain rows are the BW = 128, BH = 1 case.
+//
 // Roles (persistent, one CTA per SM, 320 threads):
 //   warps 0-7  epilogue : two warps per TMEM lane quadrant, each owns half of the tile's columns;
 //                         tcgen05.ld 32x32 -> bias / residual / ReLU / mask -> fp32 or P32 packing ->
@@ -54,23 +59,31 @@ struct PArgs {
   const float* bias;
   const uint8_t* row_keep;
   int M, N, K;
-  int rows_per_b, nb;     // rows are nb batches of rows_per_b (tiles never straddle a batch)
+  int nb;                 // batches (images); tiles never straddle a batch
+  int tiles_w, tiles_h;   // tiles per batch along w (rows mode: 128-row tiles) and h (rows mode: 1)
+  int bw_log2;            // tile = BW x BH output pixels, BW = 1 << bw_log2, BH = 128 >> bw_log2 (rows mode: 128 x 1)
+  int lim_w, lim_h;       // output extent per batch (rows mode: rows_per_b, 1)
+  int stride, pad, kw, slabs;  // conv geometry; k-block kb = filter tap kb / slabs, 64-channel slab kb % slabs
   int keep_bstride, keep_off;
   int relu, out_fmt, res_fmt, has_res;
   int splits, kb_per_split, plane_rows;
   int ncols;              // columns that exist in the output map (N, or Npad for split-K partial sums)
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int x, int y, int z) {
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c, int x, int y, int z) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_dst), "l"(tmap), "r"(ptx::smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(ptx::smem_u32(bar)), "r"(c), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int x, int y, int z) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(tmap), "r"(smem_src), "r"(x), "r"(y), "r"(z) : "memory");
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int c, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(c), "r"(x), "r"(y), "r"(z) : "memory");
 }
+
+struct TileCoord {
+  int b, w0, h0, n0, sp;
+};
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -99,11 +112,24 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mtiles_per_b = (p.rows_per_b + BLOCK_M - 1) / BLOCK_M;
+  const int mtiles_per_b = p.tiles_w * p.tiles_h;
   const int m_tiles = mtiles_per_b * p.nb;
   const int n_tiles = (p.ncols + BLOCK_N - 1) / BLOCK_N;
   const int total = m_tiles * n_tiles * p.splits;
   const int k_blocks_all = p.K / BLOCK_K;
+  auto decode = [&](int w) {
+    TileCoord t;
+    const int tg = w / p.splits;
+    t.sp = w - tg * p.splits;
+    const int mt = tg / n_tiles;
+    t.n0 = (tg - mt * n_tiles) * BLOCK_N;
+    t.b = mt / mtiles_per_b;
+    const int r = mt - t.b * mtiles_per_b;
+    const int th = r / p.tiles_w;
+    t.w0 = (r - th * p.tiles_w) << p.bw_log2;
+    t.h0 = th * (BLOCK_M >> p.bw_log2);
+    return t;
+  };
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -132,17 +158,18 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int tg = w / p.splits, sp = w - tg * p.splits;
-        const int mt = tg / n_tiles, nt = tg - mt * n_tiles;
-        const int b = mt / mtiles_per_b, m0 = (mt - b * mtiles_per_b) * BLOCK_M;
-        const int n0 = nt * BLOCK_N;
-        const int kb_lo = sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
+        const TileCoord t = decode(w);
+        const int n0 = t.n0;
+        const int kb_lo = t.sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
+        const int ax = t.w0 * p.stride - p.pad, ay = t.h0 * p.stride - p.pad;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          const int tap = kb / p.slabs, slab = kb - tap * p.slabs;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 201);
           const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_3d(st, &tmap_a, &full_bar[stage], kb * 128, m0, b);
-          tma_load_3d(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], kb * 128 + 64, m0, b);
+          tma_load_4d(st, &tmap_a, &full_bar[stage], slab * 128, ax + kx, ay + ky, t.b);
+          tma_load_4d(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], slab * 128 + 64, ax + kx, ay + ky, t.b);
           ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
           ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage],
                            kb * BLOCK_K, p.plane_rows + n0);
@@ -196,23 +223,22 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t res_phase = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tg = w / p.splits, sp = w - tg * p.splits;
-      const int mt = tg / n_tiles, nt = tg - mt * n_tiles;
-      const int b = mt / mtiles_per_b, m0 = (mt - b * mtiles_per_b) * BLOCK_M;
-      const int n0 = nt * BLOCK_N;
+      const TileCoord t = decode(w);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int row0 = m0 + q * 32;        // first row (inside batch b) of this warp's slab
-      const int zc = p.splits > 1 ? sp : b;  // third output coordinate
-      const int col_base = n0 + hf * (BLOCK_N / 2);
+      // this warp's 32 tile rows = a (min(BW,32) x 32/min(BW,32)) box of output pixels starting at (ow, oh)
+      const int ow = t.w0 + ((q * 32) & ((1 << p.bw_log2) - 1));
+      const int oh = t.h0 + ((q * 32) >> p.bw_log2);
+      const int zc = t.sp * p.nb + t.b;    // batch coordinate (split-K partial sums: one batch block per split)
+      const int col_base = t.n0 + hf * (BLOCK_N / 2);
       int nch = (p.ncols - col_base + 31) / 32;
       nch = nch < 0 ? 0 : (nch > C::CHUNKS ? C::CHUNKS : nch);
-      if (row0 >= p.rows_per_b) nch = 0;  // slab entirely in the M tail: nothing to store
+      if (ow >= p.lim_w || oh >= p.lim_h) nch = 0;  // box entirely in the tail: nothing to store
       bool keep = true;
-      if (p.row_keep != nullptr && nch > 0 && row0 + lane < p.rows_per_b)
-        keep = p.row_keep[(long long)b * p.keep_bstride + p.keep_off + row0 + lane] != 0;
+      if (p.row_keep != nullptr && nch > 0 && ow + lane < p.lim_w)  // rows mode only
+        keep = p.row_keep[(long long)t.b * p.keep_bstride + p.keep_off + ow + lane] != 0;
       if (p.has_res && nch > 0 && lane == 0) {  // first residual box of the tile, in flight while the MMAs run
         ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
-        tma_load_3d(stg_s, &tmap_res, rbar, col_base, row0, zc);
+        tma_load_4d(stg_s, &tmap_res, rbar, col_base, ow, oh, zc);
       }
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 205);
       ptx::tc_fence_after();
@@ -290,12 +316,12 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmap_out, stg_s, n, row0, zc);
+          tma_store_4d(&tmap_out, stg_s, n, ow, oh, zc);
           bulk_commit();
           bulk_wait_read0();  // the staging box may be overwritten once TMA has read it
           if (p.has_res && ci + 1 < nch) {
             ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
-            tma_load_3d(stg_s, &tmap_res, rbar, n + 32, row0, zc);
+            tma_load_4d(stg_s, &tmap_res, rbar, n + 32, ow, oh, zc);
           }
         }
         __syncwarp();
@@ -325,6 +351,7 @@ struct ReduceArgs {
   const void* res;
   void* out;
   int ldo, ldr, relu, out_fmt, res_fmt;
+  int rows_per_b, bstride, off;  // output row of GEMM row m (0: identity), as in egtr_epilogue_t
   const uint8_t* row_keep;
 };
 
@@ -343,16 +370,21 @@ p32_reduce_kernel(const ReduceArgs a) {
   const int n = (int)(wid - m * groups) * 32 + lane;
   float acc = 0.f;
   for (int s = 0; s < a.splits; ++s) acc += a.partial[((long long)s * a.M + m) * a.Npad + n];
+  long long orow = m;
+  if (a.rows_per_b > 0) {
+    const long long b = m / a.rows_per_b;
+    orow = b * a.bstride + a.off + (m - b * a.rows_per_b);
+  }
   if (a.bias) acc += __ldg(a.bias + n);
-  if (a.res) acc += a.res_fmt ? p32_load(a.res, m, a.ldr, n) : ((const float*)a.res)[m * a.ldr + n];
+  if (a.res) acc += a.res_fmt ? p32_load(a.res, orow, a.ldr, n) : ((const float*)a.res)[orow * a.ldr + n];
   if (a.relu) acc = fmaxf(acc, 0.f);
-  if (a.row_keep && !a.row_keep[m]) acc = 0.f;
+  if (a.row_keep && !a.row_keep[orow]) acc = 0.f;
   if (a.out_fmt == 0) {
-    ((float*)a.out)[m * a.ldo + n] = acc;
+    ((float*)a.out)[orow * a.ldo + n] = acc;
   } else {
     const __nv_bfloat16 h = __float2bfloat16_rn(acc);
     const __nv_bfloat16 l = __float2bfloat16_rn(acc - __bfloat162float(h));
-    __nv_bfloat16* g = (__nv_bfloat16*)((uint8_t*)a.out + (m * a.ldo + (n & ~31)) * 4);
+    __nv_bfloat16* g = (__nv_bfloat16*)((uint8_t*)a.out + (orow * a.ldo + (n & ~31)) * 4);
     g[lane] = h;
     g[32 + lane] = l;
   }
@@ -378,8 +410,8 @@ EncodeTiledFn encode_fn() {
 
 struct MapDesc {  // everything that determines a tensor map (POD, zero-initialised, compared bytewise)
   const void* ptr;
-  unsigned long long dim[3], stride[2];
-  unsigned box[3];
+  unsigned long long dim[4], stride[3];
+  unsigned box[4], estr[4];
   int dtype, rank;
 };
 struct MapDescHash {
@@ -406,30 +438,44 @@ int cached_map(const MapDesc& d, CUtensorMap* out) {
   }
   EncodeTiledFn enc = encode_fn();
   EGTR_CHECK(enc != nullptr, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[3] = {d.dim[0], d.dim[1], d.dim[2]};
-  cuuint64_t gstride[2] = {d.stride[0], d.stride[1]};
-  cuuint32_t box[3] = {d.box[0], d.box[1], d.box[2]};
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint64_t gdim[4] = {d.dim[0], d.dim[1], d.dim[2], d.dim[3]};
+  cuuint64_t gstride[3] = {d.stride[0], d.stride[1], d.stride[2]};
+  cuuint32_t box[4] = {d.box[0], d.box[1], d.box[2], d.box[3]};
+  cuuint32_t estr[4] = {d.estr[0], d.estr[1], d.estr[2], d.estr[3]};
   CUtensorMap m;
   CUresult r = enc(&m, (CUtensorMapDataType)d.dtype, (cuuint32_t)d.rank, const_cast<void*>(d.ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA,
-             "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
-             d.rank, d.dim[0], d.dim[1], d.dim[2], d.stride[0], d.stride[1], d.box[0], d.box[1], d.box[2]);
+             "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u)",
+             (int)r, d.rank, d.dim[0], d.dim[1], d.dim[2], d.dim[3], d.stride[0], d.stride[1], d.stride[2], d.box[0], d.box[1],
+             d.box[2], d.box[3]);
   cache.emplace(d, m);
   *out = m;
   return EGTR_OK;
 }
 
-MapDesc make_desc(const void* ptr, int dtype, int rank, unsigned long long d0, unsigned long long d1, unsigned long long d2,
-                  unsigned long long s0, unsigned long long s1, unsigned b0, unsigned b1) {
+// 4-D map {d0, d1, d2, d3} (d0 innermost, contiguous), byte strides s1..s3 of dims 1..3, box {b0, b1, b2, 1},
+// element (traversal) strides {1, e, e, 1}.
+MapDesc desc4(const void* ptr, int dtype, unsigned long long d0, unsigned long long d1, unsigned long long d2, unsigned long long d3,
+              unsigned long long s1, unsigned long long s2, unsigned long long s3, unsigned b0, unsigned b1, unsigned b2, unsigned e = 1) {
   MapDesc d;
   memset(&d, 0, sizeof(d));
-  d.ptr = ptr; d.dtype = dtype; d.rank = rank;
-  d.dim[0] = d0; d.dim[1] = d1; d.dim[2] = d2;
-  d.stride[0] = s0; d.stride[1] = s1;
-  d.box[0] = b0; d.box[1] = b1; d.box[2] = 1;
+  d.ptr = ptr; d.dtype = dtype; d.rank = 4;
+  d.dim[0] = d0; d.dim[1] = d1; d.dim[2] = d2; d.dim[3] = d3;
+  d.stride[0] = s1; d.stride[1] = s2; d.stride[2] = s3;
+  d.box[0] = b0; d.box[1] = b1; d.box[2] = b2; d.box[3] = 1;
+  d.estr[0] = 1; d.estr[1] = e; d.estr[2] = e; d.estr[3] = 1;
+  return d;
+}
+MapDesc desc2(const void* ptr, int dtype, unsigned long long d0, unsigned long long d1, unsigned long long s1, unsigned b0, unsigned b1) {
+  MapDesc d;
+  memset(&d, 0, sizeof(d));
+  d.ptr = ptr; d.dtype = dtype; d.rank = 2;
+  d.dim[0] = d0; d.dim[1] = d1;
+  d.stride[0] = s1;
+  d.box[0] = b0; d.box[1] = b1;
+  d.estr[0] = d.estr[1] = 1;
   return d;
 }
 
@@ -455,58 +501,99 @@ float* partial_buffer_p32(size_t floats) {  // grow-only; older buffers stay ali
   return buf;
 }
 
+// Output pixel tile of a convolution: BW x BH = 128 with BW a power of two in [8, 128]; fewest tiles wins, wider wins ties.
+int pick_bw_log2(int OW, int OH) {
+  int best = 7;
+  long long best_tiles = -1;
+  for (int l = 7; l >= 3; --l) {
+    const int bw = 1 << l, bh = BLOCK_M >> l;
+    const long long tiles = (long long)cdiv(OW, bw) * cdiv(OH, bh);
+    if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best = l; }
+  }
+  return best;
+}
+
 template <int BLOCK_N>
 int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                cudaStream_t st) {
   using C = PCfg<BLOCK_N>;
-  const int rows_per_b = ep.rows_per_b > 0 ? ep.rows_per_b : M;
-  const int nb = M / rows_per_b;
-  const int m_tiles = cdiv(rows_per_b, BLOCK_M) * nb;
+  const bool conv = a.mode == 1;
+  PArgs p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.plane_rows = plane_rows;
+  int rows_per_b, out_w, out_h;  // per batch: rows, output extent
+  if (conv) {
+    p.nb = M / (a.OH * a.OW);
+    rows_per_b = a.OH * a.OW; out_w = a.OW; out_h = a.OH;
+    p.bw_log2 = pick_bw_log2(a.OW, a.OH);
+    p.stride = a.stride; p.pad = a.pad; p.kw = a.KW; p.slabs = a.C / 64;
+  } else {
+    rows_per_b = ep.rows_per_b > 0 ? ep.rows_per_b : M;
+    p.nb = M / rows_per_b;
+    out_w = rows_per_b; out_h = 1;
+    p.bw_log2 = 7;
+    p.stride = 1; p.pad = 0; p.kw = 1; p.slabs = K / 64;
+  }
+  const int BW = 1 << p.bw_log2, BH = BLOCK_M >> p.bw_log2;
+  p.tiles_w = cdiv(out_w, BW); p.tiles_h = cdiv(out_h, BH);
+  p.lim_w = out_w; p.lim_h = out_h;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.nb;
   const int n_tiles = cdiv(N, BLOCK_N);
   const int k_blocks = K / BLOCK_K;
   int splits = 1;
-  if (nb == 1 && m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
+  if (m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
     splits = num_sms() / (m_tiles * n_tiles);
     if (splits > k_blocks / 4) splits = k_blocks / 4;
     if (splits < 1) splits = 1;
   }
   const int kbps = cdiv(k_blocks, splits);
   splits = cdiv(k_blocks, kbps);
+  p.splits = splits; p.kb_per_split = kbps;
 
-  PArgs p = {};
-  p.M = M; p.N = N; p.K = K;
-  p.rows_per_b = rows_per_b; p.nb = nb;
-  p.splits = splits; p.kb_per_split = kbps; p.plane_rows = plane_rows;
   CUtensorMap ta, tw, to, tr;
-  int rc = cached_map(make_desc(a.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, 2ull * K, rows_per_b, nb, 4ull * a.lda,
-                                4ull * a.lda * rows_per_b, 64, BLOCK_M), &ta);
+  int rc;
+  if (conv) {
+    const unsigned long long pix = 4ull * a.C;  // bytes per pixel
+    rc = cached_map(desc4(a.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2ull * a.C, a.W, a.H, p.nb, pix, pix * a.W, pix * a.W * a.H, 64,
+                          BW * a.stride, BH * a.stride, a.stride), &ta);
+  } else {
+    const unsigned long long pitch = 4ull * a.lda;
+    rc = cached_map(desc4(a.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2ull * K, rows_per_b, 1, p.nb, pitch, pitch * rows_per_b,
+                          pitch * rows_per_b, 64, BLOCK_M, 1), &ta);
+  }
   if (rc != EGTR_OK) return rc;
-  rc = cached_map(make_desc(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, 2ull * plane_rows, 1, 2ull * K, 0, BLOCK_K, BLOCK_N), &tw);
+  rc = cached_map(desc2(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, 2ull * plane_rows, 2ull * K, BLOCK_K, BLOCK_N), &tw);
   if (rc != EGTR_OK) return rc;
-  const int n_cols32 = cdiv(N, 32) * 32;
+  const unsigned box_w = BW < 32 ? BW : 32, box_h = 32 / box_w;  // one epilogue warp's 32 tile rows
   float* partial = nullptr;
   if (splits > 1) {
     partial = partial_buffer_p32((size_t)splits * M * Npad);
     EGTR_CHECK(partial != nullptr, EGTR_ERR_CUDA, "split-K scratch allocation failed");
-    rc = cached_map(make_desc(partial, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, Npad, M, splits, 4ull * Npad, 4ull * Npad * M, 32, 32), &to);
+    const unsigned long long pitch = 4ull * Npad;
+    rc = cached_map(desc4(partial, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, Npad, out_w, out_h, (unsigned long long)p.nb * splits, pitch,
+                          pitch * out_w, pitch * rows_per_b, 32, box_w, box_h), &to);
     if (rc != EGTR_OK) return rc;
     tr = to;
     p.ncols = Npad;
   } else {
     const unsigned long long bstride = ep.rows_per_b > 0 ? (unsigned long long)ep.bstride : (unsigned long long)rows_per_b;
     const uint8_t* obase = (const uint8_t*)ep.out + 4ll * ep.off * ep.ldo;
-    rc = cached_map(make_desc(obase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, n_cols32, rows_per_b, nb, 4ull * ep.ldo, 4ull * ep.ldo * bstride, 32, 32), &to);
+    const unsigned long long opitch = 4ull * ep.ldo;
+    rc = cached_map(desc4(obase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, out_w, out_h, p.nb, opitch, opitch * out_w, opitch * bstride, 32,
+                          box_w, box_h), &to);
     if (rc != EGTR_OK) return rc;
     tr = to;
     if (ep.res != nullptr) {
       const uint8_t* rbase = (const uint8_t*)ep.res + 4ll * ep.off * ep.ldr;
-      rc = cached_map(make_desc(rbase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, n_cols32, rows_per_b, nb, 4ull * ep.ldr, 4ull * ep.ldr * bstride, 32, 32), &tr);
+      const unsigned long long rpitch = 4ull * ep.ldr;
+      rc = cached_map(desc4(rbase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, out_w, out_h, p.nb, rpitch, rpitch * out_w, rpitch * bstride, 32,
+                            box_w, box_h), &tr);
       if (rc != EGTR_OK) return rc;
       p.has_res = 1;
       p.res_fmt = ep.res_fmt;
     }
     p.bias = ep.bias;
-    p.row_keep = ep.row_keep;
+    p.row_keep = conv ? nullptr : ep.row_keep;
     p.keep_bstride = (int)bstride;
     p.keep_off = ep.off;
     p.relu = ep.relu;
@@ -526,7 +613,8 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     ReduceArgs r = {};
     r.partial = partial; r.splits = splits; r.M = M; r.N = N; r.Npad = Npad;
     r.bias = ep.bias; r.res = ep.res; r.out = ep.out; r.ldo = ep.ldo; r.ldr = ep.ldr; r.relu = ep.relu;
-    r.out_fmt = ep.out_fmt; r.res_fmt = ep.res_fmt; r.row_keep = ep.row_keep;
+    r.out_fmt = ep.out_fmt; r.res_fmt = ep.res_fmt; r.row_keep = conv ? nullptr : ep.row_keep;
+    r.rows_per_b = ep.rows_per_b; r.bstride = ep.bstride; r.off = ep.off;
     const long long threads = (long long)M * (N / 32) * 32;
     p32_reduce_kernel<<<cdiv(threads, 256), 256, 0, st>>>(r);
     count_launch();
@@ -537,17 +625,25 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
 
 }  // namespace
 
-// Entry used by egtr_gemm_sbf16 when the operand source is P32 rows (a.fmt == 1, mode 0).
+// Entry used by egtr_gemm_sbf16 when the operand source is P32 (a.fmt == 1): mode 0 rows or mode 1 NHWC convolution.
 int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                       cudaStream_t st) {
-  EGTR_CHECK(a.a2 == nullptr && a.mode == 0, EGTR_ERR_UNSUPPORTED, "P32 operand rows: plain rows only (fold addends into the producer)");
-  EGTR_CHECK(N % 32 == 0 && K % 64 == 0 && a.lda % 4 == 0 && a.lda >= K && ep.ldo % 4 == 0 && ep.ldo >= N, EGTR_ERR_ARG,
-             "egtr_gemm_sbf16 (P32 rows): need N %% 32 == 0, K %% 64 == 0, 16-byte row pitches (N=%d K=%d lda=%d ldo=%d)", N, K, a.lda, ep.ldo);
+  EGTR_CHECK(a.a2 == nullptr && (a.mode == 0 || a.mode == 1), EGTR_ERR_UNSUPPORTED,
+             "P32 operand: plain rows or NHWC convolution only (fold addends into the producer)");
+  EGTR_CHECK(N % 32 == 0 && K % 64 == 0 && ep.ldo % 4 == 0 && ep.ldo >= N, EGTR_ERR_ARG,
+             "egtr_gemm_sbf16 (P32): need N %% 32 == 0, K %% 64 == 0, 16-byte row pitches (N=%d K=%d ldo=%d)", N, K, ep.ldo);
+  if (a.mode == 0) {
+    EGTR_CHECK(a.lda % 4 == 0 && a.lda >= K, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): lda=%d", a.lda);
+    EGTR_CHECK(ep.rows_per_b <= 0 || M % ep.rows_per_b == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): M %% rows_per_b != 0");
+  } else {
+    EGTR_CHECK(a.C % 64 == 0 && K == a.KH * a.KW * a.C && a.stride >= 1 && a.stride <= 2 && a.OH > 0 && a.OW > 0 &&
+                   M % (a.OH * a.OW) == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 conv): C=%d K=%d stride=%d M=%d", a.C, K, a.stride, M);
+    EGTR_CHECK(ep.rows_per_b <= 0 || ep.rows_per_b == a.OH * a.OW, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 conv): rows_per_b must be OH*OW");
+  }
   EGTR_CHECK(((uintptr_t)a.a & 127) == 0 && ((uintptr_t)ep.out & 127) == 0 && (!ep.res || ((uintptr_t)ep.res & 127) == 0) && ((uintptr_t)planes & 127) == 0,
-             EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): 128-byte aligned buffers required");
-  EGTR_CHECK(!ep.res || (ep.ldr % 4 == 0 && ep.ldr >= N), EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): ldr=%d", ep.ldr);
-  EGTR_CHECK(ep.pair_n == 0 && !ep.fin && !ep.dot_w, EGTR_ERR_UNSUPPORTED, "egtr_gemm_sbf16 (P32 rows): relation epilogues are not built here");
-  EGTR_CHECK(ep.rows_per_b <= 0 || M % ep.rows_per_b == 0, EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32 rows): M %% rows_per_b != 0");
+             EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32): 128-byte aligned buffers required");
+  EGTR_CHECK(!ep.res || (ep.ldr % 4 == 0 && ep.ldr >= N), EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32): ldr=%d", ep.ldr);
+  EGTR_CHECK(ep.pair_n == 0 && !ep.fin && !ep.dot_w, EGTR_ERR_UNSUPPORTED, "egtr_gemm_sbf16 (P32): relation epilogues are not built here");
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   int bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N >= 192 ? 128 : 64));
   if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;

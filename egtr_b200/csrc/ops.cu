@@ -164,7 +164,7 @@ __global__ void pad_nhwc4_kernel(const float* __restrict__ img, int B, int H, in
 }
 
 // ------------------------------------------------------------------ 3x3/2 pad 1 max-pool, NHWC
-__global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int OH, int OW, float* __restrict__ out) {
+__global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int OH, int OW, float* __restrict__ out, int out_fmt) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * OH * OW * C4;
   if (i >= total) return;
@@ -186,7 +186,8 @@ __global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W,
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  ((float4*)out)[i] = m;
+  if (out_fmt == 0) ((float4*)out)[i] = m;
+  else p32_store4((uint8_t*)out + (i / C4) * (long long)C4 * 16, c * 4, m);
 }
 
 // ------------------------------------------------------------------ GroupNorm (C == 256, 32 groups of 8)
@@ -492,10 +493,15 @@ extern "C" int egtr_pad_nchw3_to_nhwc4_f32(const float* img, int B, int H, int W
 }
 
 extern "C" int egtr_maxpool3x3s2_nhwc_f32(const float* x, int B, int H, int W, int C, float* out, egtr_stream_t s) {
-  EGTR_CHECK(x && out && B > 0 && H > 0 && W > 0 && C % 4 == 0, EGTR_ERR_ARG, "egtr_maxpool3x3s2_nhwc_f32: bad arguments");
+  return egtr_maxpool3x3s2_nhwc_ex(x, B, H, W, C, out, EGTR_FMT_F32, s);
+}
+
+extern "C" int egtr_maxpool3x3s2_nhwc_ex(const float* x, int B, int H, int W, int C, void* out, int out_fmt, egtr_stream_t s) {
+  EGTR_CHECK(x && out && B > 0 && H > 0 && W > 0 && C % 4 == 0 && (out_fmt == EGTR_FMT_F32 || C % 32 == 0), EGTR_ERR_ARG,
+             "egtr_maxpool3x3s2_nhwc: bad arguments");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)B * OH * OW * (C / 4);
-  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, B, H, W, C / 4, OH, OW, out);
+  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, B, H, W, C / 4, OH, OW, (float*)out, out_fmt);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

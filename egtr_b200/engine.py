@@ -305,7 +305,7 @@ class Engine:
         ep.row_keep = _ptr(row_keep)
         src.fmt, ep.out_fmt, ep.res_fmt = a_fmt, out_fmt, res_fmt
         if a_fmt == 1:
-            assert conv is None and a2 is None
+            assert a2 is None
             call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
             return
         if gemm_backend() == "simt":
@@ -435,7 +435,10 @@ class Engine:
         h, w = ws["c2_hw"]
         bufs = ws["bb"]
         x = bufs[0]
-        call("egtr_maxpool3x3s2_nhwc_f32", _ptr(ws["stem"]), B, h1, w1, 64, _ptr(x), st)
+        # P32 from here on (product path): every conv reads its operand through TMA; 3x3 / strided convs as patch tiles
+        p32 = 0 if gemm_backend() == "simt" else 1
+        call("egtr_maxpool3x3s2_nhwc_ex", _ptr(ws["stem"]), B, h1, w1, 64, _ptr(x), p32, st)
+        fm = dict(a_fmt=p32, out_fmt=p32)
         cur, cin = 0, 64
         for li, blk in self.blocks:
             s = blk["stride"]
@@ -443,17 +446,20 @@ class Engine:
             planes = blk["c1"].N
             free = [i for i in range(4) if i != cur]
             y1, y2, idt = bufs[free[0]], bufs[free[1]], bufs[free[2]]
-            self.gemm(blk["c1"], B * h * w, y1, a=x, lda=cin, relu=True)
+            self.gemm(blk["c1"], B * h * w, y1, a=x, lda=cin, relu=True, **fm)
             self.gemm(blk["c2"], B * oh * ow, y2, relu=True,
-                      conv=dict(x=y1, H=h, W=w, C=planes, OH=oh, OW=ow, KH=3, KW=3, stride=s, pad=1))
+                      conv=dict(x=y1, H=h, W=w, C=planes, OH=oh, OW=ow, KH=3, KW=3, stride=s, pad=1), **fm)
             if "ds" in blk:
-                self.gemm(blk["ds"], B * oh * ow, idt,
-                          conv=dict(x=x, H=h, W=w, C=cin, OH=oh, OW=ow, KH=1, KW=1, stride=s, pad=0))
+                if s == 1 and p32:
+                    self.gemm(blk["ds"], B * oh * ow, idt, a=x, lda=cin, **fm)
+                else:
+                    self.gemm(blk["ds"], B * oh * ow, idt,
+                              conv=dict(x=x, H=h, W=w, C=cin, OH=oh, OW=ow, KH=1, KW=1, stride=s, pad=0), **fm)
                 res = idt
             else:
                 res = x
             # conv3 + bn3 + identity + ReLU in one epilogue; output reuses y1's buffer
-            self.gemm(blk["c3"], B * oh * ow, y1, a=y2, lda=planes, relu=True, res=res, ldr=planes * 4)
+            self.gemm(blk["c3"], B * oh * ow, y1, a=y2, lda=planes, relu=True, res=res, ldr=planes * 4, res_fmt=p32, **fm)
             x, cur, cin, h, w = y1, free[0], planes * 4, oh, ow
             if blk.get("last") and li >= 2:
                 # C3/C4/C5 feed input_proj straight away: 1x1 conv + GroupNorm written into the level's
@@ -461,7 +467,7 @@ class Engine:
                 lvl = li - 2
                 lin, gw, gb = self.input_proj[lvl]
                 hw = h * w
-                self.gemm(lin, B * hw, ws["x"][0], a=x, lda=cin, ldo=256, remap=(hw, S, starts[lvl]))
+                self.gemm(lin, B * hw, ws["x"][0], a=x, lda=cin, ldo=256, remap=(hw, S, starts[lvl]), a_fmt=p32)
                 call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, hw, S, starts[lvl], 256, 32, _ptr(gw), _ptr(gb), _ptr(ws["gn_scratch"]), st)
                 if li == 4:  # extra level: 3x3/2 conv on C5
                     if Lv > 4:
@@ -469,10 +475,14 @@ class Engine:
                     lin2, gw2, gb2 = self.input_proj[3]
                     oh2, ow2 = shapes[3]
                     self.gemm(lin2, B * oh2 * ow2, ws["x"][0], ldo=256, remap=(oh2 * ow2, S, starts[3]),
-                              conv=dict(x=x, H=h, W=w, C=cin, OH=oh2, OW=ow2, KH=3, KW=3, stride=2, pad=1))
+                              conv=dict(x=x, H=h, W=w, C=cin, OH=oh2, OW=ow2, KH=3, KW=3, stride=2, pad=1), a_fmt=p32)
                     call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, oh2 * ow2, S, starts[3], 256, 32, _ptr(gw2), _ptr(gb2), _ptr(ws["gn_scratch"]), st)
                 if taps is not None:
-                    taps[f"c{li + 1}"] = x[: B * hw * cin].view(B, h, w, cin).permute(0, 3, 1, 2).clone()
+                    xf = x[: B * hw * cin]
+                    if p32:
+                        xf = torch.empty(B * hw, cin, **f32)
+                        call("egtr_p32_to_rows", _ptr(x), B * hw, cin, _ptr(xf), cin, st)
+                    taps[f"c{li + 1}"] = xf.view(B, h, w, cin).permute(0, 3, 1, 2).clone()
         if taps is not None:
             taps["source_flatten"] = ws["x"][0].view(B, S, 256).clone()
             taps["lvl_pos_embed_flatten"] = ws["pos"].view(B, S, 256).clone()

@@ -63,8 +63,10 @@ typedef struct {
   int lda;
   int H, W, C, OH, OW, KH, KW, stride, pad;
   const float* aux; /* mode 4: b1 [2*C] (layer-1 bias of the relation and connectivity MLPs) */
-  int fmt;          /* 0: fp32 rows.  1: P32 rows (see below) — mode 0 rows are then streamed by TMA with no operand-
-                     * producer warps; a2 must be NULL (fold addends into the kernel that wrote the rows) */
+  int fmt;          /* 0: fp32.  1: P32 (see below) — mode 0 rows and mode 1 NHWC convolutions (a 128-pixel M tile is a
+                     * BW x BH patch of output pixels, each filter tap one tiled TMA box, zero padding = TMA's out-of-bounds
+                     * fill) are streamed by TMA with no operand-producer warps; a2 must be NULL (fold addends into the
+                     * kernel that wrote the tensor) */
 } egtr_asrc_t;
 
 /* P32 row format ("split-bf16 planes at fp32 pitch"): an fp32 [rows, C] matrix (C % 32 == 0) stored with the same
@@ -173,6 +175,8 @@ int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, e
 int egtr_pad_nchw3_to_nhwc4_f32(const float* img, int B, int H, int W, int pad, float* out, egtr_stream_t s);
 /* NHWC 3x3/2 pad 1 max-pool. */
 int egtr_maxpool3x3s2_nhwc_f32(const float* x, int B, int H, int W, int C, float* out, egtr_stream_t s);
+/* Same; out_fmt == EGTR_FMT_P32 writes the pooled map as P32 rows (C % 32 == 0). */
+int egtr_maxpool3x3s2_nhwc_ex(const float* x, int B, int H, int W, int C, void* out, int out_fmt, egtr_stream_t s);
 /* GroupNorm(32 groups) in place over x[B, rows_per_b (at row offset `off`, batch stride `bstride`
  * rows), C], eps 1e-5 (deformable_detr.py:1996). */
 int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups,

@@ -143,3 +143,76 @@ def test_msda_fused_p32_out(cuda):
                   B, S, 8, 32, 4, S, 4, out.data_ptr(), fmt, _st())
     torch.cuda.synchronize()
     assert torch.equal(o_p.view(torch.int32), p32_encode(o_f.cpu()).to(cuda).view(torch.int32))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 13, 17, 64, 64, 3, 1, 1), (1, 20, 31, 128, 256, 3, 2, 1), (2, 9, 11, 256, 512, 1, 2, 0),
+                                                  (1, 7, 5, 2048, 256, 3, 2, 1), (1, 50, 84, 256, 256, 3, 1, 1), (1, 100, 167, 128, 128, 3, 1, 1),
+                                                  (1, 101, 167, 128, 128, 3, 2, 1), (3, 25, 42, 512, 512, 3, 1, 1)])
+@pytest.mark.parametrize("out_fmt", [0, 1])
+def test_gemm_p32_conv_nhwc(cuda, B, H, W, Cin, Cout, k, s, p, out_fmt):
+    """Convolution as patch-tiled TMA boxes over the P32 NHWC tensor (padding = OOB fill, stride = element stride)."""
+    from egtr_b200 import _lib
+    from egtr_b200._lib import ASrc, Epilogue
+    from egtr_b200.engine import Lin, _conv_mat, conv_out
+    g = torch.Generator().manual_seed(H * W + Cin + k)
+    x = torch.randn(B * H * W, Cin, generator=g)
+    xp = p32_encode(x).to(cuda)
+    xd = p32_decode(xp).cpu().view(B, H, W, Cin).permute(0, 3, 1, 2).double()
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    want = torch.nn.functional.conv2d(xd, w.double(), b.double(), stride=s, padding=p).relu()
+    OH, OW = conv_out(H, k, s, p), conv_out(W, k, s, p)
+    lin = Lin(_conv_mat(w), b, cuda)
+    src, ep = ASrc(), Epilogue()
+    src.a, src.mode, src.fmt = xp.data_ptr(), 1, 1
+    src.H, src.W, src.C, src.OH, src.OW, src.KH, src.KW, src.stride, src.pad = H, W, Cin, OH, OW, k, k, s, p
+    M = B * OH * OW
+    out = torch.full((M, Cout), float("nan"), device=cuda)
+    ep.bias, ep.out, ep.ldo, ep.ldr, ep.relu, ep.out_fmt = lin.b.data_ptr(), out.data_ptr(), Cout, Cout, 1, out_fmt
+    _lib.call("egtr_gemm_sbf16", C.byref(src), lin.planes.data_ptr(), M, lin.N, lin.Npad, lin.K, C.byref(ep), _st())
+    torch.cuda.synchronize()
+    got = (p32_decode(out) if out_fmt else out).cpu().view(B, OH, OW, Cout).permute(0, 3, 1, 2)
+    assert relerr(got, want) < 2e-5 * max(1.0, (lin.K / 1024) ** 0.5)
+
+
+def test_gemm_p32_conv_remap(cuda):
+    """The extra feature level: 3x3/2 conv on C5 written into its slice of source_flatten [B, S, 256]."""
+    from egtr_b200 import _lib
+    from egtr_b200._lib import ASrc, Epilogue
+    from egtr_b200.engine import Lin, _conv_mat, conv_out
+    g = torch.Generator().manual_seed(9)
+    B, H, W, Cin, S, off = 2, 13, 21, 256, 400, 250
+    xp = p32_encode(torch.randn(B * H * W, Cin, generator=g)).to(cuda)
+    xd = p32_decode(xp).cpu().view(B, H, W, Cin).permute(0, 3, 1, 2).double()
+    w = torch.randn(256, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(256, generator=g)
+    want = torch.nn.functional.conv2d(xd, w.double(), b.double(), stride=2, padding=1)
+    OH, OW = conv_out(H, 3, 2, 1), conv_out(W, 3, 2, 1)
+    lin = Lin(_conv_mat(w), b, cuda)
+    src, ep = ASrc(), Epilogue()
+    src.a, src.mode, src.fmt = xp.data_ptr(), 1, 1
+    src.H, src.W, src.C, src.OH, src.OW, src.KH, src.KW, src.stride, src.pad = H, W, Cin, OH, OW, 3, 3, 2, 1
+    out = torch.full((B * S, 256), 7.0, device=cuda)
+    ep.bias, ep.out, ep.ldo, ep.ldr = lin.b.data_ptr(), out.data_ptr(), 256, 256
+    ep.rows_per_b, ep.bstride, ep.off = OH * OW, S, off
+    _lib.call("egtr_gemm_sbf16", C.byref(src), lin.planes.data_ptr(), B * OH * OW, 256, 256, lin.K, C.byref(ep), _st())
+    torch.cuda.synchronize()
+    o3 = out.view(B, S, 256)
+    got = o3[:, off:off + OH * OW].cpu().view(B, OH, OW, 256).permute(0, 3, 1, 2)
+    assert relerr(got, want) < 2e-5
+    assert (o3[:, :off] == 7.0).all() and (o3[:, off + OH * OW:] == 7.0).all()
+
+
+def test_maxpool_p32_out(cuda):
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(2)
+    B, H, W, Cn = 2, 21, 34, 64
+    x = torch.randn(B, H, W, Cn, generator=g).to(cuda)
+    OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    o_f, o_p = torch.empty(B * OH * OW, Cn, device=cuda), torch.empty(B * OH * OW, Cn, device=cuda)
+    _lib.call("egtr_maxpool3x3s2_nhwc_ex", x.data_ptr(), B, H, W, Cn, o_f.data_ptr(), 0, _st())
+    _lib.call("egtr_maxpool3x3s2_nhwc_ex", x.data_ptr(), B, H, W, Cn, o_p.data_ptr(), 1, _st())
+    torch.cuda.synchronize()
+    want = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(B * OH * OW, Cn)
+    assert torch.equal(o_f, want)
+    assert torch.equal(o_p.view(torch.int32), p32_encode(o_f.cpu()).to(cuda).view(torch.int32))
