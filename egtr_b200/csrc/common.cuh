@@ -32,6 +32,48 @@ void set_last_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
+int pdl_mode();  // 0 off, 1 every launch, 2 only grids of at least one CTA per SM
+
+// Every kernel of the library is launched with programmatic dependent launch (PDL): the next kernel's CTAs may become
+// resident (and run their prologue) while the previous grid drains, and block in `pdl_entry()` / `pdl_wait()` until that grid
+// has completed and its writes are visible.  Rule: a kernel executes griddepcontrol.wait before its first global access.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  const int mode = pdl_mode();
+  if (mode == 1 || (mode == 2 && (long long)grid.x * grid.y * grid.z >= num_sms())) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_cluster_pdl(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
+}
+#endif
 
 // ----------------------------------------------------------------------------- A-operand source
 // Where the rows of a GEMM's left operand come from.  One description serves the tcgen05 kernel's

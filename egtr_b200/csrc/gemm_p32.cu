@@ -44,11 +44,15 @@ constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int A_GROUP_BYTES = BLOCK_M * 128;  // one 32-channel group of 128 rows: hi 64 B | lo 64 B per row
 constexpr int STG_BYTES = 32 * 128;           // one epilogue box: 32 rows x 32 channels
 
-template <int BLOCK_N>
+// CTAS == 2: a cluster of two CTAs computes a 256-row tile with one cta_group::2 MMA — each CTA stages its own 128 activation
+// rows and only HALF of the weight tile, so a k-block costs 64 KB instead of 96 KB of L2->SM traffic per SM at BLOCK_N = 256
+// and a third pipeline stage fits.
+template <int BLOCK_N, int CTAS>
 struct PCfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CTAS;  // weight rows staged by one CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_GROUP_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 4 ? 4 : (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int CTRL_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + 1024 /*align slack*/;
@@ -84,6 +88,16 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src
 struct TileCoord {
   int b, w0, h0, n0, sp;
 };
+
+template <int CTAS>
+__device__ __forceinline__ void release_tmem_stage(uint64_t* bar, int lane) {  // whole warp, after its last tcgen05.wait::ld
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (CTAS == 2) ptx::mbar_arrive_leader(bar);
+    else ptx::mbar_arrive(bar);
+  }
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -93,12 +107,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const PArgs p,
                 int* __restrict__ err) {
-  using C = PCfg<BLOCK_N>;
+  pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
+  using C = PCfg<BLOCK_N, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stg_all = smem + C::STAGES * C::STAGE_BYTES;         // [EPI_WARPS][4096], 1024-aligned
@@ -112,17 +127,22 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? (int)ptx::cluster_ctarank() : 0;  // position in the CTA pair (0 = leader)
   const int mtiles_per_b = p.tiles_w * p.tiles_h;
   const int m_tiles = mtiles_per_b * p.nb;
   const int n_tiles = (p.ncols + BLOCK_N - 1) / BLOCK_N;
-  const int total = m_tiles * n_tiles * p.splits;
+  // work item = (pair of consecutive m-tiles | one m-tile, n-tile, K split); CTA `rank` of a pair takes m-tile 2j + rank.  A
+  // phantom odd tile decodes to batch index nb: its loads are out of bounds (zero fill) and it stores nothing.
+  const int total = ((m_tiles + CTAS - 1) / CTAS) * n_tiles * p.splits;
+  const int w_first = blockIdx.x / CTAS, w_step = gridDim.x / CTAS;
   const int k_blocks_all = p.K / BLOCK_K;
   auto decode = [&](int w) {
     TileCoord t;
     const int tg = w / p.splits;
     t.sp = w - tg * p.splits;
-    const int mt = tg / n_tiles;
-    t.n0 = (tg - mt * n_tiles) * BLOCK_N;
+    const int mt2 = tg / n_tiles;
+    t.n0 = (tg - mt2 * n_tiles) * BLOCK_N;
+    const int mt = mt2 * CTAS + rank;
     t.b = mt / mtiles_per_b;
     const int r = mt - t.b * mtiles_per_b;
     const int th = r / p.tiles_w;
@@ -142,22 +162,28 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], EPI_WARPS * 32);
+      ptx::mbar_init(&tmem_empty[i], EPI_WARPS * CTAS);  // lane 0 of every epilogue warp of the pair
     }
     for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == MMA_WARP) ptx::tmem_alloc<C::TMEM_COLS>(tmem_holder);
+  if (warp == MMA_WARP) {
+    if (CTAS == 2) ptx::tmem_alloc_2cta<C::TMEM_COLS>(tmem_holder);
+    else ptx::tmem_alloc<C::TMEM_COLS>(tmem_holder);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTAS == 2) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // barriers, TMEM and tensor-map prefetch above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA: activation groups + weight tiles
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = w_first; w < total; w += w_step) {
         const TileCoord t = decode(w);
         const int n0 = t.n0;
         const int kb_lo = t.sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
@@ -167,21 +193,31 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 201);
           const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(st, &tmap_a, &full_bar[stage], slab * 128, ax + kx, ay + ky, t.b);
-          tma_load_4d(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], slab * 128 + 64, ax + kx, ay + ky, t.b);
-          ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
-          ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage],
-                           kb * BLOCK_K, p.plane_rows + n0);
+          if (CTAS == 2) {
+            // both CTAs' boxes are counted on the leader's barrier, which alone expects the pair's bytes
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const int nr = n0 + rank * C::B_ROWS;
+            ptx::tma_load_4d_2cta(st, &tmap_a, &full_bar[stage], slab * 128, ax + kx, ay + ky, t.b);
+            ptx::tma_load_4d_2cta(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], slab * 128 + 64, ax + kx, ay + ky, t.b);
+            ptx::tma_load_2d_2cta(st + 2 * A_GROUP_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, nr);
+            ptx::tma_load_2d_2cta(st + 2 * A_GROUP_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, p.plane_rows + nr);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_4d(st, &tmap_a, &full_bar[stage], slab * 128, ax + kx, ay + ky, t.b);
+            tma_load_4d(st + A_GROUP_BYTES, &tmap_a, &full_bar[stage], slab * 128 + 64, ax + kx, ay + ky, t.b);
+            ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0);
+            ptx::tma_load_2d(smem + stage * C::STAGE_BYTES + 2 * A_GROUP_BYTES + C::B_TILE_BYTES, &tmap_w, &full_bar[stage],
+                             kb * BLOCK_K, p.plane_rows + n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+  } else if (warp == MMA_WARP && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M * CTAS, BLOCK_N);
     int stage = 0, phase = 0, it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (int w = w_first; w < total; w += w_step, ++it) {
       const int sp = w % p.splits;
       const int kb_lo = sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -200,18 +236,29 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t at = a0 + (ks >> 1) * A_GROUP_BYTES + (ks & 1) * 32;
             const uint64_t dah = ptx::umma_desc_sw128(at), dal = ptx::umma_desc_sw128(at + 64);
             const uint64_t dbh = ptx::umma_desc_sw128(b_hi + ks * 32), dbl = ptx::umma_desc_sw128(b_lo + ks * 32);
-            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb != kb_lo) || (ks != 0));  // small terms first
-            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
-            ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+            if (CTAS == 2) {
+              ptx::umma_bf16_2cta(d_tmem, dal, dbh, idesc, (kb != kb_lo) || (ks != 0));
+              ptx::umma_bf16_2cta(d_tmem, dah, dbl, idesc, 1);
+              ptx::umma_bf16_2cta(d_tmem, dah, dbh, idesc, 1);
+            } else {
+              ptx::umma_bf16(d_tmem, dal, dbh, idesc, (kb != kb_lo) || (ks != 0));  // small terms first
+              ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+              ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+            }
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (kb == kb_hi - 1) ptx::umma_commit(&tmem_full[acc]);
+          if (CTAS == 2) {
+            ptx::umma_commit_2cta(&empty_bar[stage]);  // frees the stage in both CTAs
+            if (kb == kb_hi - 1) ptx::umma_commit_2cta(&tmem_full[acc]);
+          } else {
+            ptx::umma_commit(&empty_bar[stage]);
+            if (kb == kb_hi - 1) ptx::umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;    // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
     const int hf = warp >> 2;  // column half
@@ -222,7 +269,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* rbar = &res_bar[warp];
     uint32_t res_phase = 0;
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (int w = w_first; w < total; w += w_step, ++it) {
       const TileCoord t = decode(w);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       // this warp's 32 tile rows = a (min(BW,32) x 32/min(BW,32)) box of output pixels starting at (ow, oh)
@@ -232,7 +279,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int col_base = t.n0 + hf * (BLOCK_N / 2);
       int nch = (p.ncols - col_base + 31) / 32;
       nch = nch < 0 ? 0 : (nch > C::CHUNKS ? C::CHUNKS : nch);
-      if (ow >= p.lim_w || oh >= p.lim_h) nch = 0;  // box entirely in the tail: nothing to store
+      if (ow >= p.lim_w || oh >= p.lim_h || t.b >= p.nb) nch = 0;  // box entirely in the tail (or a phantom tile): nothing to store
       bool keep = true;
       if (p.row_keep != nullptr && nch > 0 && ow + lane < p.lim_w)  // rows mode only
         keep = p.row_keep[(long long)t.b * p.keep_bstride + p.keep_off + ow + lane] != 0;
@@ -243,8 +290,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       ptx::mbar_wait(&tmem_full[acc], acc_phase, err, 205);
       ptx::tc_fence_after();
       if (nch == 0) {
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tmem_empty[acc]);
+        release_tmem_stage<CTAS>(&tmem_empty[acc], lane);
         continue;
       }
       uint32_t r[32];
@@ -260,6 +306,8 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (ci + 1 < nch) {  // next chunk's accumulator read overlaps this chunk's arithmetic and store
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * (BLOCK_N / 2) + (ci + 1) * 32, r);
+        } else {  // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp right away
+          release_tmem_stage<CTAS>(&tmem_empty[acc], lane);
         }
         if (p.bias != nullptr) {
 #pragma unroll
@@ -309,6 +357,11 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             o[16 + j] = pack_bf16x2(l0, l1);
           }
         }
+        if (!p.has_res) {
+          // the previous store's read of the staging box was left in flight behind this chunk's arithmetic
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_s + ((c ^ sw) << 4)), "r"(o[4 * c]), "r"(o[4 * c + 1]),
@@ -318,27 +371,28 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (lane == 0) {
           tma_store_4d(&tmap_out, stg_s, n, ow, oh, zc);
           bulk_commit();
-          bulk_wait_read0();  // the staging box may be overwritten once TMA has read it
-          if (p.has_res && ci + 1 < nch) {
-            ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
-            tma_load_4d(stg_s, &tmap_res, rbar, n + 32, ow, oh, zc);
+          if (p.has_res) {
+            bulk_wait_read0();  // the staging box doubles as the residual landing zone: it must be free before the next load
+            if (ci + 1 < nch) {
+              ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
+              tma_load_4d(stg_s, &tmap_res, rbar, n + 32, ow, oh, zc);
+            }
           }
         }
-        __syncwarp();
-        if (ci + 1 == nch) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tmem_empty[acc]);
-        }
+        if (p.has_res) __syncwarp();
       }
     }
     if (lane == 0) bulk_wait0();  // all stores of this warp have left shared memory and are complete
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();  // single-lane roles reconverge before the aligned barrier
+  if (CTAS == 2) ptx::cluster_sync_all();  // the peer may still signal this CTA's barriers / read its operand tiles
+  else __syncthreads();
   if (warp == MMA_WARP) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CTAS == 2) ptx::tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+    else ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -362,31 +416,60 @@ __device__ __forceinline__ float p32_load(const void* base, long long row, int l
 
 __global__ void __launch_bounds__(256)
 p32_reduce_kernel(const ReduceArgs a) {
-  const int groups = a.N / 32;
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= (long long)a.M * groups) return;
-  const long long m = wid / groups;
-  const int n = (int)(wid - m * groups) * 32 + lane;
-  float acc = 0.f;
-  for (int s = 0; s < a.splits; ++s) acc += a.partial[((long long)s * a.M + m) * a.Npad + n];
+  pdl_entry();
+  // one thread = four consecutive channels of one row: float4 partial-sum loads, four splits in flight at a time
+  const int n4 = a.N >> 2;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)a.M * n4) return;
+  const long long m = i / n4;
+  const int n = (int)(i - m * n4) * 4;
+  const float* src = a.partial + m * a.Npad + n;
+  const long long sstride = (long long)a.M * a.Npad;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= a.splits; s += 4) {
+    const float4 v0 = *(const float4*)(src + (s + 0) * sstride), v1 = *(const float4*)(src + (s + 1) * sstride);
+    const float4 v2 = *(const float4*)(src + (s + 2) * sstride), v3 = *(const float4*)(src + (s + 3) * sstride);
+    acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+    acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+  }
+  for (; s < a.splits; ++s) {
+    const float4 v = *(const float4*)(src + s * sstride);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
   long long orow = m;
   if (a.rows_per_b > 0) {
     const long long b = m / a.rows_per_b;
     orow = b * a.bstride + a.off + (m - b * a.rows_per_b);
   }
-  if (a.bias) acc += __ldg(a.bias + n);
-  if (a.res) acc += a.res_fmt ? p32_load(a.res, orow, a.ldr, n) : ((const float*)a.res)[orow * a.ldr + n];
-  if (a.relu) acc = fmaxf(acc, 0.f);
-  if (a.row_keep && !a.row_keep[orow]) acc = 0.f;
+  if (a.bias) {
+    const float4 b4 = __ldg((const float4*)(a.bias + n));
+    acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+  }
+  if (a.res) {
+    if (a.res_fmt) {
+      acc.x += p32_load(a.res, orow, a.ldr, n); acc.y += p32_load(a.res, orow, a.ldr, n + 1);
+      acc.z += p32_load(a.res, orow, a.ldr, n + 2); acc.w += p32_load(a.res, orow, a.ldr, n + 3);
+    } else {
+      const float4 r4 = *(const float4*)((const float*)a.res + orow * a.ldr + n);
+      acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
+    }
+  }
+  if (a.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  if (a.row_keep && !a.row_keep[orow]) acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (a.out_fmt == 0) {
-    ((float*)a.out)[orow * a.ldo + n] = acc;
+    *(float4*)((float*)a.out + orow * a.ldo + n) = acc;
   } else {
-    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
-    const __nv_bfloat16 l = __float2bfloat16_rn(acc - __bfloat162float(h));
-    __nv_bfloat16* g = (__nv_bfloat16*)((uint8_t*)a.out + (orow * a.ldo + (n & ~31)) * 4);
-    g[lane] = h;
-    g[32 + lane] = l;
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    split_bf16(acc.x, h0, l0); split_bf16(acc.y, h1, l1); split_bf16(acc.z, h2, l2); split_bf16(acc.w, h3, l3);
+    uint2 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+    uint8_t* g = (uint8_t*)a.out + (orow * a.ldo + (n & ~31)) * 4 + (n & 31) * 2;
+    *(uint2*)g = ph;
+    *(uint2*)(g + 64) = pl;
   }
 }
 
@@ -513,10 +596,10 @@ int pick_bw_log2(int OW, int OH) {
   return best;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                cudaStream_t st) {
-  using C = PCfg<BLOCK_N>;
+  using C = PCfg<BLOCK_N, CTAS>;
   const bool conv = a.mode == 1;
   PArgs p = {};
   p.M = M; p.N = N; p.K = K;
@@ -562,7 +645,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
                           pitch * rows_per_b, 64, BLOCK_M, 1), &ta);
   }
   if (rc != EGTR_OK) return rc;
-  rc = cached_map(desc2(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, 2ull * plane_rows, 2ull * K, BLOCK_K, BLOCK_N), &tw);
+  rc = cached_map(desc2(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, 2ull * plane_rows, 2ull * K, BLOCK_K, C::B_ROWS), &tw);
   if (rc != EGTR_OK) return rc;
   const unsigned box_w = BW < 32 ? BW : 32, box_h = 32 / box_w;  // one epilogue warp's 32 tile rows
   float* partial = nullptr;
@@ -602,21 +685,22 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   }
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int work = m_tiles * cdiv(p.ncols, BLOCK_N) * splits;
-  const int grid = work < num_sms() ? work : num_sms();
-  gemm_p32_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tw, to, tr, p, device_error_flag_p32());
-  EGTR_CUDA(cudaGetLastError());
+  const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
+  const int slots = num_sms() / CTAS;
+  const int grid = (work < slots ? work : slots) * CTAS;
+  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS>, dim3(grid), dim3(NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, p,
+                       device_error_flag_p32()));
   if (splits > 1) {
     ReduceArgs r = {};
     r.partial = partial; r.splits = splits; r.M = M; r.N = N; r.Npad = Npad;
     r.bias = ep.bias; r.res = ep.res; r.out = ep.out; r.ldo = ep.ldo; r.ldr = ep.ldr; r.relu = ep.relu;
     r.out_fmt = ep.out_fmt; r.res_fmt = ep.res_fmt; r.row_keep = conv ? nullptr : ep.row_keep;
     r.rows_per_b = ep.rows_per_b; r.bstride = ep.bstride; r.off = ep.off;
-    const long long threads = (long long)M * (N / 32) * 32;
-    p32_reduce_kernel<<<cdiv(threads, 256), 256, 0, st>>>(r);
+    const long long threads = (long long)M * (N / 4);
+    launch_pdl(p32_reduce_kernel, dim3(cdiv(threads, 256)), dim3(256), (size_t)(0), st, r);
     count_launch();
     EGTR_CUDA(cudaGetLastError());
   }
@@ -647,9 +731,20 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   int bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N >= 192 ? 128 : 64));
   if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
-  if (bn == 256) return launch_p32<256>(a, planes, plane_rows, M, N, Npad, K, ep, st);
-  if (bn == 128) return launch_p32<128>(a, planes, plane_rows, M, N, Npad, K, ep, st);
-  return launch_p32<64>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  // CTA pairs (cta_group::2) for every 128/256-wide tile shape with at least two m-tiles: measured through the whole forward,
+  // pairs everywhere beat both 1-CTA tiles and a size threshold (less L2->SM weight traffic, one more pipeline stage)
+  static const int forced_ctas = [] { const char* e = getenv("EGTR_GEMM_CTAS"); return e ? atoi(e) : 0; }();  // dev experiments only
+  const long long tiles = (long long)cdiv(M, BLOCK_M) * cdiv(N, bn);
+  bool pair = bn >= 128 && tiles >= 2;
+  if (forced_ctas == 1) pair = false;
+  if (forced_ctas == 2 && bn >= 128) pair = true;
+  if (pair) {
+    if (bn == 256) return launch_p32<256, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+    return launch_p32<128, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  }
+  if (bn == 256) return launch_p32<256, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  if (bn == 128) return launch_p32<128, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+  return launch_p32<64, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st);
 }
 
 }  // namespace egtr

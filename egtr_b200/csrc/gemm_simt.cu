@@ -11,6 +11,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const ASrc src, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
+  pdl_entry();
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -108,6 +109,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // per CTA keeps two CTAs resident per SM.
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
+  pdl_entry();
   extern __shared__ __align__(16) float sk_smem[];
   const int g = blockIdx.z;
   const float* __restrict__ A = gt.a[g];
@@ -215,7 +217,7 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
     attr = true;
   }
   dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), groups);
-  gemm_skinny_kernel<<<grid, 256, SK_SMEM_BYTES, (cudaStream_t)s>>>(gt, w, M, N, K, *ep);
+  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, *ep);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -231,7 +233,7 @@ extern "C" int egtr_gemm_f32(const egtr_asrc_t* a, const float* w, int M, int N,
   EGTR_CHECK(a->mode != 0 || a->lda % 4 == 0, EGTR_ERR_ARG, "egtr_gemm_f32: lda %% 4 != 0");
   dim3 grid(cdiv(N, TN), cdiv(M, TM));
   EGTR_CHECK(grid.y <= 65535, EGTR_ERR_ARG, "egtr_gemm_f32: M too large for this path (%d)", M);
-  gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(*a, w, M, N, K, *ep);
+  launch_pdl(gemm_f32_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, *a, w, M, N, K, *ep);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

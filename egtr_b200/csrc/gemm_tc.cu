@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, const Epilogue ep, int M, int N,
                   int Npad, int K, int splits, int kb_per_split, float* __restrict__ partial, int groups, int plane_rows,
                   const GroupTab tab, int* __restrict__ err) {
+  pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -131,6 +132,7 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // barriers, TMEM and tensor-map prefetch above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 4) {
@@ -661,6 +663,7 @@ int* device_error_flag() {
 // out = epilogue(sum over splits of partial[s][m][n])
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, int Npad, const Epilogue ep) {
+  pdl_entry();
   const int n4 = (N + 3) / 4;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)M * n4) return;
@@ -735,11 +738,11 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   }
   const int work = tiles * splits;
   const int grid = work < num_sms() ? work : num_sms();
-  gemm_sbf16_kernel<BLOCK_N, MODE, REL><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
+  launch_pdl(gemm_sbf16_kernel<BLOCK_N, MODE, REL>, dim3(grid), dim3(NUM_THREADS), (size_t)(C::SMEM_BYTES), st, tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {
     const long long n = (long long)M * ((N + 3) / 4);
-    splitk_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(partial, splits, M, N, Npad, ep);
+    launch_pdl(splitk_reduce_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), st, partial, splits, M, N, Npad, ep);
     count_launch();
     EGTR_CUDA(cudaGetLastError());
   }
@@ -748,6 +751,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
 
 // fp32 [N,K] -> bf16 hi/lo planes [2][Npad][K]
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, int Npad, __nv_bfloat16* __restrict__ planes) {
+  pdl_entry();
   const long long total = (long long)Npad * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / K);
@@ -794,7 +798,7 @@ extern "C" int egtr_split_weight_bf16(const float* w, int N, int K, int Npad, vo
   const long long total = (long long)Npad * K;
   int grid = cdiv(total, 256);
   if (grid > 4 * 148) grid = 4 * 148;
-  split_weight_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(w, N, K, Npad, (__nv_bfloat16*)planes);
+  launch_pdl(split_weight_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, w, N, K, Npad, (__nv_bfloat16*)planes);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -50,6 +50,7 @@ struct MsdaArgs {
 template <bool FUSED>
 __global__ void __launch_bounds__(256, 6)
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
+  pdl_entry();
   __shared__ float slots[QPB * Q_STRIDE];
   __shared__ int q_of[QPB];
   __shared__ float2 q_ref[QPB];  // encoder form: pixel centre / (valid_ratio * size) of the query's own level
@@ -247,7 +248,7 @@ extern "C" int egtr_msda_fwd_f32(const float* value, const int64_t* spatial_shap
   Levels lv = {};
   lv.L = L;
   dim3 grid(cdiv(Lq, QPB), M, B);
-  msda_kernel<false><<<grid, 256, 0, (cudaStream_t)s>>>(a, lv);
+  launch_pdl(msda_kernel<false>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -283,7 +284,7 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   a.ref_points = ref_points; a.valid_ratios = valid_ratios;
   a.out = out; a.out_fmt = out_fmt; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
   dim3 grid(enc_ref ? patches : cdiv(Lq, QPB), M, B);
-  msda_kernel<true><<<grid, 256, 0, (cudaStream_t)s>>>(a, lv);
+  launch_pdl(msda_kernel<true>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -11,6 +11,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                         const float* __restrict__ beta, int rows, float* __restrict__ out) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -64,6 +65,7 @@ __device__ __forceinline__ float4 p32_load4(const uint8_t* row, int c) {
 
 __global__ void __launch_bounds__(256)
 rows_to_p32_kernel(const float* __restrict__ x, const float* __restrict__ addend, long long rows, int C4, int ldx, uint8_t* __restrict__ out) {
+  pdl_entry();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long row = i / C4;
   if (row >= rows) return;
@@ -78,6 +80,7 @@ rows_to_p32_kernel(const float* __restrict__ x, const float* __restrict__ addend
 
 __global__ void __launch_bounds__(256)
 p32_to_rows_kernel(const uint8_t* __restrict__ p32, long long rows, int C4, float* __restrict__ out, int ldo) {
+  pdl_entry();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long row = i / C4;
   if (row >= rows) return;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(256)
 add_layernorm256_p32_kernel(const float* __restrict__ x, const uint8_t* __restrict__ res, int res_fmt, const float* __restrict__ gamma,
                             const float* __restrict__ beta, int rows, uint8_t* __restrict__ out_p32, float* __restrict__ out_f32,
                             const float* __restrict__ addend, uint8_t* __restrict__ out_plus) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -139,6 +143,7 @@ add_layernorm256_p32_kernel(const float* __restrict__ x, const uint8_t* __restri
 
 // ------------------------------------------------------------------ zero masked rows
 __global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const uint8_t* __restrict__ keep, long long rows) {
+  pdl_entry();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long row = i / C4;
   if (row >= rows) return;
@@ -148,6 +153,7 @@ __global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const ui
 // ------------------------------------------------------------------ NCHW (C=3) -> zero-padded NHWC4
 // one float4 per padded pixel; the border and the 4th channel are zero so the stem's gather needs no bounds checks
 __global__ void pad_nhwc4_kernel(const float* __restrict__ img, int B, int H, int W, int pad, float4* __restrict__ out) {
+  pdl_entry();
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)B * Hp * Wp) return;
@@ -165,6 +171,7 @@ __global__ void pad_nhwc4_kernel(const float* __restrict__ img, int B, int H, in
 
 // ------------------------------------------------------------------ 3x3/2 pad 1 max-pool, NHWC
 __global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W, int C4, int OH, int OW, float* __restrict__ out, int out_fmt) {
+  pdl_entry();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * OH * OW * C4;
   if (i >= total) return;
@@ -195,6 +202,7 @@ __global__ void maxpool_kernel(const float* __restrict__ x, int B, int H, int W,
 constexpr int GN_ROWS = 64;  // rows per CTA
 __global__ void __launch_bounds__(256)
 groupnorm_partial_kernel(const float* __restrict__ x, int rows_per_b, int bstride, int off, double* __restrict__ part) {
+  pdl_entry();
   // thread = (row lane r8 in 0..7, float4 column c in 0..63 -> group c/2)
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int c = threadIdx.x & 63, r8 = threadIdx.x >> 6;  // 4 row lanes x 64 float4 columns
@@ -225,6 +233,7 @@ groupnorm_partial_kernel(const float* __restrict__ x, int rows_per_b, int bstrid
 // one warp per (image, group): fold the chunk partials into mean / rstd (float2 at the head of the scratch area)
 __global__ void __launch_bounds__(32)
 groupnorm_finalize_kernel(const double* __restrict__ part, int nchunks, int rows_per_b, float2* __restrict__ stats) {
+  pdl_entry();
   const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
   double a = 0.0, q = 0.0;
   for (int k = lane; k < nchunks; k += 32) {
@@ -248,6 +257,7 @@ groupnorm_finalize_kernel(const double* __restrict__ part, int nchunks, int rows
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int off, const float2* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta) {
+  pdl_entry();
   const int b = blockIdx.y, chunk = blockIdx.x;
   __shared__ float mean_s[32], rstd_s[32];
   if (threadIdx.x < 32) {
@@ -277,6 +287,7 @@ struct GeoLevels {
 // nearest-neighbour level masks: one thread per token (legacy 'nearest': src = floor(dst * in/out), fp32 scale)
 __global__ void __launch_bounds__(256)
 level_mask_gather_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, GeoLevels lv, int S, uint8_t* __restrict__ mask_flat) {
+  pdl_entry();
   const int tok = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
   if (tok >= S) return;
   int l = 0;
@@ -292,6 +303,7 @@ level_mask_gather_kernel(const int64_t* __restrict__ pixel_mask, int H, int W, G
 __global__ void __launch_bounds__(256)
 level_scans_kernel(GeoLevels lv, int S, const uint8_t* __restrict__ mask_flat, float* __restrict__ ycum, float* __restrict__ xcum,
                    float* __restrict__ valid_ratios) {
+  pdl_entry();
   const int l = blockIdx.x, b = blockIdx.y;
   const int h = lv.h[l], w = lv.w[l];
   const uint8_t* mk = mask_flat + (long long)b * S + lv.start[l];
@@ -321,6 +333,7 @@ level_scans_kernel(GeoLevels lv, int S, const uint8_t* __restrict__ mask_flat, f
 __global__ void __launch_bounds__(256)
 pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum, GeoLevels lv, int S, const float* __restrict__ level_embed,
                  const float* __restrict__ dim_t_tab, float* __restrict__ pos) {
+  pdl_entry();
   // 2 tokens per CTA; thread = one (sin, cos) channel pair: channels 2j, 2j+1 share dim_t (860-865), so one sincosf serves both
   const int tok = blockIdx.x * 2 + (threadIdx.x >> 7), b = blockIdx.y, j = threadIdx.x & 127;
   if (tok >= S) return;
@@ -350,6 +363,7 @@ pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum,
 // grid (heads, B, ceil(N/8)); 8 warps, one query per warp; K,V of the head staged in smem.
 __global__ void __launch_bounds__(256)
 mha_core_kernel(const float* __restrict__ qkv, int ld, int N, int C, float* __restrict__ out) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* ks = sm;                   // [N][33]
   float* vs = sm + (size_t)N * 33;  // [N][32]
@@ -400,6 +414,7 @@ mha_core_kernel(const float* __restrict__ qkv, int ld, int N, int C, float* __re
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bvec, int rows, int K,
                     int N, int act, const float* __restrict__ ref, int ld_ref, int ref_rows, float* __restrict__ y, int ldy) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -438,7 +453,7 @@ extern "C" int egtr_add_layernorm_f32(const float* x, const float* res, const fl
                                       int C, float* out, egtr_stream_t s) {
   EGTR_CHECK(x && gamma && beta && out && rows > 0, EGTR_ERR_ARG, "egtr_add_layernorm_f32: bad arguments");
   EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_f32: built for d_model 256 (got %d)", C);
-  add_layernorm256_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, res, gamma, beta, rows, out);
+  launch_pdl(add_layernorm256_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, x, res, gamma, beta, rows, out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -449,7 +464,7 @@ extern "C" int egtr_add_layernorm_p32(const float* x, const void* res, int res_f
   EGTR_CHECK(x && gamma && beta && rows > 0 && (out_p32 || out_f32 || out_plus_p32), EGTR_ERR_ARG, "egtr_add_layernorm_p32: bad arguments");
   EGTR_CHECK(!out_plus_p32 || addend, EGTR_ERR_ARG, "egtr_add_layernorm_p32: out_plus_p32 needs an addend");
   EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_p32: built for d_model 256 (got %d)", C);
-  add_layernorm256_p32_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, (const uint8_t*)res, res_fmt, gamma, beta, rows,
+  launch_pdl(add_layernorm256_p32_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, x, (const uint8_t*)res, res_fmt, gamma, beta, rows,
                                                                          (uint8_t*)out_p32, out_f32, addend, (uint8_t*)out_plus_p32);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
@@ -459,7 +474,7 @@ extern "C" int egtr_add_layernorm_p32(const float* x, const void* res, int res_f
 extern "C" int egtr_rows_to_p32(const float* x, const float* addend, int rows, int C, int ldx, void* out, egtr_stream_t s) {
   EGTR_CHECK(x && out && rows > 0 && C > 0 && C % 32 == 0 && ldx % 4 == 0 && ldx >= C, EGTR_ERR_ARG, "egtr_rows_to_p32: bad arguments (C=%d ldx=%d)", C, ldx);
   const long long total = (long long)rows * (C / 4);
-  rows_to_p32_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, addend, rows, C / 4, ldx, (uint8_t*)out);
+  launch_pdl(rows_to_p32_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, x, addend, rows, C / 4, ldx, (uint8_t*)out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -468,7 +483,7 @@ extern "C" int egtr_rows_to_p32(const float* x, const float* addend, int rows, i
 extern "C" int egtr_p32_to_rows(const void* p32, int rows, int C, float* out, int ldo, egtr_stream_t s) {
   EGTR_CHECK(p32 && out && rows > 0 && C > 0 && C % 32 == 0 && ldo % 4 == 0 && ldo >= C, EGTR_ERR_ARG, "egtr_p32_to_rows: bad arguments (C=%d ldo=%d)", C, ldo);
   const long long total = (long long)rows * (C / 4);
-  p32_to_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>((const uint8_t*)p32, rows, C / 4, out, ldo);
+  launch_pdl(p32_to_rows_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, (const uint8_t*)p32, rows, C / 4, out, ldo);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -477,7 +492,7 @@ extern "C" int egtr_p32_to_rows(const void* p32, int rows, int C, float* out, in
 extern "C" int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s) {
   EGTR_CHECK(x && keep && rows > 0 && C % 4 == 0 && ld % 4 == 0, EGTR_ERR_ARG, "egtr_mask_rows_f32: bad arguments");
   const long long total = (long long)rows * (C / 4);
-  mask_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, ld, C / 4, keep, rows);
+  launch_pdl(mask_rows_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, x, ld, C / 4, keep, rows);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -486,7 +501,7 @@ extern "C" int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, 
 extern "C" int egtr_pad_nchw3_to_nhwc4_f32(const float* img, int B, int H, int W, int pad, float* out, egtr_stream_t s) {
   EGTR_CHECK(img && out && B > 0 && H > 0 && W > 0 && pad >= 0, EGTR_ERR_ARG, "egtr_pad_nchw3_to_nhwc4_f32: bad arguments");
   const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad);
-  pad_nhwc4_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(img, B, H, W, pad, (float4*)out);
+  launch_pdl(pad_nhwc4_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, img, B, H, W, pad, (float4*)out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -501,7 +516,7 @@ extern "C" int egtr_maxpool3x3s2_nhwc_ex(const float* x, int B, int H, int W, in
              "egtr_maxpool3x3s2_nhwc: bad arguments");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)B * OH * OW * (C / 4);
-  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(x, B, H, W, C / 4, OH, OW, (float*)out, out_fmt);
+  launch_pdl(maxpool_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, x, B, H, W, C / 4, OH, OW, (float*)out, out_fmt);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -514,9 +529,9 @@ extern "C" int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, 
   dim3 grid(cdiv(rows_per_b, GN_ROWS), B);
   double* part = scratch + B * 32;  // first B*32 doubles hold the float2 (mean, rstd) table
   float2* stats = (float2*)scratch;
-  groupnorm_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, part);
-  groupnorm_finalize_kernel<<<dim3(32, B), 32, 0, (cudaStream_t)s>>>(part, grid.x, rows_per_b, stats);
-  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, rows_per_b, bstride, off, stats, gamma, beta);
+  launch_pdl(groupnorm_partial_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, x, rows_per_b, bstride, off, part);
+  launch_pdl(groupnorm_finalize_kernel, dim3(dim3(32, B)), dim3(32), (size_t)(0), (cudaStream_t)s, part, grid.x, rows_per_b, stats);
+  launch_pdl(groupnorm_apply_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, x, rows_per_b, bstride, off, stats, gamma, beta);
   count_launch();
   count_launch();
   count_launch();
@@ -545,10 +560,10 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
   }
   float* ycum = scratch;
   float* xcum = scratch + (long long)B * S;
-  level_mask_gather_kernel<<<dim3(cdiv(S, 256), B), 256, 0, (cudaStream_t)s>>>(pixel_mask, H, W, lv, S, mask_flat);
-  level_scans_kernel<<<dim3(L, B), 256, 0, (cudaStream_t)s>>>(lv, S, mask_flat, ycum, xcum, valid_ratios);
+  launch_pdl(level_mask_gather_kernel, dim3(dim3(cdiv(S, 256), B)), dim3(256), (size_t)(0), (cudaStream_t)s, pixel_mask, H, W, lv, S, mask_flat);
+  launch_pdl(level_scans_kernel, dim3(dim3(L, B)), dim3(256), (size_t)(0), (cudaStream_t)s, lv, S, mask_flat, ycum, xcum, valid_ratios);
   count_launch();
-  pos_embed_kernel<<<dim3(cdiv(S, 2), B), 256, 0, (cudaStream_t)s>>>(ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
+  launch_pdl(pos_embed_kernel, dim3(dim3(cdiv(S, 2), B)), dim3(256), (size_t)(0), (cudaStream_t)s, ycum, xcum, lv, S, level_embed, dim_t, pos_flat);
   count_launch();
   count_launch();
   EGTR_CUDA(cudaGetLastError());
@@ -564,7 +579,7 @@ extern "C" int egtr_mha_core_f32(const float* qkv, int ld, int B, int N, int hea
     EGTR_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 320 * 65 * 4));
     attr = true;
   }
-  mha_core_kernel<<<dim3(heads, B, cdiv(N, 8)), 256, smem, (cudaStream_t)s>>>(qkv, ld, N, heads * D, out);
+  launch_pdl(mha_core_kernel, dim3(dim3(heads, B, cdiv(N, 8))), dim3(256), (size_t)(smem), (cudaStream_t)s, qkv, ld, N, heads * D, out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -574,7 +589,7 @@ extern "C" int egtr_small_linear_f32(const float* x, int ldx, const float* w, co
                                      int act, const float* ref, int ld_ref, int ref_rows, float* y, int ldy, egtr_stream_t s) {
   EGTR_CHECK(x && w && y && rows > 0 && K > 0 && N >= 1 && N <= 8, EGTR_ERR_ARG, "egtr_small_linear_f32: bad arguments (N=%d)", N);
   EGTR_CHECK(act != 2 || ref != nullptr, EGTR_ERR_ARG, "egtr_small_linear_f32: act 2 needs reference points");
-  small_linear_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, ldx, w, b, rows, K, N, act, ref, ld_ref, ref_rows > 0 ? ref_rows : rows, y, ldy);
+  launch_pdl(small_linear_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, x, ldx, w, b, rows, K, N, act, ref, ld_ref, ref_rows > 0 ? ref_rows : rows, y, ldy);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

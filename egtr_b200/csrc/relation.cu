@@ -18,6 +18,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 pair_hidden_kernel(const float* __restrict__ U, const float* __restrict__ V, int ldu, const float* __restrict__ b1, int N, int Lr,
                    float* __restrict__ H1) {
+  pdl_entry();
   __shared__ float us[7 * 516];
   __shared__ float gate[32][8];
   const int b = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * 32;
@@ -55,6 +56,7 @@ pair_hidden_kernel(const float* __restrict__ U, const float* __restrict__ V, int
 
 // argmax over class logits, first maximum wins (torch.argmax)
 __global__ void argmax_kernel(const float* __restrict__ logits, int K, int rows, int* __restrict__ out) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256)
 finish_kernel(const float* __restrict__ rel_logits, int ld_rel, const float* __restrict__ conn_logits, int ld_conn,
               const int* __restrict__ cls, int K1, const float* __restrict__ triplet, const float* __restrict__ rel_dist, float tau,
               int use_freq, int logit_adj, int N, int P, long long pairs, float* __restrict__ pred_rel, float* __restrict__ pred_conn) {
+  pdl_entry();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= pairs * P) return;
   const long long pair = t / P;
@@ -105,7 +108,7 @@ extern "C" int egtr_relation_pair_hidden_f32(const float* U, const float* V, int
   EGTR_CHECK(U && V && b1 && H1 && B > 0 && N > 0, EGTR_ERR_ARG, "egtr_relation_pair_hidden_f32: bad arguments");
   EGTR_CHECK(Lr >= 1 && Lr <= 7 && ldu >= 513 && ldu <= 516 && ldu % 4 == 0 && N <= 65535 && B <= 65535, EGTR_ERR_UNSUPPORTED,
              "egtr_relation_pair_hidden_f32: Lr=%d ldu=%d", Lr, ldu);
-  pair_hidden_kernel<<<dim3(cdiv(N, 32), N, B), 256, 0, (cudaStream_t)s>>>(U, V, ldu, b1, N, Lr, H1);
+  launch_pdl(pair_hidden_kernel, dim3(dim3(cdiv(N, 32), N, B)), dim3(256), (size_t)(0), (cudaStream_t)s, U, V, ldu, b1, N, Lr, H1);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -119,9 +122,9 @@ extern "C" int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, con
              "egtr_relation_finish_f32: null pointer");
   EGTR_CHECK(!use_freq_bias || triplet_dist, EGTR_ERR_ARG, "egtr_relation_finish_f32: triplet_dist missing");
   EGTR_CHECK(!logit_adjustment || rel_dist, EGTR_ERR_ARG, "egtr_relation_finish_f32: rel_dist missing");
-  argmax_kernel<<<cdiv((long long)B * N, 8), 256, 0, (cudaStream_t)s>>>(logits, K, B * N, cls_scratch);
+  launch_pdl(argmax_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, logits, K, B * N, cls_scratch);
   const long long pairs = (long long)B * N * N;
-  finish_kernel<<<cdiv(pairs * P, 256), 256, 0, (cudaStream_t)s>>>(rel_logits, ld_rel, conn_logits, ld_conn, cls_scratch, K + 1,
+  launch_pdl(finish_kernel, dim3(cdiv(pairs * P, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, rel_logits, ld_rel, conn_logits, ld_conn, cls_scratch, K + 1,
                                                                   triplet_dist, rel_dist, tau, use_freq_bias, logit_adjustment, N, P,
                                                                   pairs, pred_rel, pred_conn);
   count_launch();
@@ -132,7 +135,7 @@ extern "C" int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, con
 
 extern "C" int egtr_argmax_rows_f32(const float* x, int cols, int rows, int* out, egtr_stream_t s) {
   EGTR_CHECK(x && out && cols > 0 && rows > 0, EGTR_ERR_ARG, "egtr_argmax_rows_f32: bad arguments");
-  argmax_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)s>>>(x, cols, rows, out);
+  launch_pdl(argmax_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, x, cols, rows, out);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

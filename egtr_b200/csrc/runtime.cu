@@ -1,5 +1,6 @@
 // Library-wide state: per-thread error string, launch counter, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -27,6 +28,12 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+// EGTR_B200_PDL: 0 = programmatic dependent launch off, 1 = every launch, 2 = launches of at least one CTA per SM
+int pdl_mode() {
+  static const int mode = [] { const char* e = getenv("EGTR_B200_PDL"); return e ? atoi(e) : 2; }();
+  return mode;
 }
 
 }  // namespace egtr

@@ -20,6 +20,7 @@ namespace {
 // ---------------------------------------------------------------- object scores / classes
 __global__ void __launch_bounds__(256)
 obj_scores_kernel(const float* __restrict__ logits, int K, int num_labels, int rows, float* __restrict__ score, int* __restrict__ cls) {
+  pdl_entry();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -49,6 +50,7 @@ obj_scores_kernel(const float* __restrict__ logits, int K, int num_labels, int r
 __global__ void __launch_bounds__(256)
 triplet_scores_kernel(const float* __restrict__ rel, const float* __restrict__ conn, const float* __restrict__ obj, int N, int P,
                       int single, long long total, float* __restrict__ out) {
+  pdl_entry();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= total) return;
   const long long pair = single ? t : t / P;
@@ -71,7 +73,8 @@ triplet_scores_kernel(const float* __restrict__ rel, const float* __restrict__ c
 
 // ---------------------------------------------------------------- radix select (two 16-bit passes)
 __global__ void __launch_bounds__(256)
-hist_hi_kernel(const float* __restrict__ sc, long long n, unsigned* __restrict__ hist) {  // hist [B][65536]
+hist_hi_kernel(const float* __restrict__ sc, long long n, unsigned* __restrict__ hist) {
+  pdl_entry();  // hist [B][65536]
   const int b = blockIdx.y;
   const float* x = sc + (long long)b * n;
   unsigned* h = hist + (long long)b * 65536;
@@ -80,7 +83,8 @@ hist_hi_kernel(const float* __restrict__ sc, long long n, unsigned* __restrict__
 }
 // one CTA per image: walk the histogram from the top, find the bin holding the k-th largest
 __global__ void __launch_bounds__(1024)
-pick_bin_kernel(const unsigned* __restrict__ hist, int k, unsigned* __restrict__ sel) {  // sel [B][4]: bin, need_in_bin, (lo passes reuse)
+pick_bin_kernel(const unsigned* __restrict__ hist, int k, unsigned* __restrict__ sel) {
+  pdl_entry();  // sel [B][4]: bin, need_in_bin, (lo passes reuse)
   const int b = blockIdx.x;
   const unsigned* h = hist + (long long)b * 65536;
   __shared__ unsigned part[1024];
@@ -107,6 +111,7 @@ pick_bin_kernel(const unsigned* __restrict__ hist, int k, unsigned* __restrict__
 }
 __global__ void __launch_bounds__(256)
 hist_lo_kernel(const float* __restrict__ sc, long long n, const unsigned* __restrict__ sel, unsigned* __restrict__ hist) {
+  pdl_entry();
   const int b = blockIdx.y;
   const float* x = sc + (long long)b * n;
   const unsigned bin = sel[b * 4];
@@ -117,7 +122,8 @@ hist_lo_kernel(const float* __restrict__ sc, long long n, const unsigned* __rest
   }
 }
 __global__ void __launch_bounds__(1024)
-pick_lo_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ sel) {  // -> sel[2] = exact threshold bits, sel[3] = ties to take
+pick_lo_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ sel) {
+  pdl_entry();  // -> sel[2] = exact threshold bits, sel[3] = ties to take
   const int b = blockIdx.x;
   const unsigned* h = hist + (long long)b * 65536;
   const unsigned need = sel[b * 4 + 1];
@@ -145,6 +151,7 @@ pick_lo_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ sel) { 
 __global__ void __launch_bounds__(256)
 collect_kernel(const float* __restrict__ sc, long long n, const unsigned* __restrict__ sel, int k, unsigned* __restrict__ counters,
                float* __restrict__ cand_score, long long* __restrict__ cand_idx) {
+  pdl_entry();
   const int b = blockIdx.y;
   const float* x = sc + (long long)b * n;
   const unsigned thr = sel[b * 4 + 2], ties = sel[b * 4 + 3];
@@ -163,6 +170,7 @@ __global__ void __launch_bounds__(128)
 emit_kernel(const float* __restrict__ cand_score, const long long* __restrict__ cand_idx, const unsigned* __restrict__ counters, int k,
             int N, int P, int single, const float* __restrict__ rel, const float* __restrict__ conn, int* __restrict__ inds,
             float* __restrict__ rel_scores) {
+  pdl_entry();
   const int b = blockIdx.x;
   extern __shared__ unsigned char sm_raw[];
   float* sc = (float*)sm_raw;
@@ -227,17 +235,17 @@ extern "C" int egtr_triplets_f32(const float* logits, const float* pred_rel, con
   long long* cand_idx = (long long*)base;             base += (long long)B * k * 8;
   float* cand_score = (float*)base;
   EGTR_CUDA(cudaMemsetAsync(hist_hi, 0, (size_t)B * 65536 * 4 * 2 + (size_t)B * 24, st));
-  obj_scores_kernel<<<cdiv((long long)B * N, 8), 256, 0, st>>>(logits, K, num_labels, B * N, obj_scores, pred_classes);
+  launch_pdl(obj_scores_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), (size_t)(0), st, logits, K, num_labels, B * N, obj_scores, pred_classes);
   const long long total = (long long)B * n;
-  triplet_scores_kernel<<<cdiv(total, 256), 256, 0, st>>>(pred_rel, pred_conn, obj_scores, N, P, single, total, scores);
+  launch_pdl(triplet_scores_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), st, pred_rel, pred_conn, obj_scores, N, P, single, total, scores);
   int gx = cdiv(n, 256 * 8);
   if (gx > 592) gx = 592;
-  hist_hi_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, hist_hi);
-  pick_bin_kernel<<<B, 1024, 0, st>>>(hist_hi, k, sel);
-  hist_lo_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, sel, hist_lo);
-  pick_lo_kernel<<<B, 1024, 0, st>>>(hist_lo, sel);
-  collect_kernel<<<dim3(gx, B), 256, 0, st>>>(scores, n, sel, k, counters, cand_score, cand_idx);
-  emit_kernel<<<B, 128, ((k * 4 + 7) / 8) * 8 + k * 8, st>>>(cand_score, cand_idx, counters, k, N, P, single, pred_rel, pred_conn, rel_inds, rel_scores);
+  launch_pdl(hist_hi_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, hist_hi);
+  launch_pdl(pick_bin_kernel, dim3(B), dim3(1024), (size_t)(0), st, hist_hi, k, sel);
+  launch_pdl(hist_lo_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, sel, hist_lo);
+  launch_pdl(pick_lo_kernel, dim3(B), dim3(1024), (size_t)(0), st, hist_lo, sel);
+  launch_pdl(collect_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, sel, k, counters, cand_score, cand_idx);
+  launch_pdl(emit_kernel, dim3(B), dim3(128), (size_t)(((k * 4 + 7) / 8) * 8 + k * 8), st, cand_score, cand_idx, counters, k, N, P, single, pred_rel, pred_conn, rel_inds, rel_scores);
   for (int i = 0; i < 8; ++i) count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -36,6 +36,7 @@ ap.add_argument("--only", type=str, default="")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--p32", action="store_true", help="feed plain-row shapes as P32 rows (TMA-fed kernel); --p32out also writes P32")
 ap.add_argument("--p32out", action="store_true")
+ap.add_argument("--noflush", action="store_true", help="do not flush L2 between iterations (operands stay L2-resident as inside the forward)")
 ap.add_argument("--prof", action="store_true", help="with an EGTR_GEMM_PROF build: print per-role cycle accounting")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -94,7 +95,8 @@ for idx, (name, M, N, K, kind) in enumerate(SHAPES):
         break
     ts = []
     for _ in range(args.iters):
-        flush.fill_(0)
+        if not args.noflush:
+            flush.fill_(0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run()
