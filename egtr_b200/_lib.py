@@ -47,6 +47,8 @@ SIGNATURES = {
     "egtr_gemm_sbf16_grouped": [_p, _p, _p, C.POINTER(_i), _i, C.POINTER(_i), _p, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _p],
     "egtr_gemm_f32_grouped": [_p, _p, _p, C.POINTER(_i), _i, C.POINTER(_i), _p, _i, _i, _i, C.POINTER(Epilogue), _p],
     "egtr_gemm_f32": [C.POINTER(ASrc), _p, _i, _i, _i, C.POINTER(Epilogue), _p],
+    "egtr_gemm_f32_splitk": [_p, _p, _i, _p, _i, _i, _i, _i, _p, _p],
+    "egtr_sum_layernorm_f32": [_p, _i, _ll, _p, _p, _p, _p, _i, _i, _p, _p, _i, _ll, _p],
     "egtr_msda_fwd_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "egtr_msda_fused_fwd_f32": [_p, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "egtr_add_layernorm_f32": [_p, _p, _p, _p, _i, _i, _p, _p],

@@ -108,10 +108,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // cp.async in one burst and the next chunk is already in flight while the current one is multiplied; 100 KB of smem
 // per CTA keeps two CTAs resident per SM.
 __global__ void __launch_bounds__(256)
-gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep) {
+gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep, int splits, int k_per,
+                   float* __restrict__ partial) {
   pdl_entry();
   extern __shared__ __align__(16) float sk_smem[];
-  const int g = blockIdx.z;
+  // blockIdx.z = group (grouped launch) or K split (split-K launch: raw partial sums, the consumer applies the epilogue)
+  const int g = splits > 1 ? 0 : blockIdx.z;
+  const int sp = splits > 1 ? blockIdx.z : 0;
+  const int k_lo = sp * k_per, k_hi = min(K, k_lo + k_per);
   const float* __restrict__ A = gt.a[g];
   const float* __restrict__ A2 = gt.a2[g];
   const int lda = gt.lda[g];
@@ -124,7 +128,7 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
     float* As = sk_smem + buf * SK_STAGE_FLOATS;
     float* A2s = As + SK_TM * SK_LD;
     float* Ws = A2s + SK_TM * SK_LD;
-    const int kc = min(SK_KC, K - k0) >> 2;  // float4 per row in this chunk
+    const int kc = min(SK_KC, k_hi - k0) >> 2;  // float4 per row in this chunk
     for (int i = tid; i < SK_TM * (SK_KC / 4); i += 256) {
       const int row = i / (SK_KC / 4), q = i - row * (SK_KC / 4);
       const bool ok = (m0 + row) < M && q < kc;
@@ -149,10 +153,10 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
   float acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = 0.f;
-  const int chunks = (K + SK_KC - 1) / SK_KC;
-  issue(0, 0);
+  const int chunks = (k_hi - k_lo + SK_KC - 1) / SK_KC;
+  issue(k_lo, 0);
   for (int c = 0; c < chunks; ++c) {
-    if (c + 1 < chunks) { issue((c + 1) * SK_KC, (c + 1) & 1); cp_async_wait<1>(); }
+    if (c + 1 < chunks) { issue(k_lo + (c + 1) * SK_KC, (c + 1) & 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
     const float* As = sk_smem + (c & 1) * SK_STAGE_FLOATS + r * SK_LD;
@@ -173,6 +177,14 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
   }
   const int m = m0 + r;
   if (m >= M) return;
+  if (splits > 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + c16 + 16 * j;
+      if (n < N) partial[((long long)sp * M + m) * N + n] = acc[j];
+    }
+    return;
+  }
   const long long orow = out_row(ep, m);
   if (orow < 0) return;
   float* __restrict__ out = gt.out[g];
@@ -217,7 +229,28 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
     attr = true;
   }
   dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), groups);
-  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, *ep);
+  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, *ep, 1, K, (float*)nullptr);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_gemm_f32_splitk(const float* a, const float* a2, int lda, const float* w, int M, int N, int K, int splits,
+                                    float* partial, egtr_stream_t s) {
+  EGTR_CHECK(a && w && partial && M > 0 && M <= 16 * 65535 && N > 0 && K > 0 && K % 4 == 0 && lda % 4 == 0 && lda >= K, EGTR_ERR_ARG,
+             "egtr_gemm_f32_splitk: bad shape (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
+  EGTR_CHECK(splits >= 2 && splits <= 64 && K % splits == 0 && (K / splits) % 4 == 0, EGTR_ERR_ARG,
+             "egtr_gemm_f32_splitk: splits=%d must divide K=%d into multiples of 4", splits, K);
+  SkinnyGroups gt = {};
+  gt.a[0] = a; gt.a2[0] = a2; gt.lda[0] = lda;
+  static bool attr = false;
+  if (!attr) {
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+    attr = true;
+  }
+  Epilogue ep = {};
+  dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), splits);
+  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, ep, splits, K / splits, partial);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -141,6 +141,49 @@ add_layernorm256_p32_kernel(const float* __restrict__ x, const uint8_t* __restri
   }
 }
 
+// LayerNorm(sum_s partial[s] + bias + res): consumes the raw split-K sums of egtr_gemm_f32_splitk; optional second (strided) copy
+__global__ void __launch_bounds__(256)
+sum_layernorm256_kernel(const float* __restrict__ partial, int splits, long long split_stride, const float* __restrict__ bias,
+                        const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta, int rows,
+                        float* __restrict__ out, float* __restrict__ out2, int rows_per_b2, long long bstride2) {
+  pdl_entry();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 a = ((const float4*)bias)[lane], b = ((const float4*)bias)[lane + 32];
+  for (int s = 0; s < splits; ++s) {
+    const float4* xp = (const float4*)(partial + s * split_stride + (long long)row * 256);
+    const float4 c = xp[lane], d = xp[lane + 32];
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+  if (res) {
+    const float4* rp = (const float4*)(res + (long long)row * 256);
+    const float4 c = rp[lane], d = rp[lane + 32];
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+  const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / 256.f);
+  a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+  b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+  const float var = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w) * (1.f / 256.f);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  const float4 g0 = ((const float4*)gamma)[lane], g1 = ((const float4*)gamma)[lane + 32];
+  const float4 b0 = ((const float4*)beta)[lane], b1 = ((const float4*)beta)[lane + 32];
+  float4 o0, o1;
+  o0.x = a.x * rstd * g0.x + b0.x; o0.y = a.y * rstd * g0.y + b0.y; o0.z = a.z * rstd * g0.z + b0.z; o0.w = a.w * rstd * g0.w + b0.w;
+  o1.x = b.x * rstd * g1.x + b1.x; o1.y = b.y * rstd * g1.y + b1.y; o1.z = b.z * rstd * g1.z + b1.z; o1.w = b.w * rstd * g1.w + b1.w;
+  float4* op = (float4*)(out + (long long)row * 256);
+  op[lane] = o0;
+  op[lane + 32] = o1;
+  if (out2) {
+    const int bb = row / rows_per_b2;
+    float4* op2 = (float4*)(out2 + bb * bstride2 + (long long)(row - bb * rows_per_b2) * 256);
+    op2[lane] = o0;
+    op2[lane + 32] = o1;
+  }
+}
+
 // ------------------------------------------------------------------ zero masked rows
 __global__ void mask_rows_kernel(float* __restrict__ x, int ld, int C4, const uint8_t* __restrict__ keep, long long rows) {
   pdl_entry();
@@ -364,15 +407,17 @@ pos_embed_kernel(const float* __restrict__ ycum, const float* __restrict__ xcum,
 __global__ void __launch_bounds__(256)
 mha_core_kernel(const float* __restrict__ qkv, int ld, int N, int C, float* __restrict__ out) {
   pdl_entry();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* ks = sm;                   // [N][33]
-  float* vs = sm + (size_t)N * 33;  // [N][32]
+  float* vs = sm + (((size_t)N * 33 + 3) & ~(size_t)3);  // [N][32], 16-byte aligned for the float4 staging stores
   const int hd = blockIdx.x, b = blockIdx.y;
   const float* base = qkv + (long long)b * N * ld + hd * 32;
-  for (int i = threadIdx.x; i < N * 32; i += blockDim.x) {
-    const int j = i >> 5, d = i & 31;
-    ks[j * 33 + d] = base[(long long)j * ld + C + d];
-    vs[j * 32 + d] = base[(long long)j * ld + 2 * C + d];
+  for (int i = threadIdx.x; i < N * 8; i += blockDim.x) {  // float4 loads, all independent: one round trip for the whole head
+    const int j = i >> 3, d = (i & 7) * 4;
+    const float4 kv = __ldg((const float4*)(base + (long long)j * ld + C + d));
+    const float4 vv = __ldg((const float4*)(base + (long long)j * ld + 2 * C + d));
+    ks[j * 33 + d] = kv.x; ks[j * 33 + d + 1] = kv.y; ks[j * 33 + d + 2] = kv.z; ks[j * 33 + d + 3] = kv.w;
+    *(float4*)(vs + j * 32 + d) = vv;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -466,6 +511,19 @@ extern "C" int egtr_add_layernorm_p32(const float* x, const void* res, int res_f
   EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_add_layernorm_p32: built for d_model 256 (got %d)", C);
   launch_pdl(add_layernorm256_p32_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, x, (const uint8_t*)res, res_fmt, gamma, beta, rows,
                                                                          (uint8_t*)out_p32, out_f32, addend, (uint8_t*)out_plus_p32);
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_sum_layernorm_f32(const float* partial, int splits, long long split_stride, const float* bias, const float* res,
+                                      const float* gamma, const float* beta, int rows, int C, float* out, float* out2, int rows_per_b2,
+                                      long long bstride2, egtr_stream_t s) {
+  EGTR_CHECK(partial && bias && gamma && beta && out && rows > 0 && splits >= 1, EGTR_ERR_ARG, "egtr_sum_layernorm_f32: bad arguments");
+  EGTR_CHECK(C == 256, EGTR_ERR_UNSUPPORTED, "egtr_sum_layernorm_f32: built for d_model 256 (got %d)", C);
+  EGTR_CHECK(!out2 || rows_per_b2 > 0, EGTR_ERR_ARG, "egtr_sum_layernorm_f32: out2 needs rows_per_b2");
+  launch_pdl(sum_layernorm256_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)0, (cudaStream_t)s, partial, splits, split_stride, bias, res,
+             gamma, beta, rows, out, out2, rows_per_b2 > 0 ? rows_per_b2 : rows, bstride2);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -573,10 +631,10 @@ extern "C" int egtr_levels_geometry_f32(const int64_t* pixel_mask, int B, int H,
 extern "C" int egtr_mha_core_f32(const float* qkv, int ld, int B, int N, int heads, int D, float* out, egtr_stream_t s) {
   EGTR_CHECK(qkv && out && B > 0 && N > 0, EGTR_ERR_ARG, "egtr_mha_core_f32: bad arguments");
   EGTR_CHECK(D == 32 && N <= 320 && ld >= 3 * heads * D, EGTR_ERR_UNSUPPORTED, "egtr_mha_core_f32: head_dim 32, N <= 320 (D=%d N=%d)", D, N);
-  const size_t smem = (size_t)N * (33 + 32) * sizeof(float);
+  const size_t smem = ((size_t)N * (33 + 32) + 4) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    EGTR_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 320 * 65 * 4));
+    EGTR_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (320 * 65 + 4) * 4));
     attr = true;
   }
   launch_pdl(mha_core_kernel, dim3(dim3(heads, B, cdiv(N, 8))), dim3(256), (size_t)(smem), (cudaStream_t)s, qkv, ld, N, heads * D, out);

@@ -344,6 +344,19 @@ class Engine:
     def layernorm(self, x, res, ln, rows, out):
         call("egtr_add_layernorm_f32", _ptr(x), _ptr(res), _ptr(ln[0]), _ptr(ln[1]), rows, 256, _ptr(out), _stream())
 
+    def _dec_self_attn(self, lay, ws, Md, B, N, h, qkv, t1, offaw):
+        """Self-attention half of a decoder layer (deformable_detr.py:1404-1417) + the cross-attention's offsets/weights
+        projection: h -> qkv (captured), t1 = LN1(h + out_proj(attn)), offaw = Linear(t1 + query_pos)."""
+        st = _stream()
+        qpos = ws["qpos"]
+        self.gemm_grouped(lay["qkv"], Md, a=[h, h, h], a2=[qpos, qpos, None], lda=[256, 256, 256],
+                          out=[(qkv, 0), (qkv, 256), (qkv, 512)], ldo=768)
+        call("egtr_mha_core_f32", _ptr(qkv), 768, B, N, 8, 32, _ptr(ws["dattn"]), st)
+        call("egtr_gemm_f32_splitk", _ptr(ws["dattn"]), None, 256, _ptr(lay["o"].w), Md, 256, 256, 2, _ptr(ws["dpart"]), st)
+        call("egtr_sum_layernorm_f32", _ptr(ws["dpart"]), 2, Md * 256, _ptr(lay["o"].b), _ptr(h), _ptr(lay["ln1"][0]), _ptr(lay["ln1"][1]),
+             Md, 256, _ptr(t1), None, 0, 0, st)
+        self.gemm(lay["offaw"], Md, offaw, a=t1, a2=qpos, lda=256)
+
     # ------------------------------------------------------------------ workspace
     def _workspace(self, B: int, H: int, W: int) -> dict:
         key = (B, H, W)
@@ -385,6 +398,7 @@ class Engine:
         ws["dattn"] = torch.empty(B * N, 256, **f32)
         ws["doffaw"] = torch.empty(B * N, 384, **f32)
         ws["dffn"] = torch.empty(B * N, 1024, **f32)
+        ws["dpart"] = torch.empty(8, B * N, 256, **f32)  # split-K partial sums of the decoder's out_proj / fc2
         ws["box_h"] = [torch.empty(B * N, 256, **f32) for _ in range(2)]
         Lr = cfg.decoder_layers + 1
         ws["U"] = torch.empty(B * N * Lr, 516, **f32)
@@ -551,35 +565,47 @@ class Engine:
             self.gemm(self.dec_value, M, dv, a=enc_p32, lda=256, a_fmt=1, row_keep=ws["mask_flat"])
         else:
             self.gemm(self.dec_value, M, dv, a=enc, lda=256, row_keep=ws["mask_flat"])
-        call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
-             None, 0, 0, _ptr(ws["ref"]), 2, st)
         Md = B * N
         qpos = ws["qpos"]
         hbuf = ws["dh"]
+        dpart = ws["dpart"]
+        if "dec0" not in ws:
+            # Input-independent prefix (weights only): the reference points and the whole self-attention half of decoder
+            # layer 0 — q|k|v of the learned queries, attention, out_proj + LayerNorm, and the sampling_offsets /
+            # attention_weights projection of its cross-attention — are computed once per workspace, not per image.
+            call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
+                 None, 0, 0, _ptr(ws["ref"]), 2, st)
+            lay = self.dec[0]
+            qkv0 = torch.empty(Md, 768, **f32)
+            t1_0 = torch.empty(Md, 256, **f32)
+            offaw0 = torch.empty(Md, 384, **f32)
+            self._dec_self_attn(lay, ws, Md, B, N, ws["tgt"], qkv0, t1_0, offaw0)
+            ws["dec0"] = (qkv0, t1_0, offaw0)
         hcur = ws["tgt"]
         qkvs = []
         inter = torch.empty(B, nl, N, 256, **f32)
         for i, lay in enumerate(self.dec):
-            qkv = torch.empty(Md, 768, **f32)  # captured per layer: q (scaled) | k | v
+            t1, t2, t3 = [b for b in hbuf if b is not hcur][:3]
+            if i == 0:
+                qkv, t1, offaw_i = ws["dec0"]
+            else:
+                qkv = torch.empty(Md, 768, **f32)  # captured per layer: q (scaled) | k | v
+                offaw_i = ws["doffaw"]
+                self._dec_self_attn(lay, ws, Md, B, N, hcur, qkv, t1, offaw_i)
             qkvs.append(qkv)
-            t0, t1, t2 = [b for b in hbuf if b is not hcur][:3]
-            self.gemm_grouped(lay["qkv"], Md, a=[hcur, hcur, hcur], a2=[qpos, qpos, None], lda=[256, 256, 256],
-                              out=[(qkv, 0), (qkv, 256), (qkv, 512)], ldo=768)
-            call("egtr_mha_core_f32", _ptr(qkv), 768, B, N, 8, 32, _ptr(ws["dattn"]), st)
-            self.gemm(lay["o"], Md, t0, a=ws["dattn"], lda=256, res=hcur, ldr=256)
-            self.layernorm(t0, None, lay["ln1"], Md, t1)
-            self.gemm(lay["offaw"], Md, ws["doffaw"], a=t1, a2=qpos, lda=256)
             with self.span("msda_dec"):
-                call("egtr_msda_fused_fwd_f32", _ptr(dv, i * 256), 256 * nl, ws["shapes_c"], _ptr(ws["doffaw"]), 384,
+                call("egtr_msda_fused_fwd_f32", _ptr(dv, i * 256), 256 * nl, ws["shapes_c"], _ptr(offaw_i), 384,
                      _ptr(ws["ref"]), _ptr(vr), 0, B, S, 8, 32, Lv, N, 4, _ptr(ws["dattn"]), st)
-            self.gemm(lay["out"], Md, t0, a=ws["dattn"], lda=256, res=t1, ldr=256)
-            self.layernorm(t0, None, lay["ln2"], Md, t2)
+            # output_proj / fc2 as split-K sums; bias + residual + LayerNorm consume them (deformable_detr.py:1441-1477)
+            call("egtr_gemm_f32_splitk", _ptr(ws["dattn"]), None, 256, _ptr(lay["out"].w), Md, 256, 256, 2, _ptr(dpart), st)
+            call("egtr_sum_layernorm_f32", _ptr(dpart), 2, Md * 256, _ptr(lay["out"].b), _ptr(t1), _ptr(lay["ln2"][0]), _ptr(lay["ln2"][1]),
+                 Md, 256, _ptr(t2), None, 0, 0, st)
             self.gemm(lay["fc1"], Md, ws["dffn"], a=t2, lda=256, relu=True)
-            self.gemm(lay["fc2"], Md, t0, a=ws["dffn"], lda=1024, res=t2, ldr=256)
-            out_h = inter[:, i]  # strided view [B,N,256] of the stacked intermediates: write through a contiguous temp
-            self.layernorm(t0, None, lay["ln3"], Md, t1)
-            out_h.copy_(t1.view(B, N, 256))
-            hcur = t1
+            call("egtr_gemm_f32_splitk", _ptr(ws["dffn"]), None, 1024, _ptr(lay["fc2"].w), Md, 256, 1024, 8, _ptr(dpart), st)
+            # the layer output also lands in its slot of the stacked intermediate states [B, layers, N, 256]
+            call("egtr_sum_layernorm_f32", _ptr(dpart), 8, Md * 256, _ptr(lay["fc2"].b), _ptr(t2), _ptr(lay["ln3"][0]), _ptr(lay["ln3"][1]),
+                 Md, 256, _ptr(t3), _ptr(inter, i * N * 256), N, nl * N * 256, st)
+            hcur = t3
         h_last = hcur
 
         # ---- detection heads (egtr.py:283-314; only the last level is returned at inference)

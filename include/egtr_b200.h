@@ -131,6 +131,11 @@ int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* const* a2_ptr
                           const int* n_base, int groups, const int* lda, const float* w, int M, int N, int K,
                           const egtr_epilogue_t* ep, egtr_stream_t s);
 
+/* Split-K form for long-K few-row products (decoder out_proj / fc2): raw partial sums partial[s][M][N] over K slices
+ * s = 0..splits-1 of (a + a2) * w^T; the consumer (egtr_sum_layernorm_f32) adds bias / residual.  K %% splits == 0. */
+int egtr_gemm_f32_splitk(const float* a, const float* a2, int lda, const float* w, int M, int N, int K, int splits,
+                         float* partial, egtr_stream_t s);
+
 /* x (+ addend) [rows, C] fp32 (row stride ldx floats) -> P32 rows [rows, C] (pitch 4*C bytes).  C % 32 == 0. */
 int egtr_rows_to_p32(const float* x, const float* addend, int rows, int C, int ldx, void* out, egtr_stream_t s);
 /* P32 rows -> fp32 (debug / tests / handing a P32 tensor back to the caller). */
@@ -169,6 +174,12 @@ int egtr_add_layernorm_f32(const float* x, const float* res, const float* gamma,
  * layer's sampling_offsets / attention_weights projections, deformable_detr.py:1040). */
 int egtr_add_layernorm_p32(const float* x, const void* res, int res_fmt, const float* gamma, const float* beta, int rows,
                            int C, void* out_p32, float* out_f32, const float* addend, void* out_plus_p32, egtr_stream_t s);
+/* out = LayerNorm(sum_s partial[s*split_stride + row*C ..] + bias + res), C == 256: the Linear + residual + LayerNorm tail
+ * of a decoder sub-layer (deformable_detr.py:1414-1417, 1441-1443, 1474-1477) on split-K sums.  out2 (optional) receives
+ * a second copy at out2[(row / rows_per_b2) * bstride2 + (row % rows_per_b2) * C] (the stacked intermediate states). */
+int egtr_sum_layernorm_f32(const float* partial, int splits, long long split_stride, const float* bias, const float* res,
+                           const float* gamma, const float* beta, int rows, int C, float* out, float* out2, int rows_per_b2,
+                           long long bstride2, egtr_stream_t s);
 /* zero rows of x[rows, C] where keep[row] == 0 (value.masked_fill, deformable_detr.py:1050-1052). */
 int egtr_mask_rows_f32(float* x, int ld, int C, const uint8_t* keep, int rows, egtr_stream_t s);
 /* pixel_values [B,3,H,W] -> zero-bordered NHWC4 [B,H+2*pad,W+2*pad,4] (4th channel zero). */

@@ -338,3 +338,31 @@ def test_mha_core_and_small_linear(cuda):
     o = torch.empty(B * N, 4, device=cuda)
     _lib.call("egtr_small_linear_f32", xd.data_ptr(), 256, wd.data_ptr(), bd.data_ptr(), B * N, 256, 4, 2, rd.data_ptr(), 2, N, o.data_ptr(), 4, st)
     assert relerr(o, y.sigmoid()) < 1e-5
+
+
+@pytest.mark.parametrize("M,K,splits", [(200, 256, 2), (200, 1024, 8), (300, 1024, 4), (7, 256, 2), (800, 1024, 8)])
+def test_gemm_splitk_sum_layernorm(cuda, M, K, splits):
+    """Decoder sub-layer tail: split-K partial sums of a Linear, then bias + residual + LayerNorm (+ strided second copy)."""
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(M + K + splits)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(256, K, generator=g) / K ** 0.5).to(cuda)
+    b, res = torch.randn(256, generator=g).to(cuda), torch.randn(M, 256, generator=g).to(cuda)
+    gamma, beta = torch.randn(256, generator=g).to(cuda), torch.randn(256, generator=g).to(cuda)
+    part = torch.full((splits, M, 256), float("nan"), device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("egtr_gemm_f32_splitk", a.data_ptr(), None, K, w.data_ptr(), M, 256, K, splits, part.data_ptr(), st)
+    torch.cuda.synchronize()
+    lin = a.double() @ w.double().t()
+    assert relerr(part.double().sum(0), lin) < 2e-6 * max(1.0, (K / 256) ** 0.5)
+    out = torch.empty(M, 256, device=cuda)
+    nb = 1 if M % 100 else M // 100  # second copy: [nb, 3, rows_per_b, 256] slot 1
+    rpb = M // nb
+    out2 = torch.full((nb, 3, rpb, 256), 7.0, device=cuda)
+    _lib.call("egtr_sum_layernorm_f32", part.data_ptr(), splits, M * 256, b.data_ptr(), res.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+              M, 256, out.data_ptr(), out2.data_ptr() + rpb * 256 * 4, rpb, 3 * rpb * 256, st)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.layer_norm(lin + b.double() + res.double(), (256,), gamma.double(), beta.double(), 1e-5)
+    assert relerr(out, want) < 5e-6
+    assert torch.equal(out2[:, 1].reshape(M, 256), out)
+    assert (out2[:, 0] == 7.0).all() and (out2[:, 2] == 7.0).all()
