@@ -171,30 +171,55 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------ leg 1: device-resident inputs, CUDA-graph replay
-    px_d, mask_d = px.to(dev), mask.to(dev)
-    runner = eng.graph_runner(Bl, H, W)
+    # Throughput mode: `conc` forwards in flight, each a captured CUDA graph with its own workspace on its own stream
+    # (at batch 1 the decoder and the deep backbone layers are latency-bound chains of small kernels; a second/third image
+    # fills the SMs they leave idle).  Inputs rotate over NIMG distinct resident images (> L2 in total), so no step finds
+    # its input in L2; one forward also streams > 2 GB of activations and weights through the 126 MB L2.
+    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", "3"))  # forwards in flight on separate compute streams
+    depth = int(os.environ.get("EGTR_PIPE_DEPTH", str(2 * conc)))
+    NIMG = 8
+    px_d = [torch.roll(px, shifts=17 * i, dims=3).to(dev) for i in range(NIMG)]
+    mask_d = mask.to(dev)
+    in_bytes = NIMG * (px_d[0].numel() * 4 + mask_d.numel() * 8)
+    runners = [eng.graph_runner(Bl, H, W, slot=i) for i in range(conc)]
+    streams = [torch.cuda.Stream() for _ in range(conc)]
+    main = torch.cuda.current_stream()
 
-    def step_resident():
-        out = runner(px_d, mask_d)
-        if world > 1:
-            return all_gather_records(pack_records(out, layout), Bl)
-        return out
+    def run_resident(n):
+        for st_ in streams:
+            st_.wait_stream(main)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % conc]):
+                out = runners[i % conc](px_d[i % NIMG], mask_d)
+                if world > 1:
+                    all_gather_records(pack_records(out, layout), Bl)
+        for st_ in streams:
+            main.wait_stream(st_)
 
-    for _ in range(args.warmup):
-        step_resident()
+    run_resident(max(args.warmup, conc))
+    barrier()
+    # single-forward latency (one image at a time, L2 flushed before it) for reference
+    lat = []
+    for i in range(5):
+        flush.fill_(1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        runners[0](px_d[i % NIMG], mask_d)
+        s1.record()
+        torch.cuda.synchronize()
+        lat.append(s0.elapsed_time(s1))
+    latency_ms = sorted(lat)[len(lat) // 2]
     barrier()
     _lib.call("egtr_launch_count_reset")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s, e in ev:
-        flush.fill_(1)
-        s.record()
-        step_resident()
-        e.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_resident(args.steps)
+    e1.record()
     barrier()
-    t_res = sum(s.elapsed_time(e) for s, e in ev) / 1000.0
+    t_res = e0.elapsed_time(e1) / 1000.0
     # launches inside one replayed graph == launches of one eager forward; count them on an eager pass below
 
     # ------------------------------------------------------------ leg 2: end to end, host buffers in -> host results out
@@ -208,16 +233,18 @@ def main():
         flat = all_gather_records(pack_records(res, layout), Bl)
         return {"records": flat[rank * Bl:(rank + 1) * Bl]}
 
-    pipe = PipelinedRunner(model, Bl, H, W, depth=2, post=post if world > 1 else None)
+    pipe = PipelinedRunner(model, Bl, H, W, depth=depth, post=post if world > 1 else None, concurrency=conc)
 
     def run_e2e(n):
-        prev = None
+        pending = []
         for _ in range(n):
-            t = pipe.submit(px_h, mask_h)
-            if prev is not None:
-                pipe.collect(prev)
-            prev = t
-        return pipe.collect(prev)
+            pending.append(pipe.submit(px_h, mask_h))
+            if len(pending) >= depth:
+                pipe.collect(pending.pop(0))
+        last = None
+        while pending:
+            last = pipe.collect(pending.pop(0))
+        return last
 
     run_e2e(args.warmup)
     barrier()
@@ -296,9 +323,12 @@ def main():
             "dtype": "bf16x3 split products with fp32 accumulate on tcgen05 (fp32-equivalent); fp32 elsewhere", "data": "synthetic",
             "config": {"workload": f"{WORKLOAD}: VG config, {Bl}x3x{H}x{W} per GPU, N_q={N}, K={K}, P={P}, S={S}",
                        "parallelism": f"image-parallel x{world}, one all-gather of per-image records" if world > 1 else "single GPU",
-                       "global_batch": world * Bl, "timing": "CUDA events per step, 256 MiB L2 flush before each step, max over ranks",
-                       "value_leg": "CUDA-graph replay, inputs resident in HBM",
-                       "e2e_leg": "egtr_b200.serving.PipelinedRunner: pinned host tensors in, host results out; per-step H2D/D2H overlapped with the graph replay of neighbouring steps (depth 2)"},
+                       "global_batch": world * Bl,
+                       "timing": f"CUDA events around the {args.steps} timed steps, max over ranks; {conc} forwards in flight per GPU",
+                       "l2": f"inputs rotate over {NIMG} distinct resident images ({in_bytes >> 20} MiB > 126 MB L2); a forward streams > 2 GB through L2",
+                       "value_leg": f"CUDA-graph replays, {conc} graphs with private workspaces on {conc} streams, inputs resident in HBM",
+                       "e2e_leg": f"egtr_b200.serving.PipelinedRunner: pinned host tensors in, host results out; per-step H2D/D2H on copy streams, {conc} compute streams, {depth} slots",
+                       "single_forward_latency_ms": latency_ms},
             "clocks": clocks,
             "e2e": {"value": img_s_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * t_e2e / args.steps, "wall_ms_per_step": 1000 * t_e2e_wall / args.steps},

@@ -33,6 +33,7 @@
 namespace egtr {
 
 void count_launch();
+int scratch_slot();
 
 namespace {
 
@@ -571,17 +572,18 @@ int* device_error_flag_p32() {
   return flag;
 }
 
-float* partial_buffer_p32(size_t floats) {  // grow-only; older buffers stay alive for captured graphs
-  static float* buf = nullptr;
-  static size_t cap = 0;
-  if (floats > cap) {
+float* partial_buffer_p32(size_t floats) {  // grow-only per scratch slot; older buffers stay alive for captured graphs
+  static float* buf[8] = {};
+  static size_t cap[8] = {};
+  const int slot = scratch_slot();
+  if (floats > cap[slot]) {
     float* nb = nullptr;
     const size_t want = floats + floats / 2;
     if (cudaMalloc(&nb, want * sizeof(float)) != cudaSuccess) return nullptr;
-    buf = nb;
-    cap = want;
+    buf[slot] = nb;
+    cap[slot] = want;
   }
-  return buf;
+  return buf[slot];
 }
 
 // Output pixel tile of a convolution: BW x BH = 128 with BW a power of two in [8, 128]; fewest tiles wins, wider wins ties.

@@ -93,9 +93,10 @@ struct SkinnyGroups {
   int lda[16];
 };
 
-constexpr int SK_TM = 16, SK_TN = 64, SK_KC = 128, SK_LD = SK_KC + 4;  // +4 floats: conflict-free float4 rows
+constexpr int SK_TM = 16, SK_TN = 64, SK_KC = 256, SK_LD = SK_KC + 4;  // +4 floats: conflict-free float4 rows
 constexpr int SK_STAGE_FLOATS = (2 * SK_TM + SK_TN) * SK_LD;              // A, A2 and W tiles of one K chunk
-constexpr int SK_SMEM_BYTES = 2 * SK_STAGE_FLOATS * 4;
+constexpr int SK_STAGE_BYTES = SK_STAGE_FLOATS * 4;                       // 99.8 KB: K <= 256 needs one stage -> two CTAs per SM
+constexpr int SK_SMEM_BYTES = 2 * SK_STAGE_BYTES;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -104,9 +105,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One CTA (256 threads) = 16 x 64 outputs, 4 per thread.  A whole 128-wide K chunk of both operands is fetched with
-// cp.async in one burst and the next chunk is already in flight while the current one is multiplied; 100 KB of smem
-// per CTA keeps two CTAs resident per SM.
+// One CTA (256 threads) = 16 x 64 outputs, 4 per thread.  A whole 256-wide K chunk of both operands is fetched with
+// cp.async in ONE burst (a single memory round trip for every K <= 256 shape of the decoder); longer K double-buffers
+// chunks.  The launch asks for one stage of smem when one chunk suffices, so two CTAs stay resident per SM.
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, int N, int K, const Epilogue ep, int splits, int k_per,
                    float* __restrict__ partial) {
@@ -162,8 +163,9 @@ gemm_skinny_kernel(const SkinnyGroups gt, const float* __restrict__ w, int M, in
     const float* As = sk_smem + (c & 1) * SK_STAGE_FLOATS + r * SK_LD;
     const float* A2s = As + SK_TM * SK_LD;
     const float* Ws = sk_smem + (c & 1) * SK_STAGE_FLOATS + 2 * SK_TM * SK_LD + c16 * SK_LD;
+    const int klen = min(SK_KC, k_hi - (k_lo + c * SK_KC));
 #pragma unroll 4
-    for (int k = 0; k < SK_KC; k += 4) {
+    for (int k = 0; k < klen; k += 4) {
       float4 a = *(const float4*)(As + k);
       if (A2) { const float4 p = *(const float4*)(A2s + k); a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w; }
 #pragma unroll
@@ -229,7 +231,8 @@ extern "C" int egtr_gemm_f32_grouped(const float* const* a_ptrs, const float* co
     attr = true;
   }
   dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), groups);
-  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, *ep, 1, K, (float*)nullptr);
+  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(K > SK_KC ? SK_SMEM_BYTES : SK_STAGE_BYTES), (cudaStream_t)s, gt, w, M, N, K,
+             *ep, 1, K, (float*)nullptr);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -250,7 +253,8 @@ extern "C" int egtr_gemm_f32_splitk(const float* a, const float* a2, int lda, co
   }
   Epilogue ep = {};
   dim3 grid(cdiv(N, SK_TN), cdiv(M, SK_TM), splits);
-  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(SK_SMEM_BYTES), (cudaStream_t)s, gt, w, M, N, K, ep, splits, K / splits, partial);
+  launch_pdl(gemm_skinny_kernel, dim3(grid), dim3(256), (size_t)(K / splits > SK_KC ? SK_SMEM_BYTES : SK_STAGE_BYTES), (cudaStream_t)s, gt, w,
+             M, N, K, ep, splits, K / splits, partial);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -31,6 +31,7 @@
 namespace egtr {
 
 void count_launch();
+int scratch_slot();
 int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                       cudaStream_t st);  // gemm_p32.cu: TMA-fed operand rows
 
@@ -691,18 +692,18 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
 }
 
 // grow-only scratch for split-K partial sums (allocated outside graph capture, during warm-up)
-float* partial_buffer(size_t floats) {
-  static float* buf = nullptr;
-  static size_t cap = 0;
-  if (floats > cap) {
-    // the previous (smaller) buffer is deliberately kept alive: captured CUDA graphs may still point at it
+float* partial_buffer(size_t floats) {  // grow-only per scratch slot; older buffers stay alive for captured graphs
+  static float* buf[8] = {};
+  static size_t cap[8] = {};
+  const int slot = scratch_slot();
+  if (floats > cap[slot]) {
     float* nb = nullptr;
-    size_t want = floats + floats / 2;
+    const size_t want = floats + floats / 2;
     if (cudaMalloc(&nb, want * sizeof(float)) != cudaSuccess) return nullptr;
-    buf = nb;
-    cap = want;
+    buf[slot] = nb;
+    cap[slot] = want;
   }
-  return buf;
+  return buf[slot];
 }
 
 template <int BLOCK_N, int MODE, bool REL>

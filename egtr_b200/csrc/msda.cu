@@ -20,7 +20,6 @@ namespace egtr {
 void count_launch();
 namespace {
 
-constexpr int QPB = 32;      // queries per CTA
 constexpr int MAX_L = 8;
 constexpr int SLOT_WORDS = 8;                      // 4 token indices + 4 weights
 constexpr int Q_STRIDE = 16 * SLOT_WORDS + 8;      // words per query, padded against bank conflicts
@@ -47,8 +46,10 @@ struct MsdaArgs {
   int enc_patches;                        // 1: queries are the S tokens, enumerated in 8x4 patches
 };
 
-template <bool FUSED>
-__global__ void __launch_bounds__(256, 6)
+// QPB queries per CTA, 8 threads each: 32 for the encoder's 8x4 pixel patches, 8 for the decoder's few hundred queries
+// (25 x 8 CTAs instead of 7 x 8, and half as many dependent gather batches per thread).
+template <bool FUSED, int QPB>
+__global__ void __launch_bounds__(QPB * 8, QPB == 32 ? 6 : 8)
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   pdl_entry();
   __shared__ float slots[QPB * Q_STRIDE];
@@ -97,7 +98,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   const int s = tid & 15;          // sample index = l*P + p   (L*P == 16)
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
-    const int qi = (tid >> 4) + pass * 16;
+    const int qi = (tid >> 4) + pass * (QPB / 2);
     const int q = q_of[qi];
     float* slot = &slots[qi * Q_STRIDE + s * SLOT_WORDS];
     int idx[4] = {-1, -1, -1, -1};
@@ -177,7 +178,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   const float* vbase = a.value + (long long)b * a.S * a.ld_value + m * 32 + c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* myslots = &slots[g * Q_STRIDE];
-#pragma unroll 4
+#pragma unroll (QPB == 32 ? 4 : 8)
   for (int ss = 0; ss < 16; ++ss) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
@@ -247,8 +248,8 @@ extern "C" int egtr_msda_fwd_f32(const float* value, const int64_t* spatial_shap
   a.out = out; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = 0;
   Levels lv = {};
   lv.L = L;
-  dim3 grid(cdiv(Lq, QPB), M, B);
-  launch_pdl(msda_kernel<false>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
+  dim3 grid(cdiv(Lq, 32), M, B);
+  launch_pdl(msda_kernel<false, 32>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;
@@ -283,8 +284,13 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   a.offaw = offaw; a.ld_offaw = ld_offaw;
   a.ref_points = ref_points; a.valid_ratios = valid_ratios;
   a.out = out; a.out_fmt = out_fmt; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
-  dim3 grid(enc_ref ? patches : cdiv(Lq, QPB), M, B);
-  launch_pdl(msda_kernel<true>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
+  if (!enc_ref && (long long)Lq * B <= 4096) {  // decoder-sized query sets: small CTAs for parallelism and latency
+    dim3 grid(cdiv(Lq, 8), M, B);
+    launch_pdl(msda_kernel<true, 8>, dim3(grid), dim3(64), (size_t)(0), (cudaStream_t)s, a, lv);
+  } else {
+    dim3 grid(enc_ref ? patches : cdiv(Lq, 32), M, B);
+    launch_pdl(msda_kernel<true, 32>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
+  }
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

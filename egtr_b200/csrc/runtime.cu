@@ -31,6 +31,10 @@ int num_sms() {
 }
 
 // EGTR_B200_PDL: 0 = programmatic dependent launch off, 1 = every launch, 2 = launches of at least one CTA per SM
+// Split-K scratch is per "slot": forwards that may run concurrently (two CUDA graphs on two streams) use different slots.
+static thread_local int g_scratch_slot = 0;
+int scratch_slot() { return g_scratch_slot; }
+
 int pdl_mode() {
   static const int mode = [] { const char* e = getenv("EGTR_B200_PDL"); return e ? atoi(e) : 2; }();
   return mode;
@@ -38,6 +42,11 @@ int pdl_mode() {
 
 }  // namespace egtr
 
+extern "C" int egtr_set_scratch_slot(int slot) {
+  EGTR_CHECK(slot >= 0 && slot < 8, EGTR_ERR_ARG, "egtr_set_scratch_slot: slot %d outside 0..7", slot);
+  egtr::g_scratch_slot = slot;
+  return EGTR_OK;
+}
 extern "C" const char* egtr_last_error(void) { return egtr::g_err; }
 extern "C" int egtr_abi_version(void) { return 1; }
 extern "C" long long egtr_launch_count(void) { return egtr::g_launches.load(); }

@@ -272,12 +272,12 @@ class Engine:
         torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------ CUDA-graph replay
-    def graph_runner(self, B: int, H: int, W: int) -> "GraphRunner":
+    def graph_runner(self, B: int, H: int, W: int, slot: int = 0) -> "GraphRunner":
         """The ~330 launches of one forward captured once per input shape and replayed as one graph:
         the host-side launch sequence disappears from the step time (batch 1 is launch-bound otherwise)."""
-        key = ("graph", B, H, W)
+        key = ("graph", B, H, W, slot)
         if key not in self._ws:
-            self._ws[key] = GraphRunner(self, B, H, W)
+            self._ws[key] = GraphRunner(self, B, H, W, slot)
         return self._ws[key]
 
     # ------------------------------------------------------------------ launch helpers
@@ -358,8 +358,10 @@ class Engine:
         self.gemm(lay["offaw"], Md, offaw, a=t1, a2=qpos, lda=256)
 
     # ------------------------------------------------------------------ workspace
-    def _workspace(self, B: int, H: int, W: int) -> dict:
-        key = (B, H, W)
+    def _workspace(self, B: int, H: int, W: int, slot: int = 0) -> dict:
+        """Activation buffers of one forward; `slot` > 0 gives an independent set for a forward that may run concurrently
+        with slot 0's (a second CUDA graph on another stream)."""
+        key = (B, H, W, slot)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -414,15 +416,17 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    def forward(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None,
+                slot: int = 0) -> Dict[str, torch.Tensor]:
         cfg, dev = self.cfg, self.device
         if pixel_values.device != dev:
             raise _lib.EgtrError(f"pixel_values on {pixel_values.device}, model on {dev}")
         with torch.cuda.device(dev):
-            return self._forward(pixel_values, pixel_mask, taps)
+            return self._forward(pixel_values, pixel_mask, taps, slot)
 
-    def _forward(self, pixel_values, pixel_mask, taps):
+    def _forward(self, pixel_values, pixel_mask, taps, slot: int = 0):
         cfg, dev = self.cfg, self.device
+        call("egtr_set_scratch_slot", slot)
         st = _stream()
         px = pixel_values.to(torch.float32).contiguous()
         B, Cin, H, W = px.shape
@@ -431,7 +435,7 @@ class Engine:
         if pixel_mask is None:
             pixel_mask = torch.ones(B, H, W, dtype=torch.long, device=dev)
         pm = pixel_mask.to(torch.long).contiguous()
-        ws = self._workspace(B, H, W)
+        ws = self._workspace(B, H, W, slot)
         shapes, S, starts = ws["shapes"], ws["S"], ws["starts"]
         N, d, Lv = cfg.num_queries, cfg.d_model, len(shapes)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -601,9 +605,9 @@ class Engine:
             call("egtr_sum_layernorm_f32", _ptr(dpart), 2, Md * 256, _ptr(lay["out"].b), _ptr(t1), _ptr(lay["ln2"][0]), _ptr(lay["ln2"][1]),
                  Md, 256, _ptr(t2), None, 0, 0, st)
             self.gemm(lay["fc1"], Md, ws["dffn"], a=t2, lda=256, relu=True)
-            call("egtr_gemm_f32_splitk", _ptr(ws["dffn"]), None, 1024, _ptr(lay["fc2"].w), Md, 256, 1024, 8, _ptr(dpart), st)
+            call("egtr_gemm_f32_splitk", _ptr(ws["dffn"]), None, 1024, _ptr(lay["fc2"].w), Md, 256, 1024, 4, _ptr(dpart), st)
             # the layer output also lands in its slot of the stacked intermediate states [B, layers, N, 256]
-            call("egtr_sum_layernorm_f32", _ptr(dpart), 8, Md * 256, _ptr(lay["fc2"].b), _ptr(t2), _ptr(lay["ln3"][0]), _ptr(lay["ln3"][1]),
+            call("egtr_sum_layernorm_f32", _ptr(dpart), 4, Md * 256, _ptr(lay["fc2"].b), _ptr(t2), _ptr(lay["ln3"][0]), _ptr(lay["ln3"][1]),
                  Md, 256, _ptr(t3), _ptr(inter, i * N * 256), N, nl * N * 256, st)
             hcur = t3
         h_last = hcur
@@ -681,8 +685,9 @@ class GraphRunner:
     """Static-buffer CUDA graph of `Engine._forward` for one (B, H, W).  Outputs are the graph's own
     buffers and are overwritten by the next replay (callers that keep results must clone them)."""
 
-    def __init__(self, eng: Engine, B: int, H: int, W: int):
+    def __init__(self, eng: Engine, B: int, H: int, W: int, slot: int = 0):
         self.eng = eng
+        self.slot = slot
         dev = eng.device
         with torch.cuda.device(dev):
             self.px = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
@@ -691,13 +696,13 @@ class GraphRunner:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: one-time attribute calls, tensor-map cache, workspace allocation
-                    eng._forward(self.px, self.pm, None)
+                    eng._forward(self.px, self.pm, None, slot)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             probe, eng.probe = eng.probe, None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = eng._forward(self.px, self.pm, None)
+                self.out = eng._forward(self.px, self.pm, None, slot)
             eng.probe = probe
 
     def __call__(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None):

@@ -6,9 +6,11 @@ the GPU, run the model, read results back — on a B200 the two PCIe copies (21 
 call shape (pinned host tensors in, host tensors out) but overlaps the three phases of consecutive
 batches on three CUDA streams with double-buffered device inputs/outputs:
 
-    copy-in  stream : H2D of batch i+1
-    compute  stream : CUDA-graph replay of the forward for batch i
-    copy-out stream : D2H of batch i-1's logits / boxes / pred_rel / pred_connectivity
+    copy-in  stream  : H2D of batch i+1
+    compute  streams : CUDA-graph replay of the forward for batch i (and, with `concurrency` 2, batch i+1 on a second
+                       stream with its own workspace: at batch 1 the decoder and the deep backbone layers are latency-bound
+                       chains of small kernels that leave most SMs idle — a second image in flight fills them)
+    copy-out stream  : D2H of batch i-1's logits / boxes / pred_rel / pred_connectivity
 
 Every batch still pays its own H2D and D2H; they just no longer serialise with the kernels.
 """
@@ -24,7 +26,7 @@ RESULT_FIELDS = ("logits", "pred_boxes", "pred_rel", "pred_connectivity")
 
 
 class PipelinedRunner:
-    def __init__(self, model, batch: int, height: int, width: int, depth: int = 2, post=None):
+    def __init__(self, model, batch: int, height: int, width: int, depth: int = 2, post=None, concurrency: int = 1):
         """`post(outputs) -> dict of device tensors` (optional) runs on the compute stream after each replay — e.g.
         the image-parallel all-gather of per-image records — and its result is what gets copied to the host."""
         self.model = model
@@ -33,10 +35,12 @@ class PipelinedRunner:
         self.dev = eng.device
         self.depth = depth
         with torch.cuda.device(self.dev):
-            # one captured graph per slot: private static inputs and outputs, shared workspace (replays are
-            # serial on the compute stream, so intermediates may alias)
-            self.slots: List[GraphRunner] = [GraphRunner(eng, batch, height, width) for _ in range(depth)]
-            self.s_in, self.s_run, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+            # one captured graph per slot: private static inputs and outputs; slots that share a compute stream replay
+            # serially and share a workspace, slots on different compute streams get their own (they overlap in time)
+            self.concurrency = max(1, min(concurrency, depth))
+            self.slots: List[GraphRunner] = [GraphRunner(eng, batch, height, width, slot=i % self.concurrency) for i in range(depth)]
+            self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self.s_runs = [torch.cuda.Stream() for _ in range(self.concurrency)]
             self.ev_in = [torch.cuda.Event() for _ in range(depth)]
             self.ev_run = [torch.cuda.Event() for _ in range(depth)]
             self.ev_out = [torch.cuda.Event() for _ in range(depth)]
@@ -68,15 +72,16 @@ class PipelinedRunner:
                 else:
                     slot.pm.fill_(1)
                 self.ev_in[s].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[s])
-                self.s_run.wait_event(self.ev_out[s])  # outputs of this slot have been read back
+            s_run = self.s_runs[s % self.concurrency]
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(self.ev_in[s])
+                s_run.wait_event(self.ev_out[s])  # outputs of this slot have been read back
                 slot.graph.replay()
                 if self.post is not None:
                     self.res[s] = self.post({k: slot.out[k] for k in RESULT_FIELDS})
                     for v in self.res[s].values():
                         v.record_stream(self.s_out)
-                self.ev_run[s].record(self.s_run)
+                self.ev_run[s].record(s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[s])
                 for k, v in self.res[s].items():

@@ -43,6 +43,10 @@ int egtr_abi_version(void);
 long long egtr_launch_count(void);
 void egtr_launch_count_reset(void);
 
+/* Internal split-K scratch is kept per slot (0..7, thread-local selection, default 0): forwards that may execute
+ * concurrently on different streams (e.g. two captured CUDA graphs) must be enqueued under different slots. */
+int egtr_set_scratch_slot(int slot);
+
 /* ---------------------------------------------------------------- GEMM-class operators ---- */
 /* Left-operand source: rows of 64-float runs.  mode 0: row m = a + m*lda (+ a2 + m*lda when a2
  * is non-null, the "x + pos" of deformable_detr.py:1040,1163).  mode 1: implicit im2col over an
