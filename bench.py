@@ -13,8 +13,9 @@ for N > 1, the single all-gather of per-image result records.  Prints ONE JSON l
   e2e   : images/s through the public model API (`model(pixel_values=..., pixel_mask=...)`) starting
           from pinned HOST buffers: H2D of the batch and D2H of logits/boxes/pred_rel/pred_connectivity
           are inside the timed region, as are the eager kernel launches.
-  roofline : the kernel class with the largest share of the step (CUDA events around its launches in
-             the e2e loop); `roofline_msda` / `roofline_relation` report the two kernels BASELINE.json names.
+  roofline : the kernel with the largest share of the step — the TMA-fed tcgen05 GEMM — timed with CUDA events around each
+             of its launches in an eager pass (tensor bound); `roofline_msda_enc` / `roofline_msda_dec` / `roofline_relation`
+             report the kernels BASELINE.json names (HBM bytes / FLOPs as defined in SURVEY.md §8d).
   cpu_baseline : the CPU oracle (a port of the reference forward, oracle/egtr_oracle.py) timed on this
                  box's host cores on a bounded sample (rank 0, N=1).
 """
@@ -269,7 +270,9 @@ def main():
     model.use_cuda_graph = False
     _lib.call("egtr_launch_count_reset")
     eng.probe = {}
+    eng.probe_flops = {}
     for _ in range(args.steps):
+        torch.cuda._sleep(int(2e7))  # ~10 ms head start for the host: the probe events then bracket GPU execution, not launch gaps
         step_e2e()
     torch.cuda.synchronize()
     launches = int(_lib.call("egtr_launch_count")) // args.steps
@@ -314,6 +317,20 @@ def main():
                      "frac": (rel_flops or 0) / tl / 1e12 / peaks["bf16"], "traffic": None, "kernel": "relation head stage (all its launches)",
                      "stage_us": 1e6 * tl, "hbm_GBps_on_algorithmic_bytes": rel_bytes / tl / 1e9,
                      "hbm_frac": rel_bytes / tl / 1e9 / peaks["hbm"], "note": "FLOPs as written in the reference (SURVEY.md §8d)"}
+        # dominant kernel of the step: the TMA-fed tcgen05 GEMM (every launch of gemm_p32_kernel: backbone convolutions,
+        # input_proj, encoder Linears, decoder value projection).  Algorithmic FLOPs = 2*M*N*K summed over its launches; each
+        # product is executed as three bf16 MMAs, so the ceiling of `frac` against the bf16 peak is 1/3.
+        r_gemm = None
+        if "gemm_p32" in spans:
+            tl, n_l = spans["gemm_p32"], counts["gemm_p32"]
+            fl = eng.probe_flops.get("gemm_p32", 0) / args.steps
+            ach = fl / tl / 1e12
+            r_gemm = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                      "traffic": None, "kernel": "gemm_p32_kernel (all launches of the step)", "launches_per_step": n_l,
+                      "avg_launch_us": 1e6 * tl / n_l, "algorithmic_flops_per_step": fl, "share_of_step_kernel_time": tl / sum(v for k, v in spans.items() if k.startswith("stage_")),
+                      "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
+                      "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
+                      "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3"}
         stage = {k[6:]: round(1e3 * v, 3) for k, v in spans.items() if k.startswith("stage_")}
         # dominant kernel class of the step = the stage with the largest share; report the HBM roofline of the
         # encoder gather kernel as `roofline` (BASELINE.json's named kernel) and keep the others beside it
@@ -333,7 +350,7 @@ def main():
             "e2e": {"value": img_s_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * t_e2e / args.steps, "wall_ms_per_step": 1000 * t_e2e_wall / args.steps},
             "gpu_launches": launches,
-            "roofline": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,
+            "roofline": r_gemm if r_gemm is not None else r_msda, "roofline_msda_enc": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,
             "stage_ms": stage,
         }
         if args.cpu_sample > 0 and world == 1:

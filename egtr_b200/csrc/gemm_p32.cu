@@ -732,6 +732,13 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
   EGTR_CHECK(ep.pair_n == 0 && !ep.fin && !ep.dot_w, EGTR_ERR_UNSUPPORTED, "egtr_gemm_sbf16 (P32): relation epilogues are not built here");
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   int bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N >= 192 ? 128 : 64));
+  if (bn == 256) {
+    // wave quantisation: a persistent grid of 74 CTA pairs runs ceil(items / 74) rounds of (bn + fixed) cost each; 87 pair
+    // items of 256 columns (the encoder's 22 223 tokens, N = 256) take two rounds, 174 items of 128 columns take three halves
+    const long long pairs_m = cdiv(cdiv(M, BLOCK_M), 2), slots = num_sms() / 2;
+    const long long c256 = cdiv(pairs_m * (N / 256), slots) * (256 + 32), c128 = cdiv(pairs_m * (N / 128), slots) * (128 + 32);
+    if (c128 < c256) bn = 128;
+  }
   if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
   // CTA pairs (cta_group::2) for every 128/256-wide tile shape with at least two m-tiles: measured through the whole forward,
   // pairs everywhere beat both 1-CTA tiles and a size threshold (less L2->SM weight traffic, one more pipeline stage)

@@ -131,6 +131,7 @@ class Engine:
             raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
         self._ws: Dict[tuple, dict] = {}
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
+        self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
             self._prepare(state_dict)
 
@@ -306,7 +307,10 @@ class Engine:
         src.fmt, ep.out_fmt, ep.res_fmt = a_fmt, out_fmt, res_fmt
         if a_fmt == 1:
             assert a2 is None
-            call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+            with self.span("gemm_p32"):
+                call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
+            if self.probe is not None:
+                self.probe_flops["gemm_p32"] = self.probe_flops.get("gemm_p32", 0) + 2 * M * lin.N * lin.K
             return
         if gemm_backend() == "simt":
             call("egtr_gemm_f32", C.byref(src), _ptr(lin.w), M, lin.N, lin.K, C.byref(ep), _stream())
