@@ -8,11 +8,12 @@ A step = one forward of the hot path over one batch of synthetic images per GPU 
 BASELINE.json: VG config, 3x800x1333, N_q=200, 150 classes, 50 predicates, batch 1 per GPU) plus,
 for N > 1, the single all-gather of per-image result records.  Prints ONE JSON line (rank 0).
 
-  value : images/s with the inputs already resident in HBM; the forward replayed as one CUDA graph;
-          per-step CUDA-event timing, L2 flushed before every step, max over ranks.
-  e2e   : images/s through the public model API (`model(pixel_values=..., pixel_mask=...)`) starting
-          from pinned HOST buffers: H2D of the batch and D2H of logits/boxes/pred_rel/pred_connectivity
-          are inside the timed region, as are the eager kernel launches.
+  value : images/s with the inputs already resident in HBM; every step one CUDA-graph replay of the forward, several
+          (default 3) forwards in flight on separate streams with private workspaces; CUDA events around the K timed
+          steps, max over ranks; inputs rotate over 8 distinct resident images (> L2).  The latency of a single forward
+          (L2 flushed before it) is reported as config.single_forward_latency_ms.
+  e2e   : images/s through the public serving API (`egtr_b200.serving.PipelinedRunner`) starting from pinned HOST
+          buffers: H2D of the batch and D2H of logits/boxes/pred_rel/pred_connectivity are inside the timed region.
   roofline : the kernel with the largest share of the step — the TMA-fed tcgen05 GEMM — timed with CUDA events around each
              of its launches in an eager pass (tensor bound); `roofline_msda_enc` / `roofline_msda_dec` / `roofline_relation`
              report the kernels BASELINE.json names (HBM bytes / FLOPs as defined in SURVEY.md §8d).
