@@ -625,10 +625,13 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   const int m_tiles = p.tiles_w * p.tiles_h * p.nb;
   const int n_tiles = cdiv(N, BLOCK_N);
   const int k_blocks = K / BLOCK_K;
+  // split-K spreads few-tile / long-K problems over the SMs for latency; capped by egtr_set_splitk_max (default 1 = off)
+  const int splitk_cap = splitk_max();
   int splits = 1;
-  if (m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
+  if (splitk_cap > 1 && m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
     splits = num_sms() / (m_tiles * n_tiles);
     if (splits > k_blocks / 4) splits = k_blocks / 4;
+    if (splits > splitk_cap) splits = splitk_cap;
     if (splits < 1) splits = 1;
   }
   const int kbps = cdiv(k_blocks, splits);

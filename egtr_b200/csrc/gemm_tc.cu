@@ -725,9 +725,10 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
   const int tiles = groups * cdiv(M, BLOCK_M) * (Npad / BLOCK_N);
   const int k_blocks = K / BLOCK_K;
   int splits = 1;
-  if (groups == 1 && tiles * 2 <= num_sms() && k_blocks >= 8) {
+  if (groups == 1 && splitk_max() > 1 && tiles * 2 <= num_sms() && k_blocks >= 8) {
     splits = num_sms() / tiles;
     if (splits > k_blocks / 4) splits = k_blocks / 4;
+    if (splits > splitk_max()) splits = splitk_max();
     if (splits < 1) splits = 1;
   }
   int kbps = cdiv(k_blocks, splits);

@@ -35,6 +35,20 @@ int num_sms() {
 static thread_local int g_scratch_slot = 0;
 int scratch_slot() { return g_scratch_slot; }
 
+// Upper bound on split-K factors of the tensor-core GEMMs.  Default 1: with several forwards in flight (the serving mode) idle
+// SMs are filled by other images and the partial-sum round trip is pure cost; a latency-bound single forward wants 64.
+static std::atomic<int> g_splitk_max{-1};
+int splitk_max() {
+  int v = g_splitk_max.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("EGTR_GEMM_SPLITK_MAX");
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+    g_splitk_max.store(v);
+  }
+  return v;
+}
+
 int pdl_mode() {
   static const int mode = [] { const char* e = getenv("EGTR_B200_PDL"); return e ? atoi(e) : 2; }();
   return mode;
@@ -45,6 +59,11 @@ int pdl_mode() {
 extern "C" int egtr_set_scratch_slot(int slot) {
   EGTR_CHECK(slot >= 0 && slot < 8, EGTR_ERR_ARG, "egtr_set_scratch_slot: slot %d outside 0..7", slot);
   egtr::g_scratch_slot = slot;
+  return EGTR_OK;
+}
+extern "C" int egtr_set_splitk_max(int max_splits) {
+  EGTR_CHECK(max_splits >= 1 && max_splits <= 64, EGTR_ERR_ARG, "egtr_set_splitk_max: %d outside 1..64", max_splits);
+  egtr::g_splitk_max.store(max_splits);
   return EGTR_OK;
 }
 extern "C" const char* egtr_last_error(void) { return egtr::g_err; }

@@ -46,6 +46,9 @@ void egtr_launch_count_reset(void);
 /* Internal split-K scratch is kept per slot (0..7, thread-local selection, default 0): forwards that may execute
  * concurrently on different streams (e.g. two captured CUDA graphs) must be enqueued under different slots. */
 int egtr_set_scratch_slot(int slot);
+/* Upper bound (1..64, process-wide) on the split-K factor of the tensor-core GEMMs.  Default 1 (off): the throughput
+ * configuration, where several forwards in flight fill the SMs; 64 minimises the latency of a single forward. */
+int egtr_set_splitk_max(int max_splits);
 
 /* ---------------------------------------------------------------- GEMM-class operators ---- */
 /* Left-operand source: rows of 64-float runs.  mode 0: row m = a + m*lda (+ a2 + m*lda when a2

@@ -23,11 +23,17 @@ def _run(cfg, sd, px, mask, cuda):
     return model, out
 
 
+@pytest.mark.parametrize("splitk_max", [1, 64])  # 1: the library default (throughput serving); 64: latency configuration
 @pytest.mark.parametrize("name", CASES)
-def test_forward_matches_reference_golden(cuda, name):
+def test_forward_matches_reference_golden(cuda, name, splitk_max):
+    from egtr_b200 import _lib
     ref, meta = load_golden(name)
     cfg, sd, px, mask = case_inputs(meta)
-    _, out = _run(cfg, sd, px, mask, cuda)
+    _lib.call("egtr_set_splitk_max", splitk_max)
+    try:
+        _, out = _run(cfg, sd, px, mask, cuda)
+    finally:
+        _lib.call("egtr_set_splitk_max", 1)
     assert out["logits"].shape == (meta["batch"], cfg.num_queries, cfg.num_labels)
     assert "pred_connectivity" in out and out.pred_rel.shape[-1] == cfg.num_rel_labels
     errs = compare_forward(out, ref)

@@ -9,6 +9,15 @@ from tests.util import load_golden, relerr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _splitk_enabled():
+    """Kernel tests exercise the split-K paths too (the library default caps split-K at 1 for throughput serving)."""
+    from egtr_b200 import _lib
+    _lib.call("egtr_set_splitk_max", 64)
+    yield
+    _lib.call("egtr_set_splitk_max", 1)
+
+
 def _eng_helpers():
     from egtr_b200 import _lib
     from egtr_b200.engine import Lin, _ptr, _stream

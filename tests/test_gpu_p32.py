@@ -9,6 +9,15 @@ from tests.util import p32_decode, p32_encode, relerr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _splitk_enabled():
+    """Kernel tests exercise the split-K paths too (the library default caps split-K at 1 for throughput serving)."""
+    from egtr_b200 import _lib
+    _lib.call("egtr_set_splitk_max", 64)
+    yield
+    _lib.call("egtr_set_splitk_max", 1)
+
+
 def _st():
     return torch.cuda.current_stream().cuda_stream
 
