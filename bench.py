@@ -332,6 +332,11 @@ def main():
                       "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
                       "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
                       "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3"}
+        if os.environ.get("EGTR_BENCH_SHAPES"):  # dev: per-shape GEMM table (warm, in-pipeline timings) on stderr
+            for k in sorted((k for k in spans if k.startswith("gemm_p32:")), key=lambda k: -spans[k]):
+                m_, n_, k_ = [int(v) for v in k.split(":")[1].split("x")]
+                us = 1e6 * spans[k] / counts[k]
+                print(f"{k:34s} n={counts[k]:3d} {us:8.1f} us/launch {2 * m_ * n_ * k_ / us / 1e6:7.1f} TFLOP/s  total {1e6 * spans[k]:8.1f} us", file=sys.stderr)
         stage = {k[6:]: round(1e3 * v, 3) for k, v in spans.items() if k.startswith("stage_")}
         # dominant kernel class of the step = the stage with the largest share; report the HBM roofline of the
         # encoder gather kernel as `roofline` (BASELINE.json's named kernel) and keep the others beside it

@@ -39,25 +39,34 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int TMA_WARP = 8, MMA_WARP = 9;
-constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
+constexpr int MAX_EPI_WARPS = 8;
 constexpr int A_GROUP_BYTES = BLOCK_M * 128;  // one 32-channel group of 128 rows: hi 64 B | lo 64 B per row
 constexpr int STG_BYTES = 32 * 128;           // one epilogue box: 32 rows x 32 channels
 
 // CTAS == 2: a cluster of two CTAs computes a 256-row tile with one cta_group::2 MMA — each CTA stages its own 128 activation
 // rows and only HALF of the weight tile, so a k-block costs 64 KB instead of 96 KB of L2->SM traffic per SM at BLOCK_N = 256
 // and a third pipeline stage fits.
-template <int BLOCK_N, int CTAS>
+// OCC == 2: the two-CTAs-per-SM configuration (128-wide tiles, four epilogue warps, two pipeline stages, 112.5 KB of shared
+// memory, 256 of the SM's 512 TMEM columns): one CTA's MMAs fill the tensor pipe while the other runs its epilogue, prologue or
+// tail, and the next kernel's CTAs can become resident (PDL) as soon as one of the two slots frees up.
+template <int BLOCK_N, int CTAS, int OCC = 1>
 struct PCfg {
+  static constexpr int EPI_WARPS = OCC == 2 ? 4 : 8;
+  static constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+  static constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
+  static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
   static constexpr int B_ROWS = BLOCK_N / CTAS;  // weight rows staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_GROUP_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 4 ? 4 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGE_BUDGET = OCC == 2 ? 96 * 1024 : 192 * 1024;
+  static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 4 ? 4 : STAGE_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int CTRL_BYTES = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + 1024 /*align slack*/;
-  static constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per epilogue warp (half of the tile's columns)
+  // OCC == 2 must fit twice into the SM's 228 KB (1 KB reserved per CTA): no alignment slack, the kernel checks the base instead
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + (OCC == 2 ? 0 : 1024 /*align slack*/);
+  static constexpr int CHUNKS = COLS_PER_WARP / 32;  // 32-column chunks per epilogue warp
+  static_assert(STAGES >= 2, "operand ring needs at least two stages");
+  static_assert(OCC == 1 || 2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM do not fit");
 };
 
 struct PArgs {
@@ -108,15 +117,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int CTAS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, int CTAS, int OCC>
+__global__ void __launch_bounds__((PCfg<BLOCK_N, CTAS, OCC>::NUM_THREADS), OCC)
 gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const PArgs p,
                 int* __restrict__ err) {
   pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
-  using C = PCfg<BLOCK_N, CTAS>;
-  extern __shared__ uint8_t smem_raw[];
+  using C = PCfg<BLOCK_N, CTAS, OCC>;
+  constexpr int EPI_WARPS = C::EPI_WARPS, TMA_WARP = C::TMA_WARP, MMA_WARP = C::MMA_WARP;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if (OCC == 2 && smem != smem_raw) {  // no slack in this configuration: the SW128 tiles need the 1024-byte aligned base
+    if (threadIdx.x == 0 && err) atomicExch(err, 299);
+    __trap();
+  }
   uint8_t* stg_all = smem + C::STAGES * C::STAGE_BYTES;         // [EPI_WARPS][4096], 1024-aligned
   uint8_t* ctrl = stg_all + EPI_WARPS * STG_BYTES;
   uint64_t* full_bar = (uint64_t*)ctrl;          // [STAGES]
@@ -124,7 +138,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_full = empty_bar + 4;           // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* res_bar = tmem_empty + 2;            // [EPI_WARPS]
-  uint32_t* tmem_holder = (uint32_t*)(res_bar + EPI_WARPS);
+  uint32_t* tmem_holder = (uint32_t*)(res_bar + MAX_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,7 +291,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int ow = t.w0 + ((q * 32) & ((1 << p.bw_log2) - 1));
       const int oh = t.h0 + ((q * 32) >> p.bw_log2);
       const int zc = t.sp * p.nb + t.b;    // batch coordinate (split-K partial sums: one batch block per split)
-      const int col_base = t.n0 + hf * (BLOCK_N / 2);
+      const int col_base = t.n0 + hf * C::COLS_PER_WARP;
       int nch = (p.ncols - col_base + 31) / 32;
       nch = nch < 0 ? 0 : (nch > C::CHUNKS ? C::CHUNKS : nch);
       if (ow >= p.lim_w || oh >= p.lim_h || t.b >= p.nb) nch = 0;  // box entirely in the tail (or a phantom tile): nothing to store
@@ -295,7 +309,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         continue;
       }
       uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * (BLOCK_N / 2), r);
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * C::COLS_PER_WARP, r);
 #pragma unroll 1
       for (int ci = 0; ci < nch; ++ci) {
         const int n = col_base + ci * 32;
@@ -306,7 +320,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (ci + 1 < nch) {  // next chunk's accumulator read overlaps this chunk's arithmetic and store
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * (BLOCK_N / 2) + (ci + 1) * 32, r);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * C::COLS_PER_WARP + (ci + 1) * 32, r);
         } else {  // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp right away
           release_tmem_stage<CTAS>(&tmem_empty[acc], lane);
         }
@@ -383,7 +397,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (p.has_res) __syncwarp();
       }
     }
-    if (lane == 0) bulk_wait0();  // all stores of this warp have left shared memory and are complete
+    if (lane == 0) bulk_wait_read0();  // all stores of this warp have been read out of shared memory (global visibility: kernel end)
   }
 
   ptx::tc_fence_before();
@@ -598,10 +612,10 @@ int pick_bw_log2(int OW, int OH) {
   return best;
 }
 
-template <int BLOCK_N, int CTAS>
+template <int BLOCK_N, int CTAS, int OCC = 1>
 int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                cudaStream_t st) {
-  using C = PCfg<BLOCK_N, CTAS>;
+  using C = PCfg<BLOCK_N, CTAS, OCC>;
   const bool conv = a.mode == 1;
   PArgs p = {};
   p.M = M; p.N = N; p.K = K;
@@ -626,7 +640,9 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   const int n_tiles = cdiv(N, BLOCK_N);
   const int k_blocks = K / BLOCK_K;
   // split-K spreads few-tile / long-K problems over the SMs for latency; capped by egtr_set_splitk_max (default 1 = off)
-  const int splitk_cap = splitk_max();
+  // ... except that a handful of CTAs never walk more than 32 k-blocks alone (the extra level's 3x3/2 conv on C5: 273 rows, K = 18432)
+  int splitk_cap = splitk_max();
+  if (k_blocks / 32 > splitk_cap) splitk_cap = k_blocks / 32;
   int splits = 1;
   if (splitk_cap > 1 && m_tiles * n_tiles * 2 <= num_sms() && k_blocks >= 8) {
     splits = num_sms() / (m_tiles * n_tiles);
@@ -690,13 +706,13 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   }
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N, CTAS, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
-  const int slots = num_sms() / CTAS;
+  const int slots = OCC * num_sms() / CTAS;
   const int grid = (work < slots ? work : slots) * CTAS;
-  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS>, dim3(grid), dim3(NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, p,
+  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, OCC>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, p,
                        device_error_flag_p32()));
   if (splits > 1) {
     ReduceArgs r = {};
@@ -750,7 +766,11 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
   bool pair = bn >= 128 && tiles >= 2;
   if (forced_ctas == 1) pair = false;
   if (forced_ctas == 2 && bn >= 128) pair = true;
+  static const int occ2 = [] { const char* e = getenv("EGTR_GEMM_OCC2"); return e ? atoi(e) : 0; }();  // dev experiments only
+  static const int occ2_maxwork = [] { const char* e = getenv("EGTR_GEMM_OCC2_MAXWORK"); return e ? atoi(e) : 0; }();  // dev experiments only
   if (pair) {
+    const long long work128 = (long long)cdiv(cdiv(M, BLOCK_M), 2) * cdiv(N, 128);
+    if (occ2 || work128 <= occ2_maxwork) return launch_p32<128, 2, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
     if (bn == 256) return launch_p32<256, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
     return launch_p32<128, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
   }

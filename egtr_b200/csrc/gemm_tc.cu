@@ -530,7 +530,22 @@ gemm_sbf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const ASrc src, co
               v.x = sigmoidf_(v.x); v.y = sigmoidf_(v.y); v.z = sigmoidf_(v.z); v.w = sigmoidf_(v.w);
             }
             }
-            if (orow[i] >= 0) *(float4*)(obase + orow[i] * ldo + n) = v;
+            if (orow[i] >= 0) {
+              if (ep.out_fmt == EGTR_FMT_P32 && splits == 1) {  // P32 rows: hi 8 bytes at (n % 32) * 2 of the group, lo 64 bytes further
+                __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                uint2 ph, pl;
+                ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+                pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+                uint8_t* g = (uint8_t*)(obase + orow[i] * ldo + (n & ~31)) + (n & 31) * 2;
+                *(uint2*)g = ph;
+                *(uint2*)(g + 64) = pl;
+              } else {
+                *(float4*)(obase + orow[i] * ldo + n) = v;
+              }
+            }
           }
         } else {  // N tail or unaligned leading dimension: per-element, still fully unrolled (registers only)
           auto put = [&](long long row, int col, float v, float bv, bool keep, const float* tp) {
@@ -820,8 +835,8 @@ extern "C" int egtr_gemm_sbf16(const egtr_asrc_t* a, const void* w_planes, int M
   count_launch();
   cudaStream_t st = (cudaStream_t)s;
   if (a->fmt == EGTR_FMT_P32) return gemm_p32_dispatch(*a, w_planes, Npad, M, N, Npad, K, *ep, st);
-  EGTR_CHECK(ep->out_fmt == EGTR_FMT_F32 && ep->res_fmt == EGTR_FMT_F32, EGTR_ERR_UNSUPPORTED,
-             "egtr_gemm_sbf16: P32 outputs / residuals are written by the P32-operand kernel only");
+  EGTR_CHECK(ep->res_fmt == EGTR_FMT_F32 && (ep->out_fmt == EGTR_FMT_F32 || (N % 32 == 0 && ep->ldo % 4 == 0 && !ep->fin)), EGTR_ERR_UNSUPPORTED,
+             "egtr_gemm_sbf16: fp32-operand kernel: no P32 residuals; P32 output needs N %% 32 == 0 and no split-K");
   return dispatch(*a, w_planes, M, N, Npad, K, *ep, st, 1, 0, nullptr);
 }
 

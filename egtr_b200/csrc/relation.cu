@@ -95,7 +95,7 @@ finish_kernel(const float* __restrict__ rel_logits, int ld_rel, const float* __r
   }
   if (logit_adj) v -= tau * logf(rel_dist[p]);  // egtr.py:509-512
   pred_rel[t] = sigmoidf_(v);
-  if (p == 0) pred_conn[pair] = sigmoidf_(conn_logits[pair * ld_conn]);
+  if (p == 0 && conn_logits != nullptr) pred_conn[pair] = sigmoidf_(conn_logits[pair * ld_conn]);
 }
 
 }  // namespace
@@ -118,16 +118,18 @@ extern "C" int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, con
                                         const float* logits, int K, const float* triplet_dist, const float* rel_dist,
                                         float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
                                         int* cls_scratch, float* pred_rel, float* pred_conn, egtr_stream_t s) {
-  EGTR_CHECK(rel_logits && conn_logits && logits && pred_rel && pred_conn && cls_scratch, EGTR_ERR_ARG,
+  EGTR_CHECK(rel_logits && pred_rel && cls_scratch && (!conn_logits || pred_conn), EGTR_ERR_ARG,
              "egtr_relation_finish_f32: null pointer");
   EGTR_CHECK(!use_freq_bias || triplet_dist, EGTR_ERR_ARG, "egtr_relation_finish_f32: triplet_dist missing");
   EGTR_CHECK(!logit_adjustment || rel_dist, EGTR_ERR_ARG, "egtr_relation_finish_f32: rel_dist missing");
-  launch_pdl(argmax_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, logits, K, B * N, cls_scratch);
+  if (logits != nullptr) {  // NULL: cls_scratch already holds the argmax classes (egtr_argmax_rows_f32)
+    launch_pdl(argmax_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), (size_t)(0), (cudaStream_t)s, logits, K, B * N, cls_scratch);
+    count_launch();
+  }
   const long long pairs = (long long)B * N * N;
   launch_pdl(finish_kernel, dim3(cdiv(pairs * P, 256)), dim3(256), (size_t)(0), (cudaStream_t)s, rel_logits, ld_rel, conn_logits, ld_conn, cls_scratch, K + 1,
                                                                   triplet_dist, rel_dist, tau, use_freq_bias, logit_adjustment, N, P,
                                                                   pairs, pred_rel, pred_conn);
-  count_launch();
   count_launch();
   EGTR_CUDA(cudaGetLastError());
   return EGTR_OK;

@@ -264,6 +264,14 @@ class Engine:
         self.rel_w2 = L(sd["rel_predictor.layers.1.weight"], sd["rel_predictor.layers.1.bias"])
         self.con_w2 = L(sd["connectivity_layer.layers.1.weight"], sd["connectivity_layer.layers.1.bias"])
         self.rel_w3 = L(sd["rel_predictor.layers.2.weight"], sd["rel_predictor.layers.2.bias"])
+        # layer 3 on the TMA-fed kernel wants N % 32 == 0: predicate rows padded with zeros to a multiple of 64
+        P_ = sd["rel_predictor.layers.2.weight"].shape[0]
+        Pp = ((P_ + 63) // 64) * 64
+        w3p = torch.zeros(Pp, 256, device=dev)
+        w3p[:P_] = sd["rel_predictor.layers.2.weight"]
+        b3p = torch.zeros(Pp, device=dev)
+        b3p[:P_] = sd["rel_predictor.layers.2.bias"]
+        self.rel_w3p = L(w3p, b3p)
         self.con_w3_w = sd["connectivity_layer.layers.2.weight"].contiguous()
         self.con_w3_b = sd["connectivity_layer.layers.2.bias"].contiguous()
         self.triplet = sd["triplet_dist"].contiguous()
@@ -307,7 +315,7 @@ class Engine:
         src.fmt, ep.out_fmt, ep.res_fmt = a_fmt, out_fmt, res_fmt
         if a_fmt == 1:
             assert a2 is None
-            with self.span("gemm_p32"):
+            with self.span("gemm_p32"), self.span(f"gemm_p32:{M}x{lin.N}x{lin.K}" + (":conv" if conv is not None else "")):
                 call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), M, lin.N, lin.Npad, lin.K, C.byref(ep), _stream())
             if self.probe is not None:
                 self.probe_flops["gemm_p32"] = self.probe_flops.get("gemm_p32", 0) + 2 * M * lin.N * lin.K
@@ -412,7 +420,7 @@ class Engine:
         ws["H1"] = torch.empty(B * N * N, 512, **f32)
         ws["H2r"] = torch.empty(B * N * N, 256, **f32)
         ws["H2c"] = torch.empty(B * N * N, 256, **f32)
-        ws["rel_logits"] = torch.empty(B * N * N, cfg.num_rel_labels, **f32)
+        ws["rel_logits"] = torch.empty(B * N * N, ((cfg.num_rel_labels + 63) // 64) * 64, **f32)
         ws["con_logits"] = torch.empty(B * N * N, 1, **f32)
         ws["cls_idx"] = torch.empty(B * N, dtype=torch.int32, device=dev)
         self._ws[key] = ws
@@ -660,19 +668,17 @@ class Engine:
             src.a, src.a2, src.aux, src.mode, src.lda = _ptr(ws["U"]), _ptr(ws["V"]), _ptr(self.rel_b1), 4, 516
             src.H, src.W, src.C, src.OH, src.OW = N, Lr, 256, TI, TJ
             ep.bias, ep.out, ep.ldo, ep.ldr, ep.relu = _ptr(self.rel_w2both.b), _ptr(ws["H2r"]), 256, 256, 1
+            ep.out_fmt = 1  # the relation MLP's hidden goes to HBM as P32 rows: layer 3 streams it by TMA
             ep.pair_n = N
             ep.dot_w, ep.dot_out, ep.dot_b, ep.dot_col0 = _ptr(self.con_w3_w), _ptr(pred_con), self.con_w3_b_host, 256
             lin = self.rel_w2both
             call("egtr_gemm_sbf16", C.byref(src), _ptr(lin.planes), B * TI * TJ * 128, lin.N, lin.Npad, lin.K, C.byref(ep), st)
             call("egtr_argmax_rows_f32", _ptr(logits), K, B * N, _ptr(ws["cls_idx"]), st)
-            src2, ep2 = ASrc(), Epilogue()
-            src2.a, src2.mode, src2.lda = _ptr(ws["H2r"]), 0, 256
-            ep2.bias, ep2.out, ep2.ldo, ep2.ldr = _ptr(self.rel_w3.b), _ptr(pred_rel), P, P
-            ep2.fin, ep2.fin_n, ep2.cls, ep2.k1 = 1, N, _ptr(ws["cls_idx"]), K + 1
-            ep2.triplet = _ptr(self.triplet) if cfg.use_freq_bias else None
-            ep2.adj = _ptr(self.rel_adj) if cfg.logit_adjustment else None
-            lin3 = self.rel_w3
-            call("egtr_gemm_sbf16", C.byref(src2), _ptr(lin3.planes), pairs, lin3.N, lin3.Npad, lin3.K, C.byref(ep2), st)
+            lin3 = self.rel_w3p
+            self.gemm(lin3, pairs, ws["rel_logits"], a=ws["H2r"], lda=256, a_fmt=1, ldo=lin3.N)
+            call("egtr_relation_finish_f32", _ptr(ws["rel_logits"]), lin3.N, None, 0, None, K,
+                 _ptr(self.triplet) if cfg.use_freq_bias else None, _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)),
+                 int(bool(cfg.use_freq_bias)), int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), None, st)
         _sp_rel.__exit__()
         # captured decoder self-attention states as [B, heads, N, 32] views (deformable_detr.py:1179-1185)
         qs = tuple(q.view(B, N, 3, 8, 32)[:, :, 0].permute(0, 2, 1, 3) for q in qkvs)

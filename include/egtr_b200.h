@@ -227,7 +227,8 @@ int egtr_small_linear_f32(const float* x, int ldx, const float* w, const float* 
 int egtr_relation_pair_hidden_f32(const float* U, const float* V, int ldu, const float* b1, int B, int N, int Lr,
                                   float* H1, egtr_stream_t s);
 /* pred_rel = sigmoid(rel_logits + triplet_dist[c_i, c_j, :] - tau*log(rel_dist)), c = argmax(logits);
- * pred_conn = sigmoid(conn_logits).  rel_logits [B*N*N, ld_rel], conn_logits [B*N*N, ld_conn]. */
+ * pred_conn = sigmoid(conn_logits).  rel_logits [B*N*N, ld_rel], conn_logits [B*N*N, ld_conn].  conn_logits may be NULL
+ * (connectivity already finished elsewhere); logits may be NULL when cls_scratch already holds the argmax classes. */
 int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, const float* conn_logits, int ld_conn,
                              const float* logits, int K, const float* triplet_dist, const float* rel_dist,
                              float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,

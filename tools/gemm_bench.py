@@ -28,6 +28,11 @@ SHAPES = [  # name, M, N, K, kind
     ("rel_w2", 40000, 256, 256, "plain"),
     ("dec_fc2", 200, 256, 1024, "res"),
     ("dec_qk", 200, 512, 256, "a2"),
+    ("tiny_1tile", 128, 64, 64, "plain"),
+    ("tiny_1pair", 256, 256, 256, "plain"),
+    ("one_round_n256", 18944, 256, 256, "plain"),
+    ("two_rounds_n256", 37888, 256, 256, "plain"),
+    ("one_round_k1024", 18944, 256, 1024, "plain"),
 ]
 
 ap = argparse.ArgumentParser()
