@@ -13,7 +13,8 @@
 //   phase 1: 256 threads = 16 (query) x 16 (sample) lanes: read the raw offsets/logits (fused form) or
 //            the precomputed locations/weights (drop-in form), softmax over the 16 samples with
 //            16-lane shuffles, turn each sample into 4 corner token indices + 4 combined weights in smem;
-//   phase 2: 32 groups of 8 lanes: stream the 16 samples of one query, 4 predicated LDG.128 each.
+//   phase 2: 32 groups of 8 lanes: stream the 16 samples of one query, 4 LDG.128 each (unconditional in the fused form:
+//            absent corners carry weight 0 and point at token 0).
 #include "common.cuh"
 
 namespace egtr {
@@ -101,7 +102,11 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     const int qi = (tid >> 4) + pass * (QPB / 2);
     const int q = q_of[qi];
     float* slot = &slots[qi * Q_STRIDE + s * SLOT_WORDS];
-    int idx[4] = {-1, -1, -1, -1};
+    // corners outside the map (and samples outside the image) keep weight 0 and point at token 0: phase 2 can then load
+    // unconditionally — no predicates and no register zeroing per gather (values are finite, so 0 * v contributes nothing)
+    // (fused form only: its value tensor is this library's own finite GEMM output; the drop-in op keeps predicated loads)
+    constexpr int kNone = FUSED ? 0 : -1;
+    int idx[4] = {kNone, kNone, kNone, kNone};
     float cw[4] = {0.f, 0.f, 0.f, 0.f};
     // L*P == 16 with P == 4 is asserted on the host.
     const int l = s >> 2;
@@ -183,10 +188,10 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-    if (id.x >= 0) v0 = __ldg((const float4*)(vbase + (long long)id.x * a.ld_value));
-    if (id.y >= 0) v1 = __ldg((const float4*)(vbase + (long long)id.y * a.ld_value));
-    if (id.z >= 0) v2 = __ldg((const float4*)(vbase + (long long)id.z * a.ld_value));
-    if (id.w >= 0) v3 = __ldg((const float4*)(vbase + (long long)id.w * a.ld_value));
+    if (FUSED || id.x >= 0) v0 = __ldg((const float4*)(vbase + (long long)id.x * a.ld_value));
+    if (FUSED || id.y >= 0) v1 = __ldg((const float4*)(vbase + (long long)id.y * a.ld_value));
+    if (FUSED || id.z >= 0) v2 = __ldg((const float4*)(vbase + (long long)id.z * a.ld_value));
+    if (FUSED || id.w >= 0) v3 = __ldg((const float4*)(vbase + (long long)id.w * a.ld_value));
     acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y); acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
     acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y); acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
     acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
