@@ -272,11 +272,15 @@ def main():
     _lib.call("egtr_launch_count_reset")
     eng.probe = {}
     eng.probe_flops = {}
+    # the probes time ONE forward's launches back to back (nothing else on the GPU): use the single-forward configuration
+    # (split-K on), not the throughput one in which few-CTA launches rely on other images to fill the SMs
+    _lib.call("egtr_set_splitk_max", 64)
     for _ in range(args.steps):
         torch.cuda._sleep(int(2e7))  # ~10 ms head start for the host: the probe events then bracket GPU execution, not launch gaps
         step_e2e()
     torch.cuda.synchronize()
     launches = int(_lib.call("egtr_launch_count")) // args.steps
+    _lib.call("egtr_set_splitk_max", 1)
     probe, eng.probe = eng.probe, None
     clocks = sampler.stop() if rank == 0 else None
 
@@ -331,7 +335,7 @@ def main():
                       "avg_launch_us": 1e6 * tl / n_l, "algorithmic_flops_per_step": fl, "share_of_step_kernel_time": tl / sum(v for k, v in spans.items() if k.startswith("stage_")),
                       "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
                       "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
-                      "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3"}
+                      "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3; launches timed one forward at a time with split-K on (egtr_set_splitk_max 64)"}
         if os.environ.get("EGTR_BENCH_SHAPES"):  # dev: per-shape GEMM table (warm, in-pipeline timings) on stderr
             for k in sorted((k for k in spans if k.startswith("gemm_p32:")), key=lambda k: -spans[k]):
                 m_, n_, k_ = [int(v) for v in k.split(":")[1].split("x")]

@@ -41,6 +41,7 @@ ap.add_argument("--only", type=str, default="")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--p32", action="store_true", help="feed plain-row shapes as P32 rows (TMA-fed kernel); --p32out also writes P32")
 ap.add_argument("--p32out", action="store_true")
+ap.add_argument("--p32prof", action="store_true", help="with an EGTR_P32_PROF build: phase timestamps of CTA 0")
 ap.add_argument("--noflush", action="store_true", help="do not flush L2 between iterations (operands stay L2-resident as inside the forward)")
 ap.add_argument("--prof", action="store_true", help="with an EGTR_GEMM_PROF build: print per-role cycle accounting")
 args = ap.parse_args()
@@ -110,6 +111,15 @@ for idx, (name, M, N, K, kind) in enumerate(SHAPES):
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
     us = ts[len(ts) // 2]
+    if args.p32prof:
+        lib = _lib.load()
+        lib.egtr_debug_p32_prof.argtypes = [C.c_void_p]
+        buf = (C.c_ulonglong * 8)()
+        flush.fill_(0); run(); torch.cuda.synchronize()
+        lib.egtr_debug_p32_prof(buf)
+        t = [int(v) for v in buf[:6]]
+        names = ["setup+pdl", "first stage full", "first acc full", "epilogue w0 done", "exit"]
+        print("   CTA0 phases (us): " + " | ".join(f"{n} +{(t[i + 1] - t[i]) / 1e3:.2f}" for i, n in enumerate(names)) + f" | total {(t[5] - t[0]) / 1e3:.2f}")
     if args.prof:
         import numpy as np
         buf = (C.c_ulonglong * (148 * 16))()
