@@ -269,7 +269,13 @@ def main():
     probe, eng.probe = eng.probe, None
     # per-kernel probes and the launch count need eager launches: one extra untimed eager pass per step count
     model.use_cuda_graph = False
+    # kernels per step in the timed (throughput) configuration = launches of one eager forward with the same settings
+    step_e2e()
+    torch.cuda.synchronize()
     _lib.call("egtr_launch_count_reset")
+    step_e2e()
+    torch.cuda.synchronize()
+    launches = int(_lib.call("egtr_launch_count"))
     eng.probe = {}
     eng.probe_flops = {}
     # the probes time ONE forward's launches back to back (nothing else on the GPU): use the single-forward configuration
@@ -279,7 +285,6 @@ def main():
         torch.cuda._sleep(int(2e7))  # ~10 ms head start for the host: the probe events then bracket GPU execution, not launch gaps
         step_e2e()
     torch.cuda.synchronize()
-    launches = int(_lib.call("egtr_launch_count")) // args.steps
     _lib.call("egtr_set_splitk_max", 1)
     probe, eng.probe = eng.probe, None
     clocks = sampler.stop() if rank == 0 else None

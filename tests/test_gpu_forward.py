@@ -137,3 +137,21 @@ def test_fused_relation_stage_matches_unfused_kernels(cuda, wl, batch, monkeypat
     torch.cuda.synchronize()
     for k in ("pred_rel", "pred_connectivity", "logits"):
         assert relerr(got[k], want[k]) < 2e-4, k
+
+
+@pytest.mark.parametrize("wl,hw,batch", [("D", (224, 320), 2), ("E", (256, 256), 2)])
+def test_forward_other_label_spaces_vs_live_oracle(cuda, wl, hw, batch):
+    """BASELINE.json configs D (601 classes / 30 predicates, N_q=200) and E (N_q=300, 200 predicates) at a reduced image size the
+    CPU oracle finishes in seconds: query / class / predicate counts are the full ones, so every N-, K- and P-dependent
+    kernel shape (pair tiles, padded predicate columns, frequency-bias gather) is the production one."""
+    from egtr_b200.config import workload_config
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from oracle import egtr_oracle as orc
+    cfg = workload_config(wl)
+    sd = synth_state_dict(cfg, 50)
+    px, mask = synth_images(batch, hw[0], hw[1], seed=51, pad_to=[hw, (hw[0] - 32, hw[1] - 48)][:batch])
+    want = orc.forward(sd, cfg, px, mask)
+    _, out = _run(cfg, sd, px, mask, cuda)
+    errs = compare_forward(out, want)
+    print(wl, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
