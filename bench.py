@@ -35,6 +35,15 @@ METRIC = "images/sec (3x800x1333, N_q=200)"
 WORKLOAD = "B"
 
 
+def _traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu pass (profiles/r01_traffic.json, tools/gpu_traffic.sh), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.isfile(p):
+        return None
+    k = json.load(open(p)).get("kernels", {}).get(kernel)
+    return k["dram_bytes_per_launch"] if k else None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -310,7 +319,7 @@ def main():
             t_launch = spans[name] / n
             ach = bytes_per_launch / t_launch / 1e9
             return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                    "traffic": None, "kernel": name, "avg_launch_us": 1e6 * t_launch, "launches_per_step": n,
+                    "traffic": _traffic(name), "kernel": name, "avg_launch_us": 1e6 * t_launch, "launches_per_step": n,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peaks["src"] + " (hbm_gbs)"}
 
         # MSDeformAttn, encoder form: SURVEY.md §8d algorithmic bytes = 4*B*[S*C + Lq*M*L*P*3 + Lq*C] = 3584*S per image
@@ -336,7 +345,8 @@ def main():
             fl = eng.probe_flops.get("gemm_p32", 0) / args.steps
             ach = fl / tl / 1e12
             r_gemm = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                      "traffic": None, "kernel": "gemm_p32_kernel (all launches of the step)", "launches_per_step": n_l,
+                      "traffic": _traffic("gemm_p32_kernel"), "traffic_note": "DRAM bytes per launch, ncu dram__bytes_read+write averaged over the step's launches (profiles/r01_traffic.json)",
+                      "kernel": "gemm_p32_kernel (all launches of the step)", "launches_per_step": n_l,
                       "avg_launch_us": 1e6 * tl / n_l, "algorithmic_flops_per_step": fl, "share_of_step_kernel_time": tl / sum(v for k, v in spans.items() if k.startswith("stage_")),
                       "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
                       "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
