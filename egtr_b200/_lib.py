@@ -28,7 +28,8 @@ class Epilogue(C.Structure):
                 ("off", C.c_int), ("row_keep", C.c_void_p),
                 ("pair_n", C.c_int), ("dot_w", C.c_void_p), ("dot_out", C.c_void_p), ("dot_b", C.c_float), ("dot_col0", C.c_int),
                 ("fin", C.c_int), ("fin_n", C.c_int), ("cls", C.c_void_p), ("triplet", C.c_void_p), ("adj", C.c_void_p), ("k1", C.c_int),
-                ("out_fmt", C.c_int), ("res_fmt", C.c_int)]
+                ("out_fmt", C.c_int), ("res_fmt", C.c_int),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_addend", C.c_void_p), ("ln_out2", C.c_void_p)]
 
 
 FMT_F32, FMT_P32 = 0, 1

@@ -86,6 +86,11 @@ struct PArgs {
   int relu, out_fmt, res_fmt, has_res;
   int splits, kb_per_split, plane_rows;
   int ncols;              // columns that exist in the output map (N, or Npad for split-K partial sums)
+  // LayerNorm epilogue (N == BLOCK_N == 256): out = LN(acc + bias + res) * gamma + beta; out2 = out + addend (optional)
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* ln_addend;
+  int ln, ln_out2, ln_ld;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c, int x, int y, int z) {
@@ -134,8 +139,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
 template <int BLOCK_N, int CTAS, int WS>
 __global__ void __launch_bounds__((PCfg<BLOCK_N, CTAS, WS>::NUM_THREADS), 1)
 gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const PArgs p,
-                int* __restrict__ err) {
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                const __grid_constant__ CUtensorMap tmap_out2, const PArgs p, int* __restrict__ err) {
   pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
   if (threadIdx.x == 0) P32_STAMP(0);
   using C = PCfg<BLOCK_N, CTAS, WS>;
@@ -404,6 +409,128 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         continue;
       }
       uint32_t r[32];
+      if (C::CHUNKS == 4 && p.ln) {
+        // ---- Linear + residual + LayerNorm in one epilogue.  A row's 256 columns live in two warps (column halves): pass A
+        // adds bias and residual, writes the sums back into the TMEM accumulator and reduces sum / sum of squares; the two
+        // warps swap their partial sums through their staging tiles; pass B re-reads TMEM, normalises and stores P32 rows.
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * C::COLS_PER_WARP;
+        float s1 = 0.f, s2 = 0.f;
+        ptx::tmem_ld_32x32(t_addr, r);
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int n = col_base + ci * 32;
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r[j]));
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ci + 1 < 4) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, r);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg((const float4*)(p.bias + n) + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.has_res) {
+            ptx::mbar_wait(rbar, res_phase, err, 206);
+            res_phase ^= 1;
+            uint32_t x[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                           : "r"(my_row_s + ((c ^ sw) << 4)) : "memory");
+            __syncwarp();  // every lane has read this residual box: the next one may land in the staging tile
+            if (lane == 0 && ci + 1 < 4) {
+              ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
+              tma_load_4d(stg_s, &tmap_res, rbar, n + 32, ow, oh, zc);
+            }
+            if (p.res_fmt == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(x[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                v[2 * j] += __uint_as_float(x[j] << 16) + __uint_as_float(x[16 + j] << 16);
+                v[2 * j + 1] += __uint_as_float(x[j] & 0xffff0000u) + __uint_as_float(x[16 + j] & 0xffff0000u);
+              }
+            }
+          }
+          uint32_t vb[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); vb[j] = __float_as_uint(v[j]); }
+          ptx::tmem_st_32x32(t_addr + ci * 32, vb);
+        }
+        ptx::tmem_st_wait();
+        {  // swap (sum, sum of squares) with the warp that owns the other 128 columns of the same 32 rows
+          float2* mine = (float2*)stg;
+          const float2* theirs = (const float2*)(stg_all + (warp ^ 4) * STG_BYTES);
+          mine[lane] = make_float2(s1, s2);
+          ptx::named_bar_sync(1 + q, 64);
+          const float2 o2 = theirs[lane];
+          ptx::named_bar_sync(1 + q, 64);  // both warps have read before either overwrites its staging tile with output
+          s1 += o2.x; s2 += o2.y;
+        }
+        const float mean = s1 * (1.f / 256.f);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.f / 256.f) - mean * mean, 0.f) + 1e-5f);
+        const long long grow = (long long)t.b * p.keep_bstride + p.keep_off + ow + lane;  // rows mode: this lane's output row
+        const bool row_ok = ow + lane < p.lim_w;
+        ptx::tmem_ld_32x32(t_addr, r);
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int n = col_base + ci * 32;
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r[j]));
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ci + 1 < 4) ptx::tmem_ld_32x32(t_addr + (ci + 1) * 32, r);
+          else release_tmem_stage<CTAS>(&tmem_empty[acc], lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg((const float4*)(p.ln_gamma + n) + j), b4 = __ldg((const float4*)(p.ln_beta + n) + j);
+            v[4 * j] = (v[4 * j] - mean) * rstd * g4.x + b4.x; v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+            v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z; v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+          }
+#pragma unroll 1
+          for (int pass = 0; pass < (p.ln_out2 ? 2 : 1); ++pass) {
+            if (pass == 1) {  // second output: + addend (this lane's own row, 128 contiguous bytes)
+              const float4* ap = (const float4*)(p.ln_addend + grow * p.ln_ld + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 a4 = row_ok ? __ldg(ap + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+              }
+            }
+            uint32_t o[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t h = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              const float l0 = v[2 * j] - __uint_as_float(h << 16), l1 = v[2 * j + 1] - __uint_as_float(h & 0xffff0000u);
+              o[j] = h;
+              o[16 + j] = pack_bf16x2(l0, l1);
+            }
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_s + ((c ^ sw) << 4)), "r"(o[4 * c]), "r"(o[4 * c + 1]),
+                           "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(pass == 0 ? &tmap_out : &tmap_out2, stg_s, n, ow, oh, zc);
+              bulk_commit();
+            }
+          }
+        }
+        if (lane == 0) bulk_wait_read0();  // the next tile's first residual box lands in the staging tile
+        __syncwarp();
+        continue;
+      }
       ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + hf * C::COLS_PER_WARP, r);
 #pragma unroll 1
       for (int ci = 0; ci < nch; ++ci) {
@@ -747,12 +874,12 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     if (splits > splitk_cap) splits = splitk_cap;
     if (splits < 1) splits = 1;
   }
-  if (WS) splits = 1;
+  if (WS || ep.ln_gamma != nullptr) splits = 1;  // (the LayerNorm epilogue needs the complete row sums in one tile)
   const int kbps = cdiv(k_blocks, splits);
   splits = cdiv(k_blocks, kbps);
   p.splits = splits; p.kb_per_split = kbps;
 
-  CUtensorMap ta, tw, to, tr;
+  CUtensorMap ta, tw, to, tr, to2;
   int rc;
   if (conv) {
     const unsigned long long pix = 4ull * a.C;  // bytes per pixel
@@ -776,6 +903,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
                           pitch * out_w, pitch * rows_per_b, 32, box_w, box_h), &to);
     if (rc != EGTR_OK) return rc;
     tr = to;
+    to2 = to;
     p.ncols = Npad;
   } else {
     const unsigned long long bstride = ep.rows_per_b > 0 ? (unsigned long long)ep.bstride : (unsigned long long)rows_per_b;
@@ -794,6 +922,21 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
       p.has_res = 1;
       p.res_fmt = ep.res_fmt;
     }
+    to2 = to;
+    if (ep.ln_gamma != nullptr) {
+      p.ln = 1;
+      p.ln_gamma = ep.ln_gamma;
+      p.ln_beta = ep.ln_beta;
+      p.ln_ld = ep.ldo;
+      if (ep.ln_out2 != nullptr) {
+        const uint8_t* o2base = (const uint8_t*)ep.ln_out2 + 4ll * ep.off * ep.ldo;
+        rc = cached_map(desc4(o2base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, out_w, out_h, p.nb, opitch, opitch * out_w, opitch * bstride, 32,
+                              box_w, box_h), &to2);
+        if (rc != EGTR_OK) return rc;
+        p.ln_out2 = 1;
+        p.ln_addend = ep.ln_addend;
+      }
+    }
     p.bias = ep.bias;
     p.row_keep = conv ? nullptr : ep.row_keep;
     p.keep_bstride = (int)bstride;
@@ -810,7 +953,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
   const int slots = num_sms() / CTAS;
   const int grid = (work < slots ? work : slots) * CTAS;
-  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, WS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, p,
+  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, WS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, to2, p,
                        device_error_flag_p32()));
   if (splits > 1) {
     ReduceArgs r = {};
@@ -857,6 +1000,12 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
     if (c128 < c256) bn = 128;
   }
   if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
+  if (ep.ln_gamma != nullptr) {
+    EGTR_CHECK(N == 256 && a.mode == 0 && ep.ln_beta != nullptr && ep.out_fmt == EGTR_FMT_P32 && ep.row_keep == nullptr &&
+                   (!ep.ln_out2 || ep.ln_addend),
+               EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32): the LayerNorm epilogue needs N == 256, plain rows, P32 output");
+    bn = 256;  // the whole row in one tile
+  }
   // CTA pairs (cta_group::2) for every 128/256-wide tile shape with at least two m-tiles: measured through the whole forward,
   // pairs everywhere beat both 1-CTA tiles and a size threshold (less L2->SM weight traffic, one more pipeline stage)
   static const int forced_ctas = [] { const char* e = getenv("EGTR_GEMM_CTAS"); return e ? atoi(e) : 0; }();  // dev experiments only

@@ -294,7 +294,8 @@ class Engine:
              a_col: int = 0, a2: Optional[torch.Tensor] = None, conv: Optional[dict] = None, relu: bool = False,
              res: Optional[torch.Tensor] = None, ldr: int = 0, ldo: Optional[int] = None, out_col: int = 0,
              remap: Optional[Tuple[int, int, int]] = None, row_keep: Optional[torch.Tensor] = None,
-             a_fmt: int = 0, out_fmt: int = 0, res_fmt: int = 0):
+             a_fmt: int = 0, out_fmt: int = 0, res_fmt: int = 0, ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+             ln_out2: Optional[torch.Tensor] = None, ln_addend: Optional[torch.Tensor] = None):
         """`a_fmt`/`out_fmt`/`res_fmt` = 1: the tensor is stored as P32 rows (include/egtr_b200.h); a P32 operand takes the
         TMA-fed tcgen05 kernel (gemm_p32.cu)."""
         src = ASrc()
@@ -313,6 +314,10 @@ class Engine:
         ep.rows_per_b, ep.bstride, ep.off = remap if remap else (0, 0, 0)
         ep.row_keep = _ptr(row_keep)
         src.fmt, ep.out_fmt, ep.res_fmt = a_fmt, out_fmt, res_fmt
+        if ln is not None:  # LayerNorm(acc + bias + res) in the epilogue (P32 operand kernel, N == 256)
+            assert a_fmt == 1 and out_fmt == 1
+            ep.ln_gamma, ep.ln_beta = _ptr(ln[0]), _ptr(ln[1])
+            ep.ln_out2, ep.ln_addend = _ptr(ln_out2), _ptr(ln_addend)
         if a_fmt == 1:
             assert a2 is None
             with self.span("gemm_p32"), self.span(f"gemm_p32:{M}x{lin.N}x{lin.K}" + (":conv" if conv is not None else "")):
@@ -545,7 +550,7 @@ class Engine:
             # Product path: every tensor that feeds a GEMM lives in HBM as P32 rows (split-bf16 at fp32 pitch), written by
             # the kernel that produces it; the GEMMs stream both operands with TMA.  x: layer input, xp: x + pos (operand of
             # the sampling_offsets / attention_weights projections, deformable_detr.py:1040), xc: post-attention LayerNorm.
-            x0, x, xp, xc, xb = ws["x"]
+            x0, x, xp, xc, _ = ws["x"]
             call("egtr_rows_to_p32", _ptr(x0), None, M, 256, 256, _ptr(x), st)
             call("egtr_rows_to_p32", _ptr(x0), _ptr(pos), M, 256, 256, _ptr(xp), st)
             enc_f32 = x0
@@ -556,16 +561,15 @@ class Engine:
                 with self.span("msda_enc"):
                     call("egtr_msda_fused_fwd_ex", _ptr(value), 256, ws["shapes_c"], _ptr(offaw), 384, None, _ptr(vr), 1,
                          B, S, 8, 32, Lv, S, 4, _ptr(attn), 1, st)
-                self.gemm(lay["out"], M, xb, a=attn, lda=256, a_fmt=1)
-                # residual adds ride in the LayerNorm kernels (same bytes as a GEMM-epilogue residual, one less format)
-                call("egtr_add_layernorm_p32", _ptr(xb), _ptr(x), 1, _ptr(lay["ln1"][0]), _ptr(lay["ln1"][1]), M, 256,
-                     _ptr(xc), None, None, None, st)
+                # output_proj + residual + LayerNorm and fc2 + residual + LayerNorm are ONE kernel each: the GEMM's epilogue
+                # normalises its 256-wide rows in TMEM and writes P32 rows (and, for the layer output, x + pos as well)
+                self.gemm(lay["out"], M, xc, a=attn, lda=256, a_fmt=1, res=x, res_fmt=1, ldr=256, out_fmt=1, ln=lay["ln1"])
                 self.gemm(lay["fc1"], M, ffn, a=xc, lda=256, a_fmt=1, relu=True, out_fmt=1)
-                self.gemm(lay["fc2"], M, xb, a=ffn, lda=1024, a_fmt=1)
                 last = i == nl_enc - 1
-                want_f32 = last or (taps is not None and i == 0)
-                call("egtr_add_layernorm_p32", _ptr(xb), _ptr(xc), 1, _ptr(lay["ln2"][0]), _ptr(lay["ln2"][1]), M, 256,
-                     _ptr(x), _ptr(enc_f32) if want_f32 else None, None if last else _ptr(pos), None if last else _ptr(xp), st)
+                self.gemm(lay["fc2"], M, x, a=ffn, lda=1024, a_fmt=1, res=xc, res_fmt=1, ldr=256, out_fmt=1, ln=lay["ln2"],
+                          ln_out2=None if last else xp, ln_addend=None if last else pos)
+                if last or (taps is not None and i == 0):
+                    call("egtr_p32_to_rows", _ptr(x), M, 256, _ptr(enc_f32), 256, st)
                 if taps is not None and i == 0:
                     taps["enc0_out"] = enc_f32.view(B, S, 256).clone()
             enc_p32 = x

@@ -107,6 +107,13 @@ typedef struct {
   int k1;
   int out_fmt;          /* EGTR_FMT_F32 / EGTR_FMT_P32: storage of `out` (P32 needs N % 32 == 0) */
   int res_fmt;          /* storage of `res` */
+  /* LayerNorm epilogue (P32-operand kernel, N == 256 == one tile row): out = LayerNorm(acc + bias + res) * ln_gamma + ln_beta
+   * (eps 1e-5) — the Linear + residual + LayerNorm tail of an encoder sub-layer (deformable_detr.py:1325-1343) without the
+   * fp32 round trip; ln_out2 (optional, P32 rows, same pitch) receives out + ln_addend (the next layer's x + pos). */
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* ln_addend; /* fp32 rows [*, ldo] at the output row mapping */
+  void* ln_out2;
 } egtr_epilogue_t;
 
 /* fp32 weight [N,K] -> split-bf16 planes [2][Npad][K] (hi, lo; rows >= N zero). Npad % 64 == 0. */

@@ -225,3 +225,42 @@ def test_maxpool_p32_out(cuda):
     want = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(B * OH * OW, Cn)
     assert torch.equal(o_f, want)
     assert torch.equal(o_p.view(torch.int32), p32_encode(o_f.cpu()).to(cuda).view(torch.int32))
+
+
+@pytest.mark.parametrize("M,K", [(200, 256), (22223, 256), (5000, 1024), (129, 64)])
+@pytest.mark.parametrize("res_fmt", [None, 0, 1])
+@pytest.mark.parametrize("with_out2", [False, True])
+def test_gemm_p32_layernorm_epilogue(cuda, M, K, res_fmt, with_out2):
+    """Linear + residual + LayerNorm in the GEMM epilogue (encoder sub-layer tails) vs fp64 torch."""
+    from egtr_b200 import _lib
+    from egtr_b200._lib import ASrc, Epilogue
+    from egtr_b200.engine import Lin
+    g = torch.Generator().manual_seed(M + K + (res_fmt or 0) * 3 + int(with_out2))
+    a = p32_encode(torch.randn(M, K, generator=g)).to(cuda)
+    w = (torch.randn(256, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(256, generator=g).to(cuda)
+    gamma, beta = (1 + 0.2 * torch.randn(256, generator=g)).to(cuda), torch.randn(256, generator=g).to(cuda)
+    res = torch.randn(M, 256, generator=g)
+    res_dev = None if res_fmt is None else (p32_encode(res) if res_fmt else res).to(cuda)
+    res_val = 0 if res_fmt is None else (p32_decode(res_dev) if res_fmt else res_dev).double()
+    addend = torch.randn(M, 256, generator=g).to(cuda)
+    lin = Lin(w, b, cuda)
+    src, ep = ASrc(), Epilogue()
+    src.a, src.mode, src.lda, src.fmt = a.data_ptr(), 0, K, 1
+    out = torch.full((M, 256), float("nan"), device=cuda)
+    out2 = torch.full((M, 256), float("nan"), device=cuda)
+    ep.bias, ep.out, ep.ldo, ep.ldr, ep.out_fmt = lin.b.data_ptr(), out.data_ptr(), 256, 256, 1
+    if res_dev is not None:
+        ep.res, ep.res_fmt = res_dev.data_ptr(), res_fmt
+    ep.ln_gamma, ep.ln_beta = gamma.data_ptr(), beta.data_ptr()
+    if with_out2:
+        ep.ln_out2, ep.ln_addend = out2.data_ptr(), addend.data_ptr()
+    _lib.call("egtr_gemm_sbf16", C.byref(src), lin.planes.data_ptr(), M, 256, lin.Npad, K, C.byref(ep), _st())
+    torch.cuda.synchronize()
+    y = p32_decode(a).double() @ w.double().t() + b.double() + res_val
+    want = torch.nn.functional.layer_norm(y, (256,), gamma.double(), beta.double(), 1e-5)
+    assert relerr(p32_decode(out), want) < 3e-5
+    if with_out2:
+        assert relerr(p32_decode(out2), want + addend.double()) < 3e-5
+    else:
+        assert torch.isnan(out2).all()
