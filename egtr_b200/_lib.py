@@ -64,6 +64,7 @@ SIGNATURES = {
     "egtr_maxpool3x3s2_nhwc_f32": [_p, _i, _i, _i, _i, _p, _p],
     "egtr_maxpool3x3s2_nhwc_ex": [_p, _i, _i, _i, _i, _p, _i, _p],
     "egtr_groupnorm_f32": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "egtr_groupnorm_ex": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "egtr_groupnorm_scratch_doubles": [_i, _i],
     "egtr_levels_geometry_f32": [_p, _i, _i, _i, C.POINTER(_i), _i, _p, _p, _i, _p, _p, _p, _p, _p],
     "egtr_mha_core_f32": [_p, _i, _i, _i, _i, _i, _p, _p],

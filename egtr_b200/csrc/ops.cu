@@ -299,7 +299,8 @@ groupnorm_finalize_kernel(const double* __restrict__ part, int nchunks, int rows
 }
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int off, const float2* __restrict__ stats,
-                       const float* __restrict__ gamma, const float* __restrict__ beta) {
+                       const float* __restrict__ gamma, const float* __restrict__ beta, uint8_t* __restrict__ out_p32,
+                       const float* __restrict__ addend, uint8_t* __restrict__ out_plus_p32) {
   pdl_entry();
   const int b = blockIdx.y, chunk = blockIdx.x;
   __shared__ float mean_s[32], rstd_s[32];
@@ -319,6 +320,13 @@ groupnorm_apply_kernel(float* __restrict__ x, int rows_per_b, int bstride, int o
     v.x = (v.x - mean) * rstd * g.x + be.x; v.y = (v.y - mean) * rstd * g.y + be.y;
     v.z = (v.z - mean) * rstd * g.z + be.z; v.w = (v.w - mean) * rstd * g.w + be.w;
     *p = v;
+    const long long row = (long long)b * bstride + off + r;
+    if (out_p32) p32_store4(out_p32 + row * 1024, c * 4, v);  // the encoder's operands, written here instead of by a conversion pass
+    if (out_plus_p32) {
+      const float4 a = *((const float4*)(addend + row * 256) + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      p32_store4(out_plus_p32 + row * 1024, c * 4, v);
+    }
   }
 }
 
@@ -582,14 +590,22 @@ extern "C" int egtr_maxpool3x3s2_nhwc_ex(const float* x, int B, int H, int W, in
 
 extern "C" int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups,
                                   const float* gamma, const float* beta, double* scratch, egtr_stream_t s) {
-  EGTR_CHECK(x && gamma && beta && scratch && B > 0 && rows_per_b > 0, EGTR_ERR_ARG, "egtr_groupnorm_f32: bad arguments");
+  return egtr_groupnorm_ex(x, B, rows_per_b, bstride, off, C, groups, gamma, beta, scratch, nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int egtr_groupnorm_ex(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups, const float* gamma,
+                                 const float* beta, double* scratch, void* out_p32, const float* addend, void* out_plus_p32,
+                                 egtr_stream_t s) {
+  EGTR_CHECK(x && gamma && beta && scratch && B > 0 && rows_per_b > 0 && (!out_plus_p32 || addend), EGTR_ERR_ARG,
+             "egtr_groupnorm: bad arguments");
   EGTR_CHECK(C == 256 && groups == 32, EGTR_ERR_UNSUPPORTED, "egtr_groupnorm_f32: built for GroupNorm(32, 256)");
   dim3 grid(cdiv(rows_per_b, GN_ROWS), B);
   double* part = scratch + B * 32;  // first B*32 doubles hold the float2 (mean, rstd) table
   float2* stats = (float2*)scratch;
   launch_pdl(groupnorm_partial_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, x, rows_per_b, bstride, off, part);
   launch_pdl(groupnorm_finalize_kernel, dim3(dim3(32, B)), dim3(32), (size_t)(0), (cudaStream_t)s, part, grid.x, rows_per_b, stats);
-  launch_pdl(groupnorm_apply_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, x, rows_per_b, bstride, off, stats, gamma, beta);
+  launch_pdl(groupnorm_apply_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, x, rows_per_b, bstride, off, stats, gamma, beta,
+             (uint8_t*)out_p32, addend, (uint8_t*)out_plus_p32);
   count_launch();
   count_launch();
   count_launch();

@@ -503,7 +503,8 @@ class Engine:
                 lin, gw, gb = self.input_proj[lvl]
                 hw = h * w
                 self.gemm(lin, B * hw, ws["x"][0], a=x, lda=cin, ldo=256, remap=(hw, S, starts[lvl]), a_fmt=p32)
-                call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, hw, S, starts[lvl], 256, 32, _ptr(gw), _ptr(gb), _ptr(ws["gn_scratch"]), st)
+                call("egtr_groupnorm_ex", _ptr(ws["x"][0]), B, hw, S, starts[lvl], 256, 32, _ptr(gw), _ptr(gb), _ptr(ws["gn_scratch"]),
+                     _ptr(ws["x"][1]) if p32 else None, _ptr(ws["pos"]), _ptr(ws["x"][2]) if p32 else None, st)
                 if li == 4:  # extra level: 3x3/2 conv on C5
                     if Lv > 4:
                         raise _lib.EgtrError("more than 4 feature levels are not built")
@@ -511,7 +512,8 @@ class Engine:
                     oh2, ow2 = shapes[3]
                     self.gemm(lin2, B * oh2 * ow2, ws["x"][0], ldo=256, remap=(oh2 * ow2, S, starts[3]),
                               conv=dict(x=x, H=h, W=w, C=cin, OH=oh2, OW=ow2, KH=3, KW=3, stride=2, pad=1), a_fmt=p32)
-                    call("egtr_groupnorm_f32", _ptr(ws["x"][0]), B, oh2 * ow2, S, starts[3], 256, 32, _ptr(gw2), _ptr(gb2), _ptr(ws["gn_scratch"]), st)
+                    call("egtr_groupnorm_ex", _ptr(ws["x"][0]), B, oh2 * ow2, S, starts[3], 256, 32, _ptr(gw2), _ptr(gb2), _ptr(ws["gn_scratch"]),
+                         _ptr(ws["x"][1]) if p32 else None, _ptr(ws["pos"]), _ptr(ws["x"][2]) if p32 else None, st)
                 if taps is not None:
                     xf = x[: B * hw * cin]
                     if p32:
@@ -550,9 +552,7 @@ class Engine:
             # Product path: every tensor that feeds a GEMM lives in HBM as P32 rows (split-bf16 at fp32 pitch), written by
             # the kernel that produces it; the GEMMs stream both operands with TMA.  x: layer input, xp: x + pos (operand of
             # the sampling_offsets / attention_weights projections, deformable_detr.py:1040), xc: post-attention LayerNorm.
-            x0, x, xp, xc, _ = ws["x"]
-            call("egtr_rows_to_p32", _ptr(x0), None, M, 256, 256, _ptr(x), st)
-            call("egtr_rows_to_p32", _ptr(x0), _ptr(pos), M, 256, 256, _ptr(xp), st)
+            x0, x, xp, xc, _ = ws["x"]  # x / xp were written as P32 by the GroupNorm of each level
             enc_f32 = x0
             nl_enc = len(self.enc)
             for i, lay in enumerate(self.enc):

@@ -206,6 +206,11 @@ int egtr_maxpool3x3s2_nhwc_ex(const float* x, int B, int H, int W, int C, void* 
  * rows), C], eps 1e-5 (deformable_detr.py:1996). */
 int egtr_groupnorm_f32(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups,
                        const float* gamma, const float* beta, double* scratch, egtr_stream_t s);
+/* Same, additionally writing the normalised rows as P32 (out_p32) and rows + addend as P32 (out_plus_p32; the encoder's
+ * x + pos operand) at the same [B, bstride rows, C] mapping; either may be NULL. */
+int egtr_groupnorm_ex(float* x, int B, int rows_per_b, int bstride, int off, int C, int groups, const float* gamma,
+                      const float* beta, double* scratch, void* out_p32, const float* addend, void* out_plus_p32,
+                      egtr_stream_t s);
 /* doubles of scratch egtr_groupnorm_f32 needs for (B, rows_per_b). */
 long long egtr_groupnorm_scratch_doubles(int B, int rows_per_b);
 /* pixel_mask [B,H,W] int64 -> per-level nearest-neighbour masks (uint8 [B,S]), sine position

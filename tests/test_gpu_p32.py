@@ -264,3 +264,28 @@ def test_gemm_p32_layernorm_epilogue(cuda, M, K, res_fmt, with_out2):
         assert relerr(p32_decode(out2), want + addend.double()) < 3e-5
     else:
         assert torch.isnan(out2).all()
+
+
+def test_groupnorm_p32_outputs(cuda):
+    """GroupNorm of a level slice, with the encoder's P32 operands (x and x + pos) written by the same pass."""
+    from egtr_b200 import _lib
+    g = torch.Generator().manual_seed(13)
+    B, S, off, hw = 2, 500, 120, 301
+    x = torch.randn(B, S, 256, generator=g).to(cuda)
+    pos = torch.randn(B, S, 256, generator=g).to(cuda)
+    gamma, beta = torch.randn(256, generator=g).to(cuda), torch.randn(256, generator=g).to(cuda)
+    ref = x.clone()
+    n = int(_lib.call("egtr_groupnorm_scratch_doubles", B, hw))
+    scratch = torch.empty(n, dtype=torch.float64, device=cuda)
+    _lib.call("egtr_groupnorm_f32", ref.data_ptr(), B, hw, S, off, 256, 32, gamma.data_ptr(), beta.data_ptr(), scratch.data_ptr(), _st())
+    o_p = torch.full((B, S, 256), 3.0, device=cuda)
+    o_q = torch.full((B, S, 256), 3.0, device=cuda)
+    _lib.call("egtr_groupnorm_ex", x.data_ptr(), B, hw, S, off, 256, 32, gamma.data_ptr(), beta.data_ptr(), scratch.data_ptr(),
+              o_p.data_ptr(), pos.data_ptr(), o_q.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(x, ref)
+    sl = slice(off, off + hw)
+    assert torch.equal(o_p[:, sl].reshape(-1, 256).contiguous().view(torch.int32), p32_encode(ref[:, sl].reshape(-1, 256).cpu()).to(cuda).view(torch.int32))
+    assert torch.equal(o_q[:, sl].reshape(-1, 256).contiguous().view(torch.int32),
+                       p32_encode((ref[:, sl] + pos[:, sl]).reshape(-1, 256).cpu()).to(cuda).view(torch.int32))
+    assert (o_p[:, :off] == 3.0).all() and (o_p[:, off + hw:] == 3.0).all()
