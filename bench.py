@@ -192,7 +192,8 @@ def main():
     px_d = [torch.roll(px, shifts=17 * i, dims=3).to(dev) for i in range(NIMG)]
     mask_d = mask.to(dev)
     in_bytes = NIMG * (px_d[0].numel() * 4 + mask_d.numel() * 8)
-    runners = [eng.graph_runner(Bl, H, W, slot=i) for i in range(conc)]
+    runners = [eng.graph_runner(Bl, H, W, slot=i, throughput=conc > 1) for i in range(conc)]
+    lone = eng.graph_runner(Bl, H, W, slot=0, throughput=False)  # latency configuration of a single forward (split-K on)
     streams = [torch.cuda.Stream() for _ in range(conc)]
     main = torch.cuda.current_stream()
 
@@ -215,7 +216,7 @@ def main():
         flush.fill_(1)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        runners[0](px_d[i % NIMG], mask_d)
+        lone(px_d[i % NIMG], mask_d)
         s1.record()
         torch.cuda.synchronize()
         lat.append(s0.elapsed_time(s1))
@@ -279,22 +280,20 @@ def main():
     # per-kernel probes and the launch count need eager launches: one extra untimed eager pass per step count
     model.use_cuda_graph = False
     # kernels per step in the timed (throughput) configuration = launches of one eager forward with the same settings
-    step_e2e()
+    eng.forward(px_d[0], mask_d, throughput=conc > 1)
     torch.cuda.synchronize()
     _lib.call("egtr_launch_count_reset")
-    step_e2e()
+    eng.forward(px_d[0], mask_d, throughput=conc > 1)
     torch.cuda.synchronize()
     launches = int(_lib.call("egtr_launch_count"))
     eng.probe = {}
     eng.probe_flops = {}
-    # the probes time ONE forward's launches back to back (nothing else on the GPU): use the single-forward configuration
-    # (split-K on), not the throughput one in which few-CTA launches rely on other images to fill the SMs
-    _lib.call("egtr_set_splitk_max", 64)
+    # the probes time ONE forward's launches back to back (nothing else on the GPU): the eager model API runs the
+    # single-forward configuration (split-K on), not the throughput one in which few-CTA launches rely on other images
     for _ in range(args.steps):
         torch.cuda._sleep(int(2e7))  # ~10 ms head start for the host: the probe events then bracket GPU execution, not launch gaps
         step_e2e()
     torch.cuda.synchronize()
-    _lib.call("egtr_set_splitk_max", 1)
     probe, eng.probe = eng.probe, None
     clocks = sampler.stop() if rank == 0 else None
 
@@ -350,7 +349,7 @@ def main():
                       "avg_launch_us": 1e6 * tl / n_l, "algorithmic_flops_per_step": fl, "share_of_step_kernel_time": tl / sum(v for k, v in spans.items() if k.startswith("stage_")),
                       "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
                       "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
-                      "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3; launches timed one forward at a time with split-K on (egtr_set_splitk_max 64)"}
+                      "note": "fp32-parity products = 3 bf16 MMAs each (hi*hi + hi*lo + lo*hi): frac is capped at 1/3; launches timed one forward at a time in the single-forward configuration (split-K on)"}
         if os.environ.get("EGTR_BENCH_SHAPES"):  # dev: per-shape GEMM table (warm, in-pipeline timings) on stderr
             for k in sorted((k for k in spans if k.startswith("gemm_p32:")), key=lambda k: -spans[k]):
                 m_, n_, k_ = [int(v) for v in k.split(":")[1].split("x")]

@@ -49,8 +49,15 @@ struct MsdaArgs {
 
 // QPB queries per CTA, 8 threads each: 32 for the encoder's 8x4 pixel patches, 8 for the decoder's few hundred queries
 // (25 x 8 CTAs instead of 7 x 8, and half as many dependent gather batches per thread).
+#ifndef EGTR_MSDA_MINB   // dev A/B knobs: resident CTAs per SM and samples in flight per thread of the 32-query form
+#define EGTR_MSDA_MINB 6
+#endif
+#ifndef EGTR_MSDA_UNROLL
+#define EGTR_MSDA_UNROLL 4
+#endif
+constexpr int kMsdaUnroll = EGTR_MSDA_UNROLL;
 template <bool FUSED, int QPB>
-__global__ void __launch_bounds__(QPB * 8, QPB == 32 ? 6 : 8)
+__global__ void __launch_bounds__(QPB * 8, QPB == 32 ? EGTR_MSDA_MINB : 8)
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   pdl_entry();
   __shared__ float slots[QPB * Q_STRIDE];
@@ -183,7 +190,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   const float* vbase = a.value + (long long)b * a.S * a.ld_value + m * 32 + c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* myslots = &slots[g * Q_STRIDE];
-#pragma unroll (QPB == 32 ? 4 : 8)
+#pragma unroll (QPB == 32 ? kMsdaUnroll : 8)
   for (int ss = 0; ss < 16; ++ss) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);

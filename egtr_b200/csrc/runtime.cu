@@ -35,14 +35,14 @@ int num_sms() {
 static thread_local int g_scratch_slot = 0;
 int scratch_slot() { return g_scratch_slot; }
 
-// Upper bound on split-K factors of the tensor-core GEMMs.  Default 1: with several forwards in flight (the serving mode) idle
-// SMs are filled by other images and the partial-sum round trip is pure cost; a latency-bound single forward wants 64.
+// Upper bound on split-K factors of the tensor-core GEMMs.  Default 64 (a lone forward is latency-bound); the engine sets 1 for
+// forwards that run several in flight (serving): idle SMs are filled by other images and the partial-sum round trip is pure cost.
 static std::atomic<int> g_splitk_max{-1};
 int splitk_max() {
   int v = g_splitk_max.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("EGTR_GEMM_SPLITK_MAX");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 64;
     if (v < 1) v = 1;
     g_splitk_max.store(v);
   }

@@ -281,12 +281,12 @@ class Engine:
         torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------ CUDA-graph replay
-    def graph_runner(self, B: int, H: int, W: int, slot: int = 0) -> "GraphRunner":
+    def graph_runner(self, B: int, H: int, W: int, slot: int = 0, throughput: bool = False) -> "GraphRunner":
         """The ~330 launches of one forward captured once per input shape and replayed as one graph:
         the host-side launch sequence disappears from the step time (batch 1 is launch-bound otherwise)."""
-        key = ("graph", B, H, W, slot)
+        key = ("graph", B, H, W, slot, throughput)
         if key not in self._ws:
-            self._ws[key] = GraphRunner(self, B, H, W, slot)
+            self._ws[key] = GraphRunner(self, B, H, W, slot, throughput)
         return self._ws[key]
 
     # ------------------------------------------------------------------ launch helpers
@@ -434,16 +434,19 @@ class Engine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None, taps: Optional[dict] = None,
-                slot: int = 0) -> Dict[str, torch.Tensor]:
+                slot: int = 0, throughput: bool = False) -> Dict[str, torch.Tensor]:
+        """`throughput`: this forward is one of several in flight (serving): few-tile GEMMs then skip split-K — other images
+        fill the SMs and the partial-sum round trip is pure cost.  A lone forward (the default) uses split-K for latency."""
         cfg, dev = self.cfg, self.device
         if pixel_values.device != dev:
             raise _lib.EgtrError(f"pixel_values on {pixel_values.device}, model on {dev}")
         with torch.cuda.device(dev):
-            return self._forward(pixel_values, pixel_mask, taps, slot)
+            return self._forward(pixel_values, pixel_mask, taps, slot, throughput)
 
-    def _forward(self, pixel_values, pixel_mask, taps, slot: int = 0):
+    def _forward(self, pixel_values, pixel_mask, taps, slot: int = 0, throughput: bool = False):
         cfg, dev = self.cfg, self.device
         call("egtr_set_scratch_slot", slot)
+        call("egtr_set_splitk_max", 1 if throughput else 64)
         st = _stream()
         px = pixel_values.to(torch.float32).contiguous()
         B, Cin, H, W = px.shape
@@ -699,9 +702,10 @@ class GraphRunner:
     """Static-buffer CUDA graph of `Engine._forward` for one (B, H, W).  Outputs are the graph's own
     buffers and are overwritten by the next replay (callers that keep results must clone them)."""
 
-    def __init__(self, eng: Engine, B: int, H: int, W: int, slot: int = 0):
+    def __init__(self, eng: Engine, B: int, H: int, W: int, slot: int = 0, throughput: bool = False):
         self.eng = eng
         self.slot = slot
+        self.throughput = throughput
         dev = eng.device
         with torch.cuda.device(dev):
             self.px = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
@@ -710,13 +714,13 @@ class GraphRunner:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: one-time attribute calls, tensor-map cache, workspace allocation
-                    eng._forward(self.px, self.pm, None, slot)
+                    eng._forward(self.px, self.pm, None, slot, throughput)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             probe, eng.probe = eng.probe, None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = eng._forward(self.px, self.pm, None, slot)
+                self.out = eng._forward(self.px, self.pm, None, slot, throughput)
             eng.probe = probe
 
     def __call__(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None):

@@ -38,7 +38,8 @@ class PipelinedRunner:
             # one captured graph per slot: private static inputs and outputs; slots that share a compute stream replay
             # serially and share a workspace, slots on different compute streams get their own (they overlap in time)
             self.concurrency = max(1, min(concurrency, depth))
-            self.slots: List[GraphRunner] = [GraphRunner(eng, batch, height, width, slot=i % self.concurrency) for i in range(depth)]
+            self.slots: List[GraphRunner] = [GraphRunner(eng, batch, height, width, slot=i % self.concurrency, throughput=self.concurrency > 1)
+                                              for i in range(depth)]
             self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
             self.s_runs = [torch.cuda.Stream() for _ in range(self.concurrency)]
             self.ev_in = [torch.cuda.Event() for _ in range(depth)]

@@ -46,8 +46,8 @@ void egtr_launch_count_reset(void);
 /* Internal split-K scratch is kept per slot (0..7, thread-local selection, default 0): forwards that may execute
  * concurrently on different streams (e.g. two captured CUDA graphs) must be enqueued under different slots. */
 int egtr_set_scratch_slot(int slot);
-/* Upper bound (1..64, process-wide) on the split-K factor of the tensor-core GEMMs.  Default 1 (off): the throughput
- * configuration, where several forwards in flight fill the SMs; 64 minimises the latency of a single forward. */
+/* Upper bound (1..64, process-wide) on the split-K factor of the tensor-core GEMMs.  Default 64: minimises the latency of a
+ * single forward; 1 (off) is the throughput configuration, where several forwards in flight fill the SMs. */
 int egtr_set_splitk_max(int max_splits);
 
 /* ---------------------------------------------------------------- GEMM-class operators ---- */

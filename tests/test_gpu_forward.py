@@ -23,19 +23,17 @@ def _run(cfg, sd, px, mask, cuda):
     return model, out
 
 
-@pytest.mark.parametrize("splitk_max", [1, 64])  # 1: the library default (throughput serving); 64: latency configuration
+@pytest.mark.parametrize("throughput", [False, True])  # lone forward (split-K on) / one of several in flight (split-K off)
 @pytest.mark.parametrize("name", CASES)
-def test_forward_matches_reference_golden(cuda, name, splitk_max):
-    from egtr_b200 import _lib
+def test_forward_matches_reference_golden(cuda, name, throughput):
     ref, meta = load_golden(name)
     cfg, sd, px, mask = case_inputs(meta)
-    _lib.call("egtr_set_splitk_max", splitk_max)
-    try:
-        _, out = _run(cfg, sd, px, mask, cuda)
-    finally:
-        _lib.call("egtr_set_splitk_max", 1)
+    model, out = _run(cfg, sd, px, mask, cuda)
+    if throughput:
+        out = model.engine().forward(px.to(cuda), mask.to(cuda), throughput=True)
+        torch.cuda.synchronize()
     assert out["logits"].shape == (meta["batch"], cfg.num_queries, cfg.num_labels)
-    assert "pred_connectivity" in out and out.pred_rel.shape[-1] == cfg.num_rel_labels
+    assert "pred_connectivity" in out and out["pred_rel"].shape[-1] == cfg.num_rel_labels
     errs = compare_forward(out, ref)
     print(name, os.environ.get("EGTR_B200_GEMM", "tc"), {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
