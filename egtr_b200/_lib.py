@@ -73,6 +73,8 @@ SIGNATURES = {
     "egtr_triplets_scratch_bytes": [_i, _i, _i, _i, _i],
     "egtr_triplets_f32": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "egtr_argmax_rows_f32": [_p, _i, _i, _p, _p],
+    "egtr_resample_h_u8": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p],
+    "egtr_resample_v_normalize_f32": [_p, _i, _i, _i, _i, _p, _p, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _ll, _i, _p, _i, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {

@@ -258,6 +258,20 @@ int egtr_triplets_f32(const float* logits, const float* pred_rel, const float* p
                       int num_labels, int P, int single, int k, void* scratch, float* obj_scores, int* pred_classes,
                       int* rel_inds, float* rel_scores, egtr_stream_t s);
 
+/* ---------------------------------------------------------------- input staging */
+/* PIL-exact bilinear resampling of uint8 images on the device (Pillow src/libImaging/Resample.c, 8-bit path): `bounds`
+ * [out][2] = (first input index, taps) and `kk` [out][ksize] = taps in 22-bit fixed point, both DEVICE arrays built by the host
+ * (egtr_b200/preprocess.py, same arithmetic as Pillow's precompute_coeffs / normalize_coeffs_8bpc).
+ * Horizontal pass: src [H,W,C] -> dst [H,OW,C]. */
+int egtr_resample_h_u8(const uint8_t* src, int H, int W, int C, int OW, const int* bounds, const int* kk, int ksize,
+                       uint8_t* dst, egtr_stream_t s);
+/* Vertical pass + DetrFeatureExtractor's rescale / normalise ((x / 255 - mean) / std, fp32, IEEE divisions; mean3 / std3 are
+ * HOST arrays) written into a [3, *, row_stride] region of the zero-padded NCHW batch tensor (plane_stride floats between
+ * channels); also sets pixel_mask (int64, 1 = real pixel) over the [OH, W] region when mask is non-NULL. */
+int egtr_resample_v_normalize_f32(const uint8_t* src, int H, int W, int C, int OH, const int* bounds, const int* kk,
+                                  int ksize, const float* mean3, const float* std3, float* dst, long long plane_stride,
+                                  int row_stride, int64_t* mask, int mask_row_stride, egtr_stream_t s);
+
 /* out[r] = argmax over x[r, :cols], first maximum wins (torch.argmax; model/egtr.py:406). */
 int egtr_argmax_rows_f32(const float* x, int cols, int rows, int* out, egtr_stream_t s);
 
