@@ -45,6 +45,7 @@ SIGNATURES = {
     "egtr_launch_count_reset": [],
     "egtr_set_scratch_slot": [_i],
     "egtr_set_splitk_max": [_i],
+    "egtr_set_grid_div": [_i],
     "egtr_split_weight_bf16": [_p, _i, _i, _i, _p, _p],
     "egtr_gemm_sbf16": [C.POINTER(ASrc), _p, _i, _i, _i, _i, C.POINTER(Epilogue), _p],
     "egtr_gemm_sbf16_grouped": [_p, _p, _p, C.POINTER(_i), _i, C.POINTER(_i), _p, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _p],

@@ -33,6 +33,7 @@ void set_last_error(const char* fmt, ...);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
 int splitk_max();  // runtime.cu: egtr_set_splitk_max / EGTR_GEMM_SPLITK_MAX
+int grid_div();    // runtime.cu: egtr_set_grid_div / EGTR_GEMM_GRID_DIV
 int pdl_mode();  // 0 off, 1 every launch, 2 only grids of at least one CTA per SM
 
 // Every kernel of the library is launched with programmatic dependent launch (PDL): the next kernel's CTAs may become

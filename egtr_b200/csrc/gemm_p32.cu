@@ -765,9 +765,11 @@ int cached_map(const MapDesc& d, CUtensorMap* out) {
   cuuint32_t box[4] = {d.box[0], d.box[1], d.box[2], d.box[3]};
   cuuint32_t estr[4] = {d.estr[0], d.estr[1], d.estr[2], d.estr[3]};
   CUtensorMap m;
+  static const int l2promo = [] { const char* e = getenv("EGTR_TMA_L2PROMO"); return e ? atoi(e) : 3; }();  // dev: 0 none, 1 64B, 2 128B, 3 256B
+  const CUtensorMapL2promotion promo = l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(&m, (CUtensorMapDataType)d.dtype, (cuuint32_t)d.rank, const_cast<void*>(d.ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA,
              "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u)",
              (int)r, d.rank, d.dim[0], d.dim[1], d.dim[2], d.dim[3], d.stride[0], d.stride[1], d.stride[2], d.box[0], d.box[1],
@@ -811,8 +813,8 @@ int* device_error_flag_p32() {
 }
 
 float* partial_buffer_p32(size_t floats) {  // grow-only per scratch slot; older buffers stay alive for captured graphs
-  static float* buf[8] = {};
-  static size_t cap[8] = {};
+  static float* buf[32] = {};
+  static size_t cap[32] = {};
   const int slot = scratch_slot();
   if (floats > cap[slot]) {
     float* nb = nullptr;
@@ -951,7 +953,10 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     attr_set = true;
   }
   const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
-  const int slots = num_sms() / CTAS;
+  // throughput mode (egtr_set_grid_div): the persistent grid takes 1/div of the GPU, so that GEMMs of the other forwards in
+  // flight run beside it on disjoint SMs instead of time-slicing the whole machine
+  int slots = num_sms() / CTAS / grid_div();
+  if (slots < 1) slots = 1;
   const int grid = (work < slots ? work : slots) * CTAS;
   EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, WS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, to2, p,
                        device_error_flag_p32()));
@@ -995,7 +1000,7 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
   if (bn == 256) {
     // wave quantisation: a persistent grid of 74 CTA pairs runs ceil(items / 74) rounds of (bn + fixed) cost each; 87 pair
     // items of 256 columns (the encoder's 22 223 tokens, N = 256) take two rounds, 174 items of 128 columns take three halves
-    const long long pairs_m = cdiv(cdiv(M, BLOCK_M), 2), slots = num_sms() / 2;
+    const long long pairs_m = cdiv(cdiv(M, BLOCK_M), 2), slots = num_sms() / 2 / grid_div() > 0 ? num_sms() / 2 / grid_div() : 1;
     const long long c256 = cdiv(pairs_m * (N / 256), slots) * (256 + 32), c128 = cdiv(pairs_m * (N / 128), slots) * (128 + 32);
     if (c128 < c256) bn = 128;
   }

@@ -708,8 +708,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
 
 // grow-only scratch for split-K partial sums (allocated outside graph capture, during warm-up)
 float* partial_buffer(size_t floats) {  // grow-only per scratch slot; older buffers stay alive for captured graphs
-  static float* buf[8] = {};
-  static size_t cap[8] = {};
+  static float* buf[32] = {};
+  static size_t cap[32] = {};
   const int slot = scratch_slot();
   if (floats > cap[slot]) {
     float* nb = nullptr;
@@ -754,7 +754,8 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
     EGTR_CHECK(partial != nullptr, EGTR_ERR_CUDA, "split-K scratch allocation failed");
   }
   const int work = tiles * splits;
-  const int grid = work < num_sms() ? work : num_sms();
+  const int cap = num_sms() / grid_div() > 0 ? num_sms() / grid_div() : 1;  // throughput mode: a share of the GPU per GEMM
+  const int grid = work < cap ? work : cap;
   launch_pdl(gemm_sbf16_kernel<BLOCK_N, MODE, REL>, dim3(grid), dim3(NUM_THREADS), (size_t)(C::SMEM_BYTES), st, tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {

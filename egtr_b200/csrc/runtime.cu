@@ -49,6 +49,20 @@ int splitk_max() {
   return v;
 }
 
+// Persistent GEMM grids are capped at num_sms / grid_div: with several forwards in flight, GEMMs of different images then run
+// side by side on disjoint SMs (better wave quantisation, prologues and tails overlap) instead of time-slicing the whole GPU.
+static std::atomic<int> g_grid_div{-1};
+int grid_div() {
+  int v = g_grid_div.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("EGTR_GEMM_GRID_DIV");
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+    g_grid_div.store(v);
+  }
+  return v;
+}
+
 int pdl_mode() {
   static const int mode = [] { const char* e = getenv("EGTR_B200_PDL"); return e ? atoi(e) : 2; }();
   return mode;
@@ -57,8 +71,13 @@ int pdl_mode() {
 }  // namespace egtr
 
 extern "C" int egtr_set_scratch_slot(int slot) {
-  EGTR_CHECK(slot >= 0 && slot < 8, EGTR_ERR_ARG, "egtr_set_scratch_slot: slot %d outside 0..7", slot);
+  EGTR_CHECK(slot >= 0 && slot < 32, EGTR_ERR_ARG, "egtr_set_scratch_slot: slot %d outside 0..31", slot);
   egtr::g_scratch_slot = slot;
+  return EGTR_OK;
+}
+extern "C" int egtr_set_grid_div(int div) {
+  EGTR_CHECK(div >= 1 && div <= 16, EGTR_ERR_ARG, "egtr_set_grid_div: %d outside 1..16", div);
+  egtr::g_grid_div.store(div);
   return EGTR_OK;
 }
 extern "C" int egtr_set_splitk_max(int max_splits) {

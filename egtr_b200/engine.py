@@ -130,6 +130,8 @@ class Engine:
                 and c.activation_function == "relu"):
             raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
         self._ws: Dict[tuple, dict] = {}
+        # forwards in flight (serving): each persistent GEMM takes half of the SMs, so GEMMs of different images run side by side
+        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "2"))
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
@@ -447,6 +449,7 @@ class Engine:
         cfg, dev = self.cfg, self.device
         call("egtr_set_scratch_slot", slot)
         call("egtr_set_splitk_max", 1 if throughput else 64)
+        call("egtr_set_grid_div", self.throughput_grid_div if throughput else 1)
         st = _stream()
         px = pixel_values.to(torch.float32).contiguous()
         B, Cin, H, W = px.shape

@@ -43,12 +43,15 @@ int egtr_abi_version(void);
 long long egtr_launch_count(void);
 void egtr_launch_count_reset(void);
 
-/* Internal split-K scratch is kept per slot (0..7, thread-local selection, default 0): forwards that may execute
+/* Internal split-K scratch is kept per slot (0..31, thread-local selection, default 0): forwards that may execute
  * concurrently on different streams (e.g. two captured CUDA graphs) must be enqueued under different slots. */
 int egtr_set_scratch_slot(int slot);
 /* Upper bound (1..64, process-wide) on the split-K factor of the tensor-core GEMMs.  Default 64: minimises the latency of a
  * single forward; 1 (off) is the throughput configuration, where several forwards in flight fill the SMs. */
 int egtr_set_splitk_max(int max_splits);
+/* Persistent GEMM grids use num_sms / div SMs (1..16, process-wide, default 1).  Throughput configuration: several forwards
+ * in flight with div > 1 run their GEMMs side by side on disjoint SMs instead of time-slicing the whole GPU. */
+int egtr_set_grid_div(int div);
 
 /* ---------------------------------------------------------------- GEMM-class operators ---- */
 /* Left-operand source: rows of 64-float runs.  mode 0: row m = a + m*lda (+ a2 + m*lda when a2
