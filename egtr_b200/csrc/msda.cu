@@ -22,7 +22,7 @@ void count_launch();
 namespace {
 
 constexpr int MAX_L = 8;
-constexpr int SLOT_WORDS = 8;                      // 4 token indices + 4 weights
+constexpr int SLOT_WORDS = 8;                      // 4 corner offsets (elements, token * row stride) + 4 weights
 constexpr int Q_STRIDE = 16 * SLOT_WORDS + 8;      // words per query, padded against bank conflicts
 
 struct Levels {
@@ -170,12 +170,15 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
         const int hl = (int)floorf(him), wl = (int)floorf(wim);
         const float lh = him - (float)hl, lw = wim - (float)wl;
         const float hh = 1.f - lh, hw = 1.f - lw;
-        const int base_tok = lvS[l] + hl * W + wl;
+        // corners are stored as 32-bit ELEMENT offsets into this image's value rows (token * row stride; the host entry points
+        // guarantee S * ld_value < 2^31), so phase 2 forms each gather address with one IMAD.WIDE instead of a 64-bit multiply
+        const int ld = a.ld_value;
+        const int base_off = (lvS[l] + hl * W + wl) * ld;
         const bool y0 = hl >= 0, y1 = hl + 1 <= H - 1, x0 = wl >= 0, x1 = wl + 1 <= W - 1;
-        if (y0 && x0) { idx[0] = base_tok;         cw[0] = hh * hw * wgt; }
-        if (y0 && x1) { idx[1] = base_tok + 1;     cw[1] = hh * lw * wgt; }
-        if (y1 && x0) { idx[2] = base_tok + W;     cw[2] = lh * hw * wgt; }
-        if (y1 && x1) { idx[3] = base_tok + W + 1; cw[3] = lh * lw * wgt; }
+        if (y0 && x0) { idx[0] = base_off;               cw[0] = hh * hw * wgt; }
+        if (y0 && x1) { idx[1] = base_off + ld;          cw[1] = hh * lw * wgt; }
+        if (y1 && x0) { idx[2] = base_off + W * ld;      cw[2] = lh * hw * wgt; }
+        if (y1 && x1) { idx[3] = base_off + W * ld + ld; cw[3] = lh * lw * wgt; }
       }
     }
     *(int4*)slot = make_int4(idx[0], idx[1], idx[2], idx[3]);
@@ -188,6 +191,10 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   const int q = q_of[g];
   if (q < 0) return;
   const float* vbase = a.value + (long long)b * a.S * a.ld_value + m * 32 + c4;
+  // keep the per-thread base opaque in one register pair: address = IMAD.WIDE.U32(offset, 4, base), one instruction per gather
+  // (left to itself the compiler re-associates base = uniform pointer + 64-bit element offset: four instructions per address)
+  unsigned long long vb;
+  asm("mov.b64 %0, %1;" : "=l"(vb) : "l"(vbase));
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* myslots = &slots[g * Q_STRIDE];
 #pragma unroll (QPB == 32 ? kMsdaUnroll : 8)
@@ -195,10 +202,10 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-    if (FUSED || id.x >= 0) v0 = __ldg((const float4*)(vbase + (long long)id.x * a.ld_value));
-    if (FUSED || id.y >= 0) v1 = __ldg((const float4*)(vbase + (long long)id.y * a.ld_value));
-    if (FUSED || id.z >= 0) v2 = __ldg((const float4*)(vbase + (long long)id.z * a.ld_value));
-    if (FUSED || id.w >= 0) v3 = __ldg((const float4*)(vbase + (long long)id.w * a.ld_value));
+    if (FUSED || id.x >= 0) v0 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.x * 4ull));
+    if (FUSED || id.y >= 0) v1 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.y * 4ull));
+    if (FUSED || id.z >= 0) v2 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.z * 4ull));
+    if (FUSED || id.w >= 0) v3 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.w * 4ull));
     acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y); acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
     acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y); acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
     acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
@@ -286,6 +293,7 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   EGTR_CHECK(ld_value % 4 == 0 && ld_value >= M * D && ld_offaw >= M * L * P * 3 && ld_offaw % 2 == 0, EGTR_ERR_ARG,
              "egtr_msda_fused_fwd_f32: bad leading dimensions");
   EGTR_CHECK(B <= 65535 && M <= 65535, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: grid limits");
+  EGTR_CHECK((long long)S * ld_value < (1LL << 31), EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: S*ld_value must be < 2^31");
   Levels lv = {};
   int S_chk = 0;
   const int patches = fill_levels(shapes_hw, L, &lv, &S_chk);

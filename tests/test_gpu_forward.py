@@ -153,3 +153,47 @@ def test_forward_other_label_spaces_vs_live_oracle(cuda, wl, hw, batch):
     errs = compare_forward(out, want)
     print(wl, {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
+
+
+FULL = {  # BASELINE.json configs at their full per-GPU size: (workload, per-GPU batch, smaller image of the ragged batch)
+    "B": ("B", 1, None),                 # configs[1]: VG, batch 1
+    "C": ("B", 4, (736, 1216)),          # configs[2]: VG, 32 images over 8 GPUs
+    "D": ("D", 4, (768, 1024)),          # configs[3]: Open Images label space, 16 images over 4 GPUs
+    "E": ("E", 8, (960, 992)),           # configs[4]: stress, N_q=300 / 200 predicates, 64 images over 8 GPUs
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_forward_full_size_configs(cuda, name):
+    """Full-size parity.  One image of the batch (the ragged one, so pixel_mask has zeros) is checked against the live CPU oracle;
+    the rest of the batch through the size-independent property the domain offers — images are independent units,
+    so a batched forward must reproduce the forward of each image alone (same padded tensor, same mask)."""
+    from egtr_b200.config import WORKLOADS, workload_config
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from oracle import egtr_oracle as orc
+    from tests.util import relerr
+    wl, batch, small = FULL[name]
+    cfg = workload_config(wl)
+    H, W = WORKLOADS[wl]["image"]
+    sd = synth_state_dict(cfg, 60)
+    pad = None if small is None else [(H, W)] * (batch - 1) + [small]
+    px, mask = synth_images(batch, H, W, seed=61, pad_to=pad)
+    model, out = _run(cfg, sd, px, mask, cuda)
+    keys = ("logits", "pred_boxes", "pred_rel", "pred_connectivity")
+    for k in keys:
+        assert torch.isfinite(out[k]).all(), k
+    assert out["pred_rel"].shape == (batch, cfg.num_queries, cfg.num_queries, cfg.num_rel_labels)
+    assert float(out["pred_rel"].min()) >= 0.0 and float(out["pred_rel"].max()) <= 1.0
+    last = batch - 1
+    want = orc.forward(sd, cfg, px[last:], mask[last:])
+    errs = {k: relerr(out[k][last:], want[k]) for k in keys}
+    print(name, "vs oracle", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    if batch > 1:
+        for b in sorted({0, last}):
+            alone = model(pixel_values=px[b:b + 1].to(cuda), pixel_mask=mask[b:b + 1].to(cuda), output_attentions=False,
+                          output_attention_states=True, output_hidden_states=True)
+            torch.cuda.synchronize()
+            inv = {k: relerr(out[k][b:b + 1], alone[k]) for k in keys}
+            print(name, f"image {b} batched vs alone", {k: f"{v:.2e}" for k, v in inv.items()})
+            assert max(inv.values()) < TOL / 10, (b, inv)

@@ -1,5 +1,5 @@
 #!/bin/bash
-for v in "" m5u4 m4u8 m3u16 m8u2; do
+for v in "" m5u4 m4u8 m3u16 m8u4; do
   if [ -n "$v" ]; then export EGTR_B200_LIB=$PWD/egtr_b200/csrc/libvar_$v.so; else unset EGTR_B200_LIB; fi
   echo "=== ${v:-default m6u4}"; timeout 600 python bench.py --cpu-sample 0 --steps 10 2>/dev/null | python -c "
 import json,sys
