@@ -56,8 +56,11 @@ struct MsdaArgs {
 #define EGTR_MSDA_UNROLL 4
 #endif
 constexpr int kMsdaUnroll = EGTR_MSDA_UNROLL;
+#ifndef EGTR_MSDA_ENC_QPB  // encoder patch: 32 = 8x4 pixels (256 threads), 64 = 8x8 pixels (512 threads)
+#define EGTR_MSDA_ENC_QPB 32
+#endif
 template <bool FUSED, int QPB>
-__global__ void __launch_bounds__(QPB * 8, QPB == 32 ? EGTR_MSDA_MINB : 8)
+__global__ void __launch_bounds__(QPB * 8, QPB == 32 ? EGTR_MSDA_MINB : (QPB == 64 ? EGTR_MSDA_MINB / 2 : 8))
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   pdl_entry();
   __shared__ float slots[QPB * Q_STRIDE];
@@ -85,7 +88,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       while (l + 1 < L && (int)blockIdx.x >= lv_in.patch_start[l + 1]) ++l;
       const int pid = blockIdx.x - lv_in.patch_start[l];
       const int py = pid / lv_in.patches_x[l], px = pid - py * lv_in.patches_x[l];
-      const int y = py * 4 + (tid >> 3), x = px * 8 + (tid & 7);
+      const int y = py * (QPB / 8) + (tid >> 3), x = px * 8 + (tid & 7);
       if (y < lv_in.H[l] && x < lv_in.W[l]) {
         q = lv_in.start[l] + y * lv_in.W[l] + x;
         // deformable_detr.py:1642-1644: linspace(0.5, n-0.5, n)[i] / (valid_ratio * n); the per-level
@@ -197,7 +200,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   asm("mov.b64 %0, %1;" : "=l"(vb) : "l"(vbase));
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* myslots = &slots[g * Q_STRIDE];
-#pragma unroll (QPB == 32 ? kMsdaUnroll : 8)
+#pragma unroll (QPB >= 32 ? kMsdaUnroll : 8)
   for (int ss = 0; ss < 16; ++ss) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
@@ -228,7 +231,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   }
 }
 
-int fill_levels(const int* shapes_hw, int L, Levels* lv, int* S_out) {
+int fill_levels(const int* shapes_hw, int L, Levels* lv, int* S_out, int patch_h = 4) {
   lv->L = L;
   int start = 0, pstart = 0;
   for (int l = 0; l < L; ++l) {
@@ -238,7 +241,7 @@ int fill_levels(const int* shapes_hw, int L, Levels* lv, int* S_out) {
     start += lv->H[l] * lv->W[l];
     lv->patch_start[l] = pstart;
     lv->patches_x[l] = (lv->W[l] + 7) / 8;
-    pstart += lv->patches_x[l] * ((lv->H[l] + 3) / 4);
+    pstart += lv->patches_x[l] * ((lv->H[l] + patch_h - 1) / patch_h);
   }
   lv->patch_start[L] = pstart;
   *S_out = start;
@@ -296,7 +299,8 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   EGTR_CHECK((long long)S * ld_value < (1LL << 31), EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: S*ld_value must be < 2^31");
   Levels lv = {};
   int S_chk = 0;
-  const int patches = fill_levels(shapes_hw, L, &lv, &S_chk);
+  constexpr int kEncQ = EGTR_MSDA_ENC_QPB;
+  const int patches = fill_levels(shapes_hw, L, &lv, &S_chk, kEncQ / 8);
   EGTR_CHECK(S_chk == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: sum(H*W)=%d != S=%d", S_chk, S);
   EGTR_CHECK(!enc_ref || Lq == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_f32: encoder form needs Lq == S");
   MsdaArgs a = {};
@@ -307,8 +311,11 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   if (!enc_ref && (long long)Lq * B <= 4096) {  // decoder-sized query sets: small CTAs for parallelism and latency
     dim3 grid(cdiv(Lq, 8), M, B);
     launch_pdl(msda_kernel<true, 8>, dim3(grid), dim3(64), (size_t)(0), (cudaStream_t)s, a, lv);
+  } else if (enc_ref) {
+    dim3 grid(patches, M, B);
+    launch_pdl(msda_kernel<true, kEncQ>, dim3(grid), dim3(kEncQ * 8), (size_t)(0), (cudaStream_t)s, a, lv);
   } else {
-    dim3 grid(enc_ref ? patches : cdiv(Lq, 32), M, B);
+    dim3 grid(cdiv(Lq, 32), M, B);
     launch_pdl(msda_kernel<true, 32>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
   }
   count_launch();
