@@ -12,7 +12,7 @@
 // encoder queries (neighbouring pixels sample neighbouring tokens), or 32 consecutive decoder queries.
 //   phase 1: 256 threads = 16 (query) x 16 (sample) lanes: read the raw offsets/logits (fused form) or
 //            the precomputed locations/weights (drop-in form), softmax over the 16 samples with
-//            16-lane shuffles, turn each sample into 4 corner token indices + 4 combined weights in smem;
+//            16-lane shuffles, turn each sample into 4 corner offsets (32-bit elements) + 4 combined weights in smem;
 //   phase 2: 32 groups of 8 lanes: stream the 16 samples of one query, 4 LDG.128 each (unconditional in the fused form:
 //            absent corners carry weight 0 and point at token 0).
 #include "common.cuh"
