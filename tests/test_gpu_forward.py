@@ -9,7 +9,8 @@ from tests.util import TOL, case_inputs, compare_forward, load_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq", "forward_A"]
+CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq", "forward_A",
+         "forward_B", "forward_D_small_b2_ragged", "forward_E_small"]  # B: BASELINE.json configs[1] at full size, from the reference itself
 
 
 def _run(cfg, sd, px, mask, cuda):

@@ -5,7 +5,8 @@ import torch
 from oracle import egtr_oracle as orc
 from tests.util import case_inputs, compare_forward, load_golden, relerr
 
-FORWARD_CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq"]
+FORWARD_CASES = ["forward_tiny_b1", "forward_tiny_b2_ragged", "forward_small_b2_ragged_logitadj", "forward_small_nofreq",
+                 "forward_D_small_b2_ragged", "forward_E_small", "forward_B"]  # D / E: the Open-Images and stress label spaces (BASELINE.json configs 3, 4); B: configs[1] at full size
 
 
 @pytest.mark.parametrize("name", FORWARD_CASES)

@@ -29,7 +29,7 @@ def case_inputs(meta):
     from egtr_b200.synth import synth_images, synth_state_dict
 
     cfg = workload_config(meta["workload"], **meta["overrides"])
-    H, W = WORKLOADS[meta["workload"]]["image"]
+    H, W = meta.get("image") or WORKLOADS[meta["workload"]]["image"]
     sd = synth_state_dict(cfg, seed=meta["weight_seed"])
     pad = [tuple(p) for p in meta["pad_to"]] if meta["pad_to"] else None
     px, mask = synth_images(meta["batch"], H, W, seed=meta["image_seed"], pad_to=pad)
@@ -51,8 +51,8 @@ def compare_forward(out, ref, tol=TOL, argmax_guard=None):
         errs["pred_rel"] = relerr(rel, ref["pred_rel"])
     else:
         errs["pred_rel"] = relerr(rel[:, ::3, ::7, :], ref["pred_rel_sample"])
-        errs["pred_rel_sum_p"] = relerr(rel.sum(-1), ref["pred_rel_sum_p"])
-        errs["pred_rel_sum_ij"] = relerr(rel.sum((1, 2)), ref["pred_rel_sum_ij"])
+        errs["pred_rel_sum_p"] = relerr(rel.double().sum(-1), ref["pred_rel_sum_p"])
+        errs["pred_rel_sum_ij"] = relerr(rel.double().sum((1, 2)), ref["pred_rel_sum_ij"])
     return errs
 
 
