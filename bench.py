@@ -186,7 +186,7 @@ def main():
     # (at batch 1 the decoder and the deep backbone layers are latency-bound chains of small kernels; a second/third image
     # fills the SMs they leave idle).  Inputs rotate over NIMG distinct resident images (> L2 in total), so no step finds
     # its input in L2; one forward also streams > 2 GB of activations and weights through the 126 MB L2.
-    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", "8"))  # forwards in flight on separate compute streams
+    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", "4"))  # forwards in flight on separate compute streams (full grids: 4)
     depth = int(os.environ.get("EGTR_PIPE_DEPTH", str(2 * conc)))
     NIMG = 8
     px_d = [torch.roll(px, shifts=17 * i, dims=3).to(dev) for i in range(NIMG)]
@@ -233,6 +233,31 @@ def main():
     barrier()
     t_res = e0.elapsed_time(e1) / 1000.0
     # launches inside one replayed graph == launches of one eager forward; count them on an eager pass below
+
+    # ------------------------------------------------------------ output check of the timed configuration (untimed)
+    # Every forward in flight must reproduce the same image's forward run alone in the latency configuration (which the GPU tests
+    # pin against the reference's golden at this size).  A throughput number whose outputs deviate is not a number.
+    CHECK_KEYS = ("logits", "pred_boxes", "pred_rel", "pred_connectivity")
+    want = []
+    for i in range(NIMG):
+        o = lone(px_d[i], mask_d)
+        want.append({k: o[k].clone() for k in CHECK_KEYS})
+    torch.cuda.synchronize()
+    chk_n, chk_bad, chk_worst = 0, 0, 0.0
+    for r in range(4):
+        for st_ in streams:
+            st_.wait_stream(main)
+        for i in range(conc):
+            with torch.cuda.stream(streams[i]):
+                runners[i](px_d[(i + r) % NIMG], mask_d)
+        for st_ in streams:
+            main.wait_stream(st_)
+        torch.cuda.synchronize()
+        for i in range(conc):
+            w_ = want[(i + r) % NIMG]
+            e = max(float((runners[i].out[k] - w_[k]).abs().max() / w_[k].abs().max()) for k in CHECK_KEYS)
+            chk_n, chk_bad, chk_worst = chk_n + 1, chk_bad + (e > 1e-3), max(chk_worst, e)
+    del want
 
     # ------------------------------------------------------------ leg 2: end to end, host buffers in -> host results out
     # public API: egtr_b200.serving.PipelinedRunner(model, ...) — every step pays its own H2D (pixel_values fp32 +
@@ -308,9 +333,12 @@ def main():
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([t_res, t_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([t_res, t_e2e, chk_worst], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = float(t[0]), float(t[1])
+        t_res, t_e2e, chk_worst = float(t[0]), float(t[1]), float(t[2])
+        c = torch.tensor([chk_n, chk_bad], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        chk_n, chk_bad = int(c[0]), int(c[1])
     spans = {k: sum(a.elapsed_time(b) for a, b in v) / 1000.0 / args.steps for k, v in probe.items()}  # seconds per step
     counts = {k: len(v) // args.steps for k, v in probe.items()}
 
@@ -383,6 +411,9 @@ def main():
             "e2e": {"value": img_s_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * t_e2e / args.steps, "wall_ms_per_step": 1000 * t_e2e_wall / args.steps},
             "gpu_launches": launches,
+            "output_check": {"forwards_checked": chk_n, "deviating": chk_bad, "worst_rel_err": chk_worst, "tolerance": 1e-3,
+                             "what": f"{conc} forwards in flight (the timed configuration) vs the same images run alone, max-norm relative error "
+                                     "over logits / boxes / pred_rel / pred_connectivity, all ranks"},
             "roofline": r_gemm if r_gemm is not None else r_msda, "roofline_msda_enc": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,
             "stage_ms": stage,
         }

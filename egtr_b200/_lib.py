@@ -46,6 +46,9 @@ SIGNATURES = {
     "egtr_set_scratch_slot": [_i],
     "egtr_set_splitk_max": [_i],
     "egtr_set_grid_div": [_i],
+    "egtr_set_grid_balance": [_i],
+    "egtr_set_pdl_mode": [_i],
+    "egtr_set_debug_flags": [_i],
     "egtr_split_weight_bf16": [_p, _i, _i, _i, _p, _p],
     "egtr_gemm_sbf16": [C.POINTER(ASrc), _p, _i, _i, _i, _i, C.POINTER(Epilogue), _p],
     "egtr_gemm_sbf16_grouped": [_p, _p, _p, C.POINTER(_i), _i, C.POINTER(_i), _p, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _p],

@@ -34,7 +34,9 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int num_sms();
 int splitk_max();  // runtime.cu: egtr_set_splitk_max / EGTR_GEMM_SPLITK_MAX
 int grid_div();    // runtime.cu: egtr_set_grid_div / EGTR_GEMM_GRID_DIV
+int balanced_grid(long long work, int slots);  // runtime.cu: smallest grid <= slots that needs no more rounds of tiles
 int pdl_mode();  // 0 off, 1 every launch, 2 only grids of at least one CTA per SM
+int debug_flags();  // runtime.cu: diagnostic switches (egtr_set_debug_flags)
 
 // Every kernel of the library is launched with programmatic dependent launch (PDL): the next kernel's CTAs may become
 // resident (and run their prologue) while the previous grid drains, and block in `pdl_entry()` / `pdl_wait()` until that grid

@@ -91,6 +91,7 @@ struct PArgs {
   const float* ln_beta;
   const float* ln_addend;
   int ln, ln_out2, ln_ld;
+  int dbg;                // egtr_set_debug_flags
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c, int x, int y, int z) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__((PCfg<BLOCK_N, CTAS, WS>::NUM_THREADS), 1)
 gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                 const __grid_constant__ CUtensorMap tmap_out2, const PArgs p, int* __restrict__ err) {
-  pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
+  if (!(p.dbg & 4)) pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
   if (threadIdx.x == 0) P32_STAMP(0);
   using C = PCfg<BLOCK_N, CTAS, WS>;
   constexpr int EPI_WARPS = C::EPI_WARPS, TMA_WARP = C::TMA_WARP, MMA_WARP = C::MMA_WARP;
@@ -619,7 +620,10 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (p.has_res) __syncwarp();
       }
     }
-    if (lane == 0) bulk_wait_read0();  // all stores of this warp have been read out of shared memory (global visibility: kernel end)
+    if (lane == 0) {  // all stores of this warp have been read out of shared memory (global visibility: kernel end)
+      if (p.dbg & 2) bulk_wait0();
+      else bulk_wait_read0();
+    }
     if (warp == 0 && lane == 0) P32_STAMP(4);
   }
 
@@ -880,6 +884,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   const int kbps = cdiv(k_blocks, splits);
   splits = cdiv(k_blocks, kbps);
   p.splits = splits; p.kb_per_split = kbps;
+  p.dbg = debug_flags();
 
   CUtensorMap ta, tw, to, tr, to2;
   int rc;
@@ -955,9 +960,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
   // throughput mode (egtr_set_grid_div): the persistent grid takes 1/div of the GPU, so that GEMMs of the other forwards in
   // flight run beside it on disjoint SMs instead of time-slicing the whole machine
-  int slots = num_sms() / CTAS / grid_div();
-  if (slots < 1) slots = 1;
-  const int grid = (work < slots ? work : slots) * CTAS;
+  const int grid = balanced_grid(work, num_sms() / CTAS / grid_div()) * CTAS;
   EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, WS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, to2, p,
                        device_error_flag_p32()));
   if (splits > 1) {

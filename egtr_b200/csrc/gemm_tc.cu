@@ -754,8 +754,7 @@ int launch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, con
     EGTR_CHECK(partial != nullptr, EGTR_ERR_CUDA, "split-K scratch allocation failed");
   }
   const int work = tiles * splits;
-  const int cap = num_sms() / grid_div() > 0 ? num_sms() / grid_div() : 1;  // throughput mode: a share of the GPU per GEMM
-  const int grid = work < cap ? work : cap;
+  const int grid = balanced_grid(work, num_sms() / grid_div());  // throughput mode: a share of the GPU per GEMM
   launch_pdl(gemm_sbf16_kernel<BLOCK_N, MODE, REL>, dim3(grid), dim3(NUM_THREADS), (size_t)(C::SMEM_BYTES), st, tmap, a, ep, M, N, Npad, K, splits, kbps, partial, groups, plane_rows, tab, device_error_flag());
   EGTR_CUDA(cudaGetLastError());
   if (splits > 1) {

@@ -59,7 +59,7 @@ constexpr int kMsdaUnroll = EGTR_MSDA_UNROLL;
 #ifndef EGTR_MSDA_ENC_QPB  // encoder patch: 32 = 8x4 pixels (256 threads), 64 = 8x8 pixels (512 threads)
 #define EGTR_MSDA_ENC_QPB 32
 #endif
-template <bool FUSED, int QPB>
+template <bool FUSED, int QPB, bool BYPASS_L1 = false>
 __global__ void __launch_bounds__(QPB * 8, QPB == 32 ? EGTR_MSDA_MINB : (QPB == 64 ? EGTR_MSDA_MINB / 2 : 8))
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   pdl_entry();
@@ -128,8 +128,13 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       float logit = 0.f;
       if (q >= 0) {
         const float* row = a.offaw + ((long long)b * a.Lq + q) * a.ld_offaw;
-        off = *(const float2*)(row + (m * 16 + s) * 2);
-        logit = row[a.M * 32 + m * 16 + s];
+        if (BYPASS_L1) {
+          off = __ldcg((const float2*)(row + (m * 16 + s) * 2));
+          logit = __ldcg(row + a.M * 32 + m * 16 + s);
+        } else {
+          off = *(const float2*)(row + (m * 16 + s) * 2);
+          logit = row[a.M * 32 + m * 16 + s];
+        }
       }
       float mx = logit;
 #pragma unroll
@@ -198,6 +203,7 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   // (left to itself the compiler re-associates base = uniform pointer + 64-bit element offset: four instructions per address)
   unsigned long long vb;
   asm("mov.b64 %0, %1;" : "=l"(vb) : "l"(vbase));
+  auto ldv = [](const float4* ptr) { return BYPASS_L1 ? __ldcg(ptr) : __ldg(ptr); };
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* myslots = &slots[g * Q_STRIDE];
 #pragma unroll (QPB >= 32 ? kMsdaUnroll : 8)
@@ -205,10 +211,10 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     const int4 id = *(const int4*)(myslots + ss * SLOT_WORDS);
     const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-    if (FUSED || id.x >= 0) v0 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.x * 4ull));
-    if (FUSED || id.y >= 0) v1 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.y * 4ull));
-    if (FUSED || id.z >= 0) v2 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.z * 4ull));
-    if (FUSED || id.w >= 0) v3 = __ldg((const float4*)(vb + (unsigned long long)(uint32_t)id.w * 4ull));
+    if (FUSED || id.x >= 0) v0 = ldv((const float4*)(vb + (unsigned long long)(uint32_t)id.x * 4ull));
+    if (FUSED || id.y >= 0) v1 = ldv((const float4*)(vb + (unsigned long long)(uint32_t)id.y * 4ull));
+    if (FUSED || id.z >= 0) v2 = ldv((const float4*)(vb + (unsigned long long)(uint32_t)id.z * 4ull));
+    if (FUSED || id.w >= 0) v3 = ldv((const float4*)(vb + (unsigned long long)(uint32_t)id.w * 4ull));
     acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y); acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
     acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y); acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
     acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
@@ -308,12 +314,14 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   a.offaw = offaw; a.ld_offaw = ld_offaw;
   a.ref_points = ref_points; a.valid_ratios = valid_ratios;
   a.out = out; a.out_fmt = out_fmt; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
+  const bool cg = debug_flags() & 1;  // diagnostic (egtr_set_debug_flags bit 0): gathers and offset reads bypass L1
   if (!enc_ref && (long long)Lq * B <= 4096) {  // decoder-sized query sets: small CTAs for parallelism and latency
     dim3 grid(cdiv(Lq, 8), M, B);
     launch_pdl(msda_kernel<true, 8>, dim3(grid), dim3(64), (size_t)(0), (cudaStream_t)s, a, lv);
   } else if (enc_ref) {
     dim3 grid(patches, M, B);
-    launch_pdl(msda_kernel<true, kEncQ>, dim3(grid), dim3(kEncQ * 8), (size_t)(0), (cudaStream_t)s, a, lv);
+    if (cg) launch_pdl(msda_kernel<true, kEncQ, true>, dim3(grid), dim3(kEncQ * 8), (size_t)(0), (cudaStream_t)s, a, lv);
+    else launch_pdl(msda_kernel<true, kEncQ>, dim3(grid), dim3(kEncQ * 8), (size_t)(0), (cudaStream_t)s, a, lv);
   } else {
     dim3 grid(cdiv(Lq, 32), M, B);
     launch_pdl(msda_kernel<true, 32>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);

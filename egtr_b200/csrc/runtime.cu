@@ -63,9 +63,47 @@ int grid_div() {
   return v;
 }
 
+// Balanced persistent grids: a grid capped at `slots` CTAs (or pairs) runs ceil(work / slots) rounds of tiles whatever its size
+// between ceil(work / rounds) and slots, so the smallest such grid finishes at the same time and leaves the other SMs to the
+// kernels of the other forwards in flight (87 pair tiles on 37 slots: 3 rounds either way, 29 pairs instead of 37).
+// EGTR_GEMM_BALANCE=0 restores min(work, slots) (dev A/B).
+static std::atomic<int> g_grid_balance{-1};
+int balanced_grid(long long work, int slots) {
+  int on = g_grid_balance.load(std::memory_order_relaxed);
+  if (on < 0) {
+    const char* e = getenv("EGTR_GEMM_BALANCE");
+    on = e ? (atoi(e) != 0) : 1;
+    g_grid_balance.store(on);
+  }
+  if (slots < 1) slots = 1;
+  if (work <= slots) return (int)work;
+  if (!on || grid_div() == 1) return slots;  // a lone forward has nobody to leave SMs to (and full grids keep their PDL attribute)
+  const long long rounds = (work + slots - 1) / slots;
+  return (int)((work + rounds - 1) / rounds);
+}
+
+static std::atomic<int> g_pdl_mode{-1};
 int pdl_mode() {
-  static const int mode = [] { const char* e = getenv("EGTR_B200_PDL"); return e ? atoi(e) : 2; }();
-  return mode;
+  int v = g_pdl_mode.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("EGTR_B200_PDL");
+    v = e ? atoi(e) : 2;
+    g_pdl_mode.store(v);
+  }
+  return v;
+}
+// dev/diagnostic switches (tools/diag_race.py): bit 0 MSDA gathers bypass L1 (ld.global.cg), bit 1 the TMA-store epilogue waits
+// for full completion of its bulk stores (not only for the reads of its staging tiles) before the CTA exits, bit 2 the GEMM
+// kernels do not trigger their dependents early
+static std::atomic<int> g_debug_flags{-1};
+int debug_flags() {
+  int v = g_debug_flags.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("EGTR_B200_DEBUG_FLAGS");
+    v = e ? atoi(e) : 0;
+    g_debug_flags.store(v);
+  }
+  return v;
 }
 
 }  // namespace egtr
@@ -78,6 +116,19 @@ extern "C" int egtr_set_scratch_slot(int slot) {
 extern "C" int egtr_set_grid_div(int div) {
   EGTR_CHECK(div >= 1 && div <= 16, EGTR_ERR_ARG, "egtr_set_grid_div: %d outside 1..16", div);
   egtr::g_grid_div.store(div);
+  return EGTR_OK;
+}
+extern "C" int egtr_set_pdl_mode(int mode) {
+  EGTR_CHECK(mode >= 0 && mode <= 2, EGTR_ERR_ARG, "egtr_set_pdl_mode: %d outside 0..2", mode);
+  egtr::g_pdl_mode.store(mode);
+  return EGTR_OK;
+}
+extern "C" int egtr_set_debug_flags(int flags) {
+  egtr::g_debug_flags.store(flags & 0xff);
+  return EGTR_OK;
+}
+extern "C" int egtr_set_grid_balance(int on) {
+  egtr::g_grid_balance.store(on != 0);
   return EGTR_OK;
 }
 extern "C" int egtr_set_splitk_max(int max_splits) {

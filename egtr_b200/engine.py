@@ -130,8 +130,11 @@ class Engine:
                 and c.activation_function == "relu"):
             raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
         self._ws: Dict[tuple, dict] = {}
-        # forwards in flight (serving): each persistent GEMM takes half of the SMs, so GEMMs of different images run side by side
-        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "2"))
+        # forwards in flight (serving).  A share of the SMs per persistent GEMM (egtr_set_grid_div > 1: GEMMs of different images
+        # side by side) measured +10 % at workload B, but it is OFF: with partial grids 10-28 % of full-size forwards deviate
+        # (a race that full grids never showed in hundreds of forwards; profiles/r01_throughput_race_matrix.txt).
+        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "1"))
+        self.throughput_splitk = int(os.environ.get("EGTR_THROUGHPUT_SPLITK", "1"))  # split-K cap of forwards in flight (1 = off)
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
@@ -448,7 +451,7 @@ class Engine:
     def _forward(self, pixel_values, pixel_mask, taps, slot: int = 0, throughput: bool = False):
         cfg, dev = self.cfg, self.device
         call("egtr_set_scratch_slot", slot)
-        call("egtr_set_splitk_max", 1 if throughput else 64)
+        call("egtr_set_splitk_max", self.throughput_splitk if throughput else 64)
         call("egtr_set_grid_div", self.throughput_grid_div if throughput else 1)
         st = _stream()
         px = pixel_values.to(torch.float32).contiguous()

@@ -49,9 +49,18 @@ int egtr_set_scratch_slot(int slot);
 /* Upper bound (1..64, process-wide) on the split-K factor of the tensor-core GEMMs.  Default 64: minimises the latency of a
  * single forward; 1 (off) is the throughput configuration, where several forwards in flight fill the SMs. */
 int egtr_set_splitk_max(int max_splits);
-/* Persistent GEMM grids use num_sms / div SMs (1..16, process-wide, default 1).  Throughput configuration: several forwards
- * in flight with div > 1 run their GEMMs side by side on disjoint SMs instead of time-slicing the whole GPU. */
+/* Persistent GEMM grids use num_sms / div SMs (1..16, process-wide, default 1).  With several forwards in flight div > 1 runs
+ * their GEMMs side by side on disjoint SMs instead of time-slicing the whole GPU (+10 % at 800x1333) — EXPERIMENTAL: round 1
+ * measured nondeterministic deviations in 10-28 % of full-size forwards with div > 1; keep 1 in production. */
 int egtr_set_grid_div(int div);
+/* With div > 1: size each persistent grid as the smallest one that needs no more rounds of tiles than num_sms / div CTAs would
+ * (default on; 0 = always take num_sms / div).  The SMs it leaves go to the kernels of the other forwards in flight. */
+int egtr_set_grid_balance(int on);
+/* Programmatic dependent launch: 0 off, 1 every launch, 2 (default) grids of at least one CTA per SM. */
+int egtr_set_pdl_mode(int mode);
+/* Diagnostic switches (tools/diag_race.py), default 0: bit 0 MSDA gathers bypass L1, bit 1 GEMM epilogues wait for full
+ * completion of their bulk stores before exit, bit 2 GEMM kernels do not trigger dependent launches early. */
+int egtr_set_debug_flags(int flags);
 
 /* ---------------------------------------------------------------- GEMM-class operators ---- */
 /* Left-operand source: rows of 64-float runs.  mode 0: row m = a + m*lda (+ a2 + m*lda when a2

@@ -1,11 +1,9 @@
 #!/bin/bash
-# quick GPU pass: MSDA encoder patch A/B (8x4 vs 8x8 pixels per CTA), correctness of the variant first
+# GPU pass: bisect the throughput-mode deviation at full size B, then bench the candidate fallback configurations
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-EGTR_B200_LIB=$PWD/egtr_b200/csrc/libvar_q64.so timeout 600 python -m pytest tests -m gpu -q -x -k "msda or golden" 2>&1 | tail -5 | tee gpurun_out/q64_tests.log
-for v in "" q64 "" q64; do
-  if [ -n "$v" ]; then export EGTR_B200_LIB=$PWD/egtr_b200/csrc/libvar_$v.so; else unset EGTR_B200_LIB; fi
-  echo "=== ${v:-default}"; timeout 600 python bench.py --cpu-sample 0 --steps 20 2>/dev/null | python -c "
+timeout 150 python tools/diag_throughput.py golden 2>&1 | tail -60
+ab() { echo "=== $1"; shift; env "$@" timeout 60 python bench.py --cpu-sample 0 --steps 20 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],2), round(d['e2e']['value'],2), 'msda_enc us', round(d['roofline_msda_enc']['avg_launch_us'],1))"
-done 2>&1 | tee gpurun_out/msda_ab2.txt
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],2), round(d['e2e']['value'],2), 'latency ms', round(d['config']['single_forward_latency_ms'],3))"; }
+{ ab unbalanced EGTR_GEMM_BALANCE=0; ab latency-knobs EGTR_THROUGHPUT_SPLITK=64 EGTR_THROUGHPUT_GRID_DIV=1; ab splitk64-div2-bal EGTR_THROUGHPUT_SPLITK=64; } 2>&1 | tee gpurun_out/fallback_ab.txt
