@@ -198,23 +198,3 @@ def test_forward_full_size_configs(cuda, name):
             inv = {k: relerr(out[k][b:b + 1], alone[k]) for k in keys}
             print(name, f"image {b} batched vs alone", {k: f"{v:.2e}" for k, v in inv.items()})
             assert max(inv.values()) < TOL / 10, (b, inv)
-
-
-@pytest.mark.parametrize("hw,pad", [((33, 47), None), ((17, 23), None), ((64, 64), [(64, 64), (40, 33)]),
-                                    ((97, 131), [(97, 131), (50, 131), (97, 60)])])
-def test_forward_edge_sizes_vs_live_oracle(cuda, hw, pad):
-    """Degenerate geometries: images so small that the coarse levels shrink to 1x1 / 2x2 maps (patch tiles, TMA boxes and the
-    MSDA patches are then larger than the map), sizes that are not multiples of the strides, and images padded to less than
-    half of the batch canvas."""
-    from egtr_b200.config import workload_config
-    from egtr_b200.synth import synth_images, synth_state_dict
-    from oracle import egtr_oracle as orc
-    cfg = workload_config("tiny")
-    sd = synth_state_dict(cfg, 70)
-    batch = len(pad) if pad else 1
-    px, mask = synth_images(batch, hw[0], hw[1], seed=71, pad_to=pad)
-    want = orc.forward(sd, cfg, px, mask)
-    _, out = _run(cfg, sd, px, mask, cuda)
-    errs = compare_forward(out, want)
-    print(hw, batch, {k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) < TOL, errs

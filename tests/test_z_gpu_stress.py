@@ -75,3 +75,33 @@ def test_partial_grid_race_reproducer(case):
     finally:
         eng.throughput_grid_div = keep
     assert max(errs) < TOL, f"{sum(e > TOL for e in errs)}/60 forwards deviate"
+
+
+# Last in the last file: a device-side fault here cannot take other tests with it.
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: not yet run on hardware (geometries far "
+                                        "below anything the reference is used with); an XPASS promotes it to a regular test next round")
+@pytest.mark.parametrize("hw,pad", [((33, 47), None), ((17, 23), None), ((64, 64), [(64, 64), (40, 33)]),
+                                    ((97, 131), [(97, 131), (50, 131), (97, 60)])])
+def test_forward_edge_sizes_vs_live_oracle(cuda, hw, pad):
+    """Degenerate geometries: images so small that the coarse levels shrink to 1x1 / 2x2 maps (patch tiles, TMA boxes and the
+    MSDA patches are then larger than the map), sizes that are not multiples of the strides, and images padded to less than
+    half of the batch canvas."""
+    from egtr_b200.config import workload_config
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from oracle import egtr_oracle as orc
+    cfg = workload_config("tiny")
+    sd = synth_state_dict(cfg, 70)
+    batch = len(pad) if pad else 1
+    px, mask = synth_images(batch, hw[0], hw[1], seed=71, pad_to=pad)
+    want = orc.forward(sd, cfg, px, mask)
+    from egtr_b200.model.egtr import DetrForSceneGraphGeneration
+    model = DetrForSceneGraphGeneration(cfg)
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    out = model(pixel_values=px.to(cuda), pixel_mask=mask.to(cuda), output_attentions=False, output_attention_states=True,
+                output_hidden_states=True)
+    torch.cuda.synchronize()
+    from tests.util import compare_forward
+    errs = compare_forward(out, want)
+    print(hw, batch, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
