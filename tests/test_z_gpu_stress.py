@@ -77,6 +77,83 @@ def test_partial_grid_race_reproducer(case):
     assert max(errs) < TOL, f"{sum(e > TOL for e in errs)}/60 forwards deviate"
 
 
+KERNELS = {  # the five GEMMs of one encoder layer at workload B (M = 22 223 tokens)
+    "offaw": dict(N=384, K=256),
+    "value": dict(N=256, K=256, keep=True),
+    "out_proj_ln": dict(N=256, K=256, ln=True, res=True),
+    "fc1": dict(N=1024, K=256, relu=True),
+    "fc2_ln_out2": dict(N=256, K=1024, ln=True, res=True, out2=True),
+}
+
+
+@pytest.mark.xfail(strict=False, reason="locator for the partial-grid race: which encoder GEMM stops being repeatable under "
+                                        "egtr_set_grid_div(2)?  Result is reported as a warning in the pytest summary")
+@pytest.mark.parametrize("kind", list(KERNELS))
+def test_partial_grid_race_per_kernel(cuda, kind):
+    """One kernel at a time, same inputs: the launch with full grids is the reference, 40 launches on half of the SMs must be
+    bit-identical to it (no split-K at these shapes: the tiles and their arithmetic are the same, only the CTA that runs them
+    differs)."""
+    import ctypes as C
+    import warnings
+
+    from egtr_b200 import _lib
+    from egtr_b200._lib import ASrc, Epilogue
+    from egtr_b200.engine import Lin
+    from tests.util import p32_encode
+    k = KERNELS[kind]
+    M, N, K = 22223, k["N"], k["K"]
+    g = torch.Generator().manual_seed(N * 7 + K)
+    a = p32_encode(torch.randn(M, K, generator=g)).to(cuda)
+    lin = Lin((torch.randn(N, K, generator=g) / K ** 0.5).to(cuda), torch.randn(N, generator=g).to(cuda), cuda)
+    res = p32_encode(torch.randn(M, 256, generator=g)).to(cuda) if k.get("res") else None
+    gamma, beta = (1 + 0.2 * torch.randn(256, generator=g)).to(cuda), torch.randn(256, generator=g).to(cuda)
+    addend = torch.randn(M, 256, generator=g).to(cuda)
+    keep = (torch.rand(M, generator=g) > 0.1).to(torch.uint8).to(cuda) if k.get("keep") else None
+    st = torch.cuda.current_stream().cuda_stream
+
+    def launch(div):
+        out = torch.full((M, N), float("nan"), device=cuda)
+        out2 = torch.full((M, 256), float("nan"), device=cuda)
+        src, ep = ASrc(), Epilogue()
+        src.a, src.mode, src.lda, src.fmt = a.data_ptr(), 0, K, 1
+        ep.bias, ep.out, ep.ldo, ep.ldr = lin.b.data_ptr(), out.data_ptr(), N, N
+        ep.relu, ep.out_fmt = int(bool(k.get("relu"))), (1 if k.get("ln") else 0)
+        if res is not None:
+            ep.res, ep.res_fmt = res.data_ptr(), 1
+        if keep is not None:
+            ep.row_keep = keep.data_ptr()
+        if k.get("ln"):
+            ep.ln_gamma, ep.ln_beta = gamma.data_ptr(), beta.data_ptr()
+            if k.get("out2"):
+                ep.ln_out2, ep.ln_addend = out2.data_ptr(), addend.data_ptr()
+        _lib.call("egtr_set_splitk_max", 1)
+        _lib.call("egtr_set_grid_div", div)
+        try:
+            _lib.call("egtr_gemm_sbf16", C.byref(src), lin.planes.data_ptr(), M, N, lin.Npad, K, C.byref(ep), st)
+            torch.cuda.synchronize()
+        finally:
+            _lib.call("egtr_set_grid_div", 1)
+            _lib.call("egtr_set_splitk_max", 64)
+        return out.view(torch.int32), out2.view(torch.int32)
+
+    ref, ref2 = launch(1)
+    again, _ = launch(1)
+    assert torch.equal(ref, again), "full grids are not repeatable either"
+    bad_runs, bad_rows, bad_cols = 0, set(), set()
+    for _ in range(40):
+        o, o2 = launch(2)
+        diff = (o != ref) | ((o2 != ref2) if k.get("out2") else False)
+        if bool(diff.any()):
+            bad_runs += 1
+            rows, cols = diff.nonzero(as_tuple=True)
+            bad_rows.update((rows // 32).unique().tolist()[:64])
+            bad_cols.update((cols // 32).unique().tolist())
+    msg = (f"partial-grid repeatability, {kind} (M={M} N={N} K={K}): {bad_runs}/40 launches differ from the full-grid launch; "
+           f"32-row groups hit {sorted(bad_rows)[:24]}, 32-column chunks hit {sorted(bad_cols)}")
+    warnings.warn(msg)
+    assert bad_runs == 0, msg
+
+
 # Last in the last file: a device-side fault here cannot take other tests with it.
 @pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: not yet run on hardware (geometries far "
                                         "below anything the reference is used with); an XPASS promotes it to a regular test next round")
