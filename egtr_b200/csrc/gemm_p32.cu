@@ -443,6 +443,11 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
                            : "r"(my_row_s + ((c ^ sw) << 4)) : "memory");
+            // The next residual box lands in the same staging tile.  Generic-proxy reads followed by an asynchronous-proxy write
+            // of the same shared memory need a proxy fence (the plain path gets one from its output staging; this path requested
+            // the next box right after issuing its ld.shared, which __syncwarp alone does not order: WARPSYNC does not wait for
+            // the loads' data, and with a lightly loaded memory system the box can land inside a congested LDS latency).
+            ptx::fence_proxy_async_smem();
             __syncwarp();  // every lane has read this residual box: the next one may land in the staging tile
             if (lane == 0 && ci + 1 < 4) {
               ptx::mbar_arrive_expect_tx(rbar, STG_BYTES);
