@@ -186,7 +186,7 @@ def main():
     # (at batch 1 the decoder and the deep backbone layers are latency-bound chains of small kernels; a second/third image
     # fills the SMs they leave idle).  Inputs rotate over NIMG distinct resident images (> L2 in total), so no step finds
     # its input in L2; one forward also streams > 2 GB of activations and weights through the 126 MB L2.
-    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", "4"))  # forwards in flight on separate compute streams (full grids: 4)
+    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", "8"))  # forwards in flight on separate compute streams (half-GPU grids: 8)
     depth = int(os.environ.get("EGTR_PIPE_DEPTH", str(2 * conc)))
     NIMG = 8
     px_d = [torch.roll(px, shifts=17 * i, dims=3).to(dev) for i in range(NIMG)]

@@ -475,7 +475,11 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const float2* theirs = (const float2*)(stg_all + (warp ^ 4) * STG_BYTES);
           mine[lane] = make_float2(s1, s2);
           ptx::named_bar_sync(1 + q, 64);
-          const float2 o2 = theirs[lane];
+          float2 o2 = theirs[lane];
+          // the partner's staging tile is next written by ITS asynchronous-proxy traffic (residual boxes): order this generic-proxy
+          // read before it explicitly (bar.sync orders the accesses of the participating threads, the proxy fence the proxies)
+          asm volatile("" : "+f"(o2.x), "+f"(o2.y));  // the loaded values exist before the fence and the barrier are issued
+          ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(1 + q, 64);  // both warps have read before either overwrites its staging tile with output
           s1 += o2.x; s2 += o2.y;
         }

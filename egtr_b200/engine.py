@@ -130,10 +130,10 @@ class Engine:
                 and c.activation_function == "relu"):
             raise _lib.EgtrError("kernels are built for the shipped EGTR architecture (d_model 256, 8 heads, 4 levels x 4 points, resnet50)")
         self._ws: Dict[tuple, dict] = {}
-        # forwards in flight (serving).  A share of the SMs per persistent GEMM (egtr_set_grid_div > 1: GEMMs of different images
-        # side by side) measured +10 % at workload B, but it is OFF: with partial grids 10-28 % of full-size forwards deviate
-        # (a race that full grids never showed in hundreds of forwards; profiles/r01_throughput_race_matrix.txt).
-        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "1"))
+        # forwards in flight (serving): each persistent GEMM takes a share of the SMs (egtr_set_grid_div(2)) so that GEMMs of
+        # different images run side by side, +10 % at workload B.  Round 1 found a race in this mode (LayerNorm epilogue, a missing
+        # proxy fence); fixed, and re-measured in round 2: 0 / 1188 full-size forwards deviate (profiles/r02_race_matrix.txt).
+        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "2"))
         self.throughput_splitk = int(os.environ.get("EGTR_THROUGHPUT_SPLITK", "1"))  # split-K cap of forwards in flight (1 = off)
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
