@@ -32,6 +32,13 @@ class Epilogue(C.Structure):
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_addend", C.c_void_p), ("ln_out2", C.c_void_p)]
 
 
+class RelheadWeights(C.Structure):
+    """egtr_relhead_weights_t (include/egtr_b200.h)."""
+    _fields_ = [("layers", C.c_int), ("uv_planes", C.c_void_p), ("uv_bias", C.c_void_p), ("uv_npad", C.c_int),
+                ("b1", C.c_void_p), ("w2g", C.c_void_p), ("b2", C.c_void_p), ("w3g", C.c_void_p), ("b3", C.c_void_p),
+                ("w3c", C.c_void_p), ("b3c", C.c_float)]
+
+
 FMT_F32, FMT_P32 = 0, 1
 
 
@@ -79,6 +86,10 @@ SIGNATURES = {
     "egtr_argmax_rows_f32": [_p, _i, _i, _p, _p],
     "egtr_resample_h_u8": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p],
     "egtr_resample_v_normalize_f32": [_p, _i, _i, _i, _i, _p, _p, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _ll, _i, _p, _i, _p],
+    "egtr_pack_weight_p32g": [_p, _i, _i, _i, _p, _p, _p],
+    "egtr_relation_pairs_fused_f32": [_p, _p, _i, _i, C.POINTER(RelheadWeights), _p, _p, _i, _p, _f, _i, _i, _i, _p, _p, _p],
+    "egtr_relation_head_fwd_f32": [_p, _p, _i, _p, _i, _p, _i, C.POINTER(RelheadWeights), _p, _p, _f, _i, _i, _i, _i, _i,
+                                   _p, _p, _p, _p, _p, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ASrc, Epilogue, call
+from ._lib import ASrc, Epilogue, RelheadWeights, call
 
 RESNET_BLOCKS = (3, 4, 6, 3)
 SKINNY_M = 512  # GEMMs with at most this many rows may take the fp32 skinny kernel (decoder, detection heads)
@@ -283,6 +283,23 @@ class Engine:
         self.rel_dist = sd["rel_dist"].contiguous()
         self.rel_adj = (float(getattr(cfg, "logit_adj_tau", 0.3)) * self.rel_dist.log()).contiguous()  # egtr.py:509-512
         self.con_w3_b_host = float(sd["connectivity_layer.layers.2.bias"].item())
+        # fused relation head (relhead.cu): layer-2 / layer-3 weights as bf16 "P32 group" rows for its TMA boxes
+        Lr = cfg.decoder_layers + 1
+        self.rel_fused = P_ <= 64 and Lr <= 7
+        if self.rel_fused:
+            bf16 = dict(dtype=torch.bfloat16, device=dev)
+            self.rel_w2g = torch.empty(512, 512, **bf16)
+            call("egtr_pack_weight_p32g", _ptr(self.rel_w2both.w), 512, 256, 512, None, _ptr(self.rel_w2g), _stream())
+            r = torch.arange(64, device=dev)
+            # each CTA of a pair feeds 16 weight rows to each of the two N = 32 layer-3 MMAs (include/egtr_b200.h)
+            self.rel_w3perm = (32 * ((r % 32) // 16) + 16 * (r // 32) + r % 16).to(torch.int32).contiguous()
+            self.rel_w3g = torch.empty(64, 512, **bf16)
+            call("egtr_pack_weight_p32g", _ptr(self.rel_w3.w), P_, 256, 64, _ptr(self.rel_w3perm), _ptr(self.rel_w3g), _stream())
+            hw = RelheadWeights()
+            hw.layers, hw.uv_planes, hw.uv_bias, hw.uv_npad = Lr, _ptr(self.rel_uv.planes), _ptr(self.rel_uv.b), self.rel_uv.Npad
+            hw.b1, hw.w2g, hw.b2 = _ptr(self.rel_b1), _ptr(self.rel_w2g), _ptr(self.rel_w2both.b)
+            hw.w3g, hw.b3, hw.w3c, hw.b3c = _ptr(self.rel_w3g), _ptr(self.rel_w3.b), _ptr(self.con_w3_w), self.con_w3_b_host
+            self.rel_head_w = hw
         torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------ CUDA-graph replay
@@ -657,7 +674,9 @@ class Engine:
         a_cols = [0] * nl + [0] + [256] * nl + [0]
         ldas = [768] * nl + [256] + [768] * nl + [256]
         outs = [(ws["U"], l * 516) for l in range(Lr)] + [(ws["V"], l * 516) for l in range(Lr)]
-        self.gemm_grouped(self.rel_uv, Md, a=a_list, a_col=a_cols, lda=ldas, out=outs, ldo=Lr * 516)
+        fused = self.rel_fused and gemm_backend() != "simt" and os.environ.get("EGTR_RELHEAD", "fused") == "fused"
+        if not fused:
+            self.gemm_grouped(self.rel_uv, Md, a=a_list, a_col=a_cols, lda=ldas, out=outs, ldo=Lr * 516)
         pairs = B * N * N
         pred_rel = torch.empty(B, N, N, P, **f32)
         pred_con = torch.empty(B, N, N, 1, **f32)
@@ -672,8 +691,17 @@ class Engine:
             call("egtr_relation_finish_f32", _ptr(ws["rel_logits"]), P, _ptr(ws["con_logits"]), 1, _ptr(logits), K,
                  _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
                  int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["cls_idx"]), _ptr(pred_rel), _ptr(pred_con), st)
+        elif fused:
+            # ONE entry point: 14 per-query projections -> class argmax -> the fused pair kernel (relhead.cu);
+            # nothing of the pair dimension except pred_rel / pred_connectivity reaches HBM
+            qp = (C.c_void_p * nl)(*[_ptr(q, 0) for q in qkvs])
+            kp = (C.c_void_p * nl)(*[_ptr(q, 256) for q in qkvs])
+            call("egtr_relation_head_fwd_f32", qp, kp, 768, _ptr(h_last), 256, _ptr(logits), K, C.byref(self.rel_head_w),
+                 _ptr(self.triplet), _ptr(self.rel_dist), float(getattr(cfg, "logit_adj_tau", 0.3)), int(bool(cfg.use_freq_bias)),
+                 int(bool(cfg.logit_adjustment)), B, N, P, _ptr(ws["U"]), _ptr(ws["V"]), _ptr(ws["cls_idx"]), _ptr(pred_rel),
+                 _ptr(pred_con), st)
         else:
-            # fused pair stage: the gating + layer 1 is the GEMM's operand producer (never in HBM), layer 2 of both MLPs is
+            # P > 64 (stress config E) — fused pair stage: the gating + layer 1 is the GEMM's operand producer (never in HBM), layer 2 of both MLPs is
             # one block-diagonal tcgen05 GEMM, the connectivity head's last layer + sigmoid is its epilogue; only the
             # relation MLP's 256-wide hidden goes to HBM for the layer-3 GEMM whose epilogue finishes pred_rel.
             TI, TJ = (N + 7) // 8, (N + 15) // 16
@@ -706,27 +734,39 @@ class Engine:
 
 class GraphRunner:
     """Static-buffer CUDA graph of `Engine._forward` for one (B, H, W).  Outputs are the graph's own
-    buffers and are overwritten by the next replay (callers that keep results must clone them)."""
+    buffers and are overwritten by the next replay (callers that keep results must clone them).
 
-    def __init__(self, eng: Engine, B: int, H: int, W: int, slot: int = 0, throughput: bool = False):
+    `prologue(runner)` / `epilogue(runner, out) -> dict` (optional) are captured into the same graph before / after the
+    forward: input staging that fills `runner.px` / `runner.pm` from the caller's own static buffers (uint8 images,
+    egtr_b200/serving.py) and post-processing of the outputs (triplet extraction); the epilogue's result is `runner.extra`."""
+
+    def __init__(self, eng: Engine, B: int, H: int, W: int, slot: int = 0, throughput: bool = False, prologue=None, epilogue=None):
         self.eng = eng
         self.slot = slot
         self.throughput = throughput
+        self.extra = None
         dev = eng.device
         with torch.cuda.device(dev):
             self.px = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
             self.pm = torch.ones(B, H, W, dtype=torch.long, device=dev)
+
+            def run():
+                if prologue is not None:
+                    prologue(self)
+                out = eng._forward(self.px, self.pm, None, slot, throughput)
+                return out, (epilogue(self, out) if epilogue is not None else None)
+
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: one-time attribute calls, tensor-map cache, workspace allocation
-                    eng._forward(self.px, self.pm, None, slot, throughput)
+                    run()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             probe, eng.probe = eng.probe, None
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = eng._forward(self.px, self.pm, None, slot, throughput)
+                self.out, self.extra = run()
             eng.probe = probe
 
     def __call__(self, pixel_values: torch.Tensor, pixel_mask: Optional[torch.Tensor] = None):

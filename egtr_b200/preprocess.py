@@ -107,3 +107,44 @@ class DeviceImageStager:
                 for t in tensors:
                     t.record_stream(torch.cuda.current_stream())
         return px, mask, sizes
+
+
+class StaticStager:
+    """Fixed-shape staging for CUDA-graph capture (egtr_b200/serving.py): `B` uint8 RGB images of one raw size
+    [B, h0, w0, 3] in a static device buffer `u8` -> `pixel_values` / `pixel_mask` of a (Hm, Wm) batch tensor, with the same
+    two kernels (and the same Pillow-exact arithmetic) as `DeviceImageStager`.  The tap tables are built once; a step uploads
+    only the uint8 pixels (3.2 MB for 800x1333 instead of 21.3 MB of fp32 pixels + int64 mask)."""
+
+    def __init__(self, B: int, raw_hw: Tuple[int, int], pad_hw: Tuple[int, int], device, size: int = 800, max_size: Optional[int] = 1333,
+                 out_hw: Optional[Tuple[int, int]] = None):
+        self.B, self.raw_hw, self.pad_hw = B, tuple(raw_hw), tuple(pad_hw)
+        h0, w0 = self.raw_hw
+        self.out_hw = tuple(out_hw) if out_hw is not None else target_size(h0, w0, size, max_size)
+        oh, ow = self.out_hw
+        if oh > pad_hw[0] or ow > pad_hw[1]:
+            raise ValueError(f"resized image {self.out_hw} does not fit the batch tensor {self.pad_hw}")
+        self.device = torch.device(device)
+        bh, kh, self.ksh = tap_tables(w0, ow)
+        bv, kv, self.ksv = tap_tables(h0, oh)
+        with torch.cuda.device(self.device):
+            self.u8 = torch.zeros(B, h0, w0, 3, dtype=torch.uint8, device=self.device)
+            self.t_bh, self.t_kh, self.t_bv, self.t_kv = (torch.from_numpy(a).to(self.device) for a in (bh, kh, bv, kv))
+            self.tmp = torch.empty(h0, ow, 3, dtype=torch.uint8, device=self.device) if w0 != ow else None
+        self._mean = (C.c_float * 3)(*IMAGE_MEAN)
+        self._std = (C.c_float * 3)(*IMAGE_STD)
+
+    def enqueue(self, px: torch.Tensor, pm: torch.Tensor) -> None:
+        """Launch the staging kernels on the current stream: self.u8 -> px [B,3,Hm,Wm] f32, pm [B,Hm,Wm] i64."""
+        (h0, w0), (oh, ow), (hm, wm) = self.raw_hw, self.out_hw, self.pad_hw
+        st = torch.cuda.current_stream().cuda_stream
+        if (oh, ow) != (hm, wm):
+            px.zero_()
+            pm.zero_()
+        for b in range(self.B):
+            src = self.u8[b]
+            if self.tmp is not None:
+                call("egtr_resample_h_u8", src.data_ptr(), h0, w0, 3, ow, self.t_bh.data_ptr(), self.t_kh.data_ptr(), self.ksh,
+                     self.tmp.data_ptr(), st)
+                src = self.tmp
+            call("egtr_resample_v_normalize_f32", src.data_ptr(), h0, ow, 3, oh, self.t_bv.data_ptr(), self.t_kv.data_ptr(), self.ksv,
+                 self._mean, self._std, px[b].data_ptr(), hm * wm, wm, pm[b].data_ptr(), wm, st)

@@ -258,6 +258,50 @@ int egtr_relation_finish_f32(const float* rel_logits, int ld_rel, const float* c
                              float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
                              int* cls_scratch /* B*N ints */, float* pred_rel, float* pred_conn, egtr_stream_t s);
 
+/* ---- The relation head behind one entry point (model/egtr.py:322-418, 507-516) ----
+ * Weights prepared once at load.  The per-query stage composes proj_q[l] / proj_k[l] / final_sub_proj / final_obj_proj with
+ * layer 1 of both MLPs and the gate (two stacked Linears with nothing in between, composed in fp64 by the host):
+ * group l < layers gives U_l (subject side), group layers + l gives V_l (object side, gate bias folded in); each group has 513
+ * output rows: relation MLP 0..255 | connectivity MLP 256..511 | gate logit 512. */
+typedef struct {
+  int layers;            /* decoder_layers + 1, <= 7 */
+  const void* uv_planes; /* egtr_split_weight_bf16 planes of the stacked [2*layers*uv_npad, 256] weight */
+  const float* uv_bias;  /* [2*layers*uv_npad] */
+  int uv_npad;           /* rows per group in the stack (>= 513, % 64 == 0) */
+  const float* b1;       /* [512] layer-1 bias: rel_predictor.layers.0.bias | connectivity_layer.layers.0.bias */
+  const void* w2g;       /* egtr_pack_weight_p32g of [512,256]: rel_predictor.layers.1.weight | connectivity_layer.layers.1.weight */
+  const float* b2;       /* [512] */
+  const void* w3g;       /* egtr_pack_weight_p32g of rel_predictor.layers.2.weight [P,256] into p3 rows (see below) */
+  const float* b3;       /* [P] */
+  const float* w3c;      /* [256] connectivity_layer.layers.2.weight */
+  float b3c;             /* connectivity_layer.layers.2.bias */
+} egtr_relhead_weights_t;
+
+/* fp32 [N,K] rows -> bf16 "P32 group" rows for the fused kernel's TMA boxes: output row r = K/32 groups of (32 hi | 32 lo),
+ * taken from source row perm[r] (DEVICE int array; NULL: r); rows whose source is outside [0,N) are zero.  K % 32 == 0.
+ * Layer 3 (w3g): P <= 64 -> rows_out = 64 and perm[r] = 32*((r%32)/16) + 16*(r/32) + r%16 (each CTA of a pair feeds 16 rows to
+ * each of the two N = 32 MMAs); P > 64 -> rows_out = 64*ceil(P/64), no permutation. */
+int egtr_pack_weight_p32g(const float* w, int N, int K, int rows_out, const int* perm, void* out, egtr_stream_t s);
+
+/* Pair stage as ONE kernel (relhead.cu): U, V [B*N, layers, ldu] per-query partials (ldu % 4 == 0, >= 513) ->
+ * pred_rel [B,N,N,P] = sigmoid(MLP_rel(h1) + triplet_dist[cls_i, cls_j] - tau*log(rel_dist)),
+ * pred_conn [B,N,N] = sigmoid(MLP_conn(h1)), h1 = relu(b1 + sum_l sigmoid(g_l(i,j)) (U_l(i) + V_l(j))).
+ * The gated pair tensor, both hidden layers and the logits stay in shared memory / TMEM.  cls == NULL: no frequency bias;
+ * rel_dist == NULL: no logit adjustment.  k1 = row length of triplet_dist's class axes (num_labels + 1). */
+int egtr_relation_pairs_fused_f32(const float* U, const float* V, int ldu, int layers, const egtr_relhead_weights_t* w,
+                                  const int* cls, const float* triplet_dist, int k1, const float* rel_dist, float tau,
+                                  int B, int N, int P, float* pred_rel, float* pred_conn, egtr_stream_t s);
+
+/* The whole head: q_ptrs[l] / k_ptrs[l] (HOST arrays of layers-1 device pointers) are the captured decoder self-attention
+ * queries (scaled, as captured) / keys of layer l as rows [B*N, 256] with row stride ld_qk; h_last [B*N, 256] (stride ld_h) the
+ * decoder output; logits [B*N, K] the class logits (argmax -> frequency-bias classes).  Scratch: U, V [B*N*layers*516] floats,
+ * cls [B*N] ints.  Three launches: the 2*layers per-query projections, the class argmax, the fused pair kernel. */
+int egtr_relation_head_fwd_f32(const float* const* q_ptrs, const float* const* k_ptrs, int ld_qk, const float* h_last, int ld_h,
+                               const float* logits, int K, const egtr_relhead_weights_t* w, const float* triplet_dist,
+                               const float* rel_dist, float tau, int use_freq_bias, int logit_adjustment, int B, int N, int P,
+                               float* U_scratch, float* V_scratch, int* cls_scratch, float* pred_rel, float* pred_conn,
+                               egtr_stream_t s);
+
 /* ---------------------------------------------------------------- triplet extraction */
 /* Device-side equivalent of the model-output post-processing in train_egtr.py:56-94 (multiple predicates per pair,
  * single == 0) and 56-69 + 120-128 (one entry per pair, single == 1): object scores/classes from softmax(logits)

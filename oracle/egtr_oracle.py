@@ -301,7 +301,7 @@ def relation_head(sd, cfg, queries: Sequence[Tensor], keys: Sequence[Tensor], h_
 # --------------------------------------------------------------------------- whole forward
 @torch.no_grad()
 def forward(sd: StateDict, cfg, pixel_values: Tensor, pixel_mask: Optional[Tensor] = None,
-            taps: Optional[dict] = None) -> Dict[str, Tensor]:
+            taps: Optional[dict] = None, relation_row_chunk: int = 16) -> Dict[str, Tensor]:
     """DetrForSceneGraphGeneration.forward at inference (labels=None)."""
     B, _, H, W = pixel_values.shape
     d = cfg.d_model
@@ -366,7 +366,7 @@ def forward(sd: StateDict, cfg, pixel_values: Tensor, pixel_mask: Optional[Tenso
     delta[..., :2] += inverse_sigmoid(ref_pts)
     boxes = delta.sigmoid()
 
-    pred_rel, pred_con = relation_head(sd, cfg, qs, ks, h, logits)
+    pred_rel, pred_con = relation_head(sd, cfg, qs, ks, h, logits, row_chunk=relation_row_chunk)
     return dict(
         logits=logits,
         pred_boxes=boxes,
