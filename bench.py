@@ -42,7 +42,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (3x800x1333, N_q=200)"
 # BASELINE.json configs[1..4]: (label-space / image-size table of egtr_b200.config.WORKLOADS, per-GPU batch, description)
-MSDA_L1_BYTES_PER_SAMPLE = 4 * 128  # fp32 value rows [S, M, D]: every bilinear corner is its own 128-byte line
+# L1 wavefront bytes per bilinear sample: fp32 value rows [S, M, D] make every corner its own 128-byte line; the fp16 pair
+# records (EGTR_FMT_H16PAIR) put the two x-neighbours in one line
+MSDA_L1_BYTES_PER_SAMPLE = {"f32": 4 * 128, "h16": 2 * 128}
 BENCH_WORKLOADS = {
     "B": ("B", 1, "VG config, batch 1 per GPU (configs[1])"),
     "C": ("B", 4, "VG config, 32 images image-parallel over 8 GPUs = 4 per GPU (configs[2])"),
@@ -201,7 +203,9 @@ def summarize(trace, n_forwards, sms):
         t = tot[name]
         t[0] += 1
         t[1] += us
-        t[2] += us * min(1.0, ctas / sms)  # a persistent one-CTA-per-SM grid of g CTAs holds g / sms of the GPU
+        # a persistent one-CTA-per-SM grid of g CTAs holds g / sms of the GPU; other kernels (many small CTAs per SM) are charged in full
+        persistent = name.startswith(("gemm_p32_kernel", "gemm_sbf16_kernel", "relhead_kernel"))
+        t[2] += us * (min(1.0, ctas / sms) if persistent else 1.0)
         t[3] += ctas
     return {k: dict(n=v[0] / n_forwards, us=v[1] / n_forwards, us_sm_weighted=v[2] / n_forwards, avg_ctas=v[3] / max(1, v[0])) for k, v in tot.items()}
 
@@ -325,7 +329,28 @@ def main():
     # Every forward in flight must reproduce the same image's forward run alone in the latency configuration (which the GPU tests
     # pin against the reference's golden at this size).  A throughput number whose outputs deviate is not a number.
     CHECK_KEYS = ("logits", "pred_boxes", "pred_rel", "pred_connectivity")
-    chk_n, chk_bad, chk_worst, chk_error = 0, 0, 0.0, None
+    chk_n, chk_bad, chk_worst, chk_error, chk_flips = 0, 0, 0.0, None, 0
+
+    def check_err(got, want):
+        """Worst max-norm relative error over the four outputs.  A query whose arg-max class differs from the lone forward's (a
+        near-tie of its two best logits: `torch.argmax` then selects another frequency-bias row, model/egtr.py:405-413) is counted
+        in `class_flips`; it is excused — its pairs left out of pred_rel — only if the lone forward's own margin between the two
+        classes is below 2e-3 of max|logits|, otherwise the forward counts as deviating."""
+        lg, lw = got["logits"], want["logits"]
+        cg, cw = lg.argmax(-1), lw.argmax(-1)
+        flip = cg != cw
+        nflip, bad = int(flip.sum()), False
+        if nflip:
+            margin = (lw.gather(-1, cw[..., None]) - lw.gather(-1, cg[..., None])).squeeze(-1)
+            bad = bool((margin[flip] > 2e-3 * lw.abs().max()).any())
+        keep = ~(flip[:, :, None] | flip[:, None, :])
+        e = 0.0
+        for k in CHECK_KEYS:
+            d = (got[k] - want[k]).abs()
+            if k == "pred_rel":
+                d = d * keep[..., None]
+            e = max(e, float(d.max() / want[k].abs().max()))
+        return (1.0 if bad else e), nflip
     try:
         want = []
         for i in range(NIMG):
@@ -342,9 +367,8 @@ def main():
                 main_s.wait_stream(st_)
             torch.cuda.synchronize()
             for i in range(conc):
-                w_ = want[(i + r) % NIMG]
-                e = max(float((runners[i].out[k] - w_[k]).abs().max() / w_[k].abs().max()) for k in CHECK_KEYS)
-                chk_n, chk_bad, chk_worst = chk_n + 1, chk_bad + int(e > 1e-3), max(chk_worst, e)
+                e, nf = check_err(runners[i].out, want[(i + r) % NIMG])
+                chk_n, chk_bad, chk_worst, chk_flips = chk_n + 1, chk_bad + int(e > 1e-3), max(chk_worst, e), chk_flips + nf
         del want
     except Exception as exc:  # noqa: BLE001  (the check must never cost the bench line; it is reported instead)
         chk_error = repr(exc)
@@ -380,14 +404,16 @@ def main():
     t_e2e_wall = time.perf_counter() - t0
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     del pipe
-    # the round-1 boundary for continuity: fp32 pixel_values + int64 mask in, raw model outputs out
+    # the round-1 boundary for continuity (workload B only): fp32 pixel_values + int64 mask in, raw model outputs out
     px_h, mask_h = px.pin_memory(), mask.pin_memory()
-    pipe_raw = PipelinedRunner(model, Bl, H, W, depth=depth, concurrency=conc)
-    run_raw = make_e2e(pipe_raw, px_h, mask_h)
-    run_raw(args.warmup)
-    blocks_raw = timed_blocks(run_raw, args.steps)
-    raw_h2d, raw_d2h = pipe_raw.h2d_bytes, pipe_raw.d2h_bytes
-    del pipe_raw
+    blocks_raw, raw_h2d, raw_d2h = None, 0, 0
+    if args.workload == "B":
+        pipe_raw = PipelinedRunner(model, Bl, H, W, depth=depth, concurrency=conc)
+        run_raw = make_e2e(pipe_raw, px_h, mask_h)
+        run_raw(args.warmup)
+        blocks_raw = timed_blocks(run_raw, args.steps)
+        raw_h2d, raw_d2h = pipe_raw.h2d_bytes, pipe_raw.d2h_bytes
+        del pipe_raw
     clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------ eager passes: launch count, stage spans (lone forward)
@@ -423,22 +449,23 @@ def main():
         t = torch.tensor([chk_worst], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         chk_worst = float(t[0])
-        c = torch.tensor([chk_n, chk_bad], device=dev, dtype=torch.int64)
+        c = torch.tensor([chk_n, chk_bad, chk_flips], device=dev, dtype=torch.int64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        chk_n, chk_bad = int(c[0]), int(c[1])
+        chk_n, chk_bad, chk_flips = int(c[0]), int(c[1]), int(c[2])
 
     if rank == 0:
         peaks = _peaks()
         S = sum(h * w for h, w in eng._workspace(Bl, H, W)["shapes"])
         med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
         imgs = world * Bl * args.steps
-        t_res, t_e2e, t_raw = med(blocks_res), med(blocks_e2e), med(blocks_raw)
+        t_res, t_e2e, t_raw = med(blocks_res), med(blocks_e2e), (med(blocks_raw) if blocks_raw else None)
         ms_step = 1000 * t_res / args.steps
         k_timed = summarize(tr_timed, n_tr, sms) if tr_timed else {}
         k_lone = summarize(tr_lone, 4, sms) if tr_lone else {}
 
         def pick(tab, prefix):
-            ks = [k for k in tab if k.startswith(prefix)]
+            prefixes = prefix if isinstance(prefix, tuple) else (prefix,)
+            ks = [k for k in tab if k.startswith(prefixes)]
             if not ks:
                 return None
             return dict(n=sum(tab[k]["n"] for k in ks), us=sum(tab[k]["us"] for k in ks), us_w=sum(tab[k]["us_sm_weighted"] for k in ks))
@@ -449,7 +476,7 @@ def main():
             kt, kl = pick(k_timed, prefix), pick(k_lone, prefix)
             src = "CUPTI trace of the timed configuration"
             if kt is None:  # no trace: CUDA events around the launches of a lone eager forward
-                name = "msda_enc" if "32" in prefix else "msda_dec"
+                name = label
                 if name not in spans or not probe.get(name):
                     return None
                 kt = dict(n=len(probe[name]) / n_probe, us=1e6 * spans[name])
@@ -457,7 +484,7 @@ def main():
             us = kt["us"] / kt["n"]
             ach = bytes_per_launch / us / 1e3
             r = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                 "traffic": _traffic(label), "kernel": prefix, "avg_launch_us": us, "launches_per_step": kt["n"],
+                 "traffic": _traffic(label), "kernel": label + " (" + prefix[0] + "...>)", "avg_launch_us": us, "launches_per_step": kt["n"],
                  "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peaks["src"] + " (hbm_gbs)", "timing": src}
             if kl is not None:
                 us_l = kl["us"] / kl["n"]
@@ -465,15 +492,16 @@ def main():
             return r
 
         # MSDeformAttn, encoder form: SURVEY.md §8d algorithmic bytes = 4*B*[S*C + Lq*M*L*P*3 + Lq*C] = 3584*S per image
-        r_msda = hbm_roof("msda_kernel<1, 32>", 3584 * S * Bl, "msda_enc")
-        r_msda_dec = hbm_roof("msda_kernel<1, 8>", (1024 * S + 2560 * N) * Bl, "msda_dec")
+        r_msda = hbm_roof(("msda_kernel<true, 32", "msda_kernel<1, 32"), 3584 * S * Bl, "msda_enc")
+        r_msda_dec = hbm_roof(("msda_kernel<true, 8", "msda_kernel<1, 8"), (1024 * S + 2560 * N) * Bl, "msda_dec")
         if r_msda is not None:
             # the binding roof of the gather is the SM's L1 path, not HBM: one 128-byte wavefront per
             # (query, head, level, point, corner) at 128 B/clk/SM — report the fraction of THAT roof beside the HBM one
-            l1_bytes = Bl * S * 8 * 16 * MSDA_L1_BYTES_PER_SAMPLE
+            per_sample = MSDA_L1_BYTES_PER_SAMPLE[eng.msda_value]
+            l1_bytes = Bl * S * 8 * 16 * per_sample
             floor_us = l1_bytes / (sms * 128.0 * (clocks["sm_mhz"] or 1965.0 if clocks else 1965.0) * 1e6) * 1e6
             r_msda["l1_roof"] = {"bytes_through_l1_per_launch": l1_bytes, "floor_us": floor_us, "frac": floor_us / r_msda["avg_launch_us"],
-                                 "note": f"{MSDA_L1_BYTES_PER_SAMPLE} B of L1 wavefronts per bilinear sample"}
+                                 "note": f"{per_sample} B of L1 wavefronts per bilinear sample (value layout: {eng.msda_value})"}
         # relation head (a13-a16): algorithmic HBM bytes per image: Q/K/h in 13*N*1024, logits 4NK, freq-bias
         # gather min(4N^2P, 4(K+1)^2P), outputs 4N^2(P+1), weights ~5.3 MB once; FLOPs as written in the reference
         rel_bytes = Bl * (13 * N * 1024 + 4 * N * K + min(4 * N * N * P, 4 * (K + 1) ** 2 * P) + 4 * N * N * (P + 1)) + 5.3e6
@@ -518,7 +546,7 @@ def main():
                       "kernel": "gemm_p32_kernel (all launches of a forward)", "launches_per_forward": kt["n"],
                       "avg_launch_us": kt["us"] / kt["n"], "avg_launch_us_sm_weighted": kt["us_w"] / kt["n"],
                       "kernel_ms_per_step_sm_weighted": kt["us_w"] / 1e3, "ms_per_step": ms_step,
-                      "algorithmic_flops_per_forward": gemm_flops, "share_of_step_sm_time": kt["us_w"] / total_w,
+                      "algorithmic_flops_per_forward": gemm_flops, "share_of_kernel_sm_time": kt["us_w"] / total_w,
                       "executed_bf16_tflops": 3 * ach, "frac_executed_bf16": 3 * ach / peaks["bf16_sustained"],
                       "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernels timed inside a long step)",
                       "timing": "CUPTI trace (torch.profiler) of the TIMED configuration: graph replays, forwards in flight; a launch's "
@@ -567,11 +595,12 @@ def main():
             "e2e": {"value": imgs / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * t_e2e / args.steps, "blocks": len(blocks_e2e), "value_best_block": imgs / min(blocks_e2e),
                     "wall_s_all_blocks": t_e2e_wall, "boundary": "uint8 RGB images [B,H,W,3] in (staged on the device), triplet records out"},
-            "e2e_raw": {"value": imgs / t_raw, "unit": "images/s", "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
-                        "ms_per_step": 1000 * t_raw / args.steps,
-                        "boundary": "fp32 pixel_values + int64 pixel_mask in, logits / pred_boxes / pred_rel / pred_connectivity out (the round-1 e2e)"},
+            "e2e_raw": None if t_raw is None else {
+                "value": imgs / t_raw, "unit": "images/s", "h2d_bytes_per_step": raw_h2d, "d2h_bytes_per_step": raw_d2h,
+                "ms_per_step": 1000 * t_raw / args.steps,
+                "boundary": "fp32 pixel_values + int64 pixel_mask in, logits / pred_boxes / pred_rel / pred_connectivity out (the round-1 e2e)"},
             "gpu_launches": launches,
-            "output_check": {"forwards_checked": chk_n, "deviating": chk_bad, "worst_rel_err": chk_worst, "tolerance": 1e-3,
+            "output_check": {"forwards_checked": chk_n, "deviating": chk_bad, "worst_rel_err": chk_worst, "tolerance": 1e-3, "class_flips": chk_flips,
                              "what": f"{conc} forwards in flight (the timed configuration) vs the same images run alone, max-norm relative error "
                                      "over logits / boxes / pred_rel / pred_connectivity, all ranks", "error": chk_error},
             "roofline": r_gemm if r_gemm is not None else r_msda, "roofline_msda_enc": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,

@@ -39,7 +39,7 @@ class RelheadWeights(C.Structure):
                 ("w3c", C.c_void_p), ("b3c", C.c_float)]
 
 
-FMT_F32, FMT_P32 = 0, 1
+FMT_F32, FMT_P32, FMT_H16PAIR = 0, 1, 2
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -70,6 +70,7 @@ SIGNATURES = {
     "egtr_rows_to_p32": [_p, _p, _i, _i, _i, _p, _p],
     "egtr_p32_to_rows": [_p, _i, _i, _p, _i, _p],
     "egtr_msda_fused_fwd_ex": [_p, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "egtr_msda_fused_fwd_h16": [_p, _ll, _i, _i, C.POINTER(_i), _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "egtr_mask_rows_f32": [_p, _i, _i, _p, _i, _p],
     "egtr_pad_nchw3_to_nhwc4_f32": [_p, _i, _i, _i, _i, _p, _p],
     "egtr_maxpool3x3s2_nhwc_f32": [_p, _i, _i, _i, _i, _p, _p],

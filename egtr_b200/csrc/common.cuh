@@ -32,6 +32,9 @@ void set_last_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int num_sms();
+int bound_device_ok();  // runtime.cu: 1 when the current device is the one this process first used the library on
+#define EGTR_ONE_DEVICE() \
+  EGTR_CHECK(::egtr::bound_device_ok(), EGTR_ERR_UNSUPPORTED, "libegtr_b200 drives one GPU per process: the current CUDA device is not the one first used")
 int splitk_max();  // runtime.cu: egtr_set_splitk_max / EGTR_GEMM_SPLITK_MAX
 int grid_div();    // runtime.cu: egtr_set_grid_div / EGTR_GEMM_GRID_DIV
 int balanced_grid(long long work, int slots);  // runtime.cu: smallest grid <= slots that needs no more rounds of tiles

@@ -27,6 +27,8 @@
 #include <string.h>
 #include <unordered_map>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -591,6 +593,33 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
+        if (p.out_fmt == 2) {
+          // H16 pair records (include/egtr_b200.h): this chunk = 32 tokens x one head; the 64-byte fp16 row of token t goes to
+          // slot 0 of record t + 1 and to slot 1 of record t — two TMA stores of the same staging box (SWIZZLE_64B rows)
+          uint32_t hh[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            hh[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          const uint32_t row_s = stg_s + lane * 64;
+          const int sw2 = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_s + ((c ^ sw2) << 4)), "r"(hh[4 * c]), "r"(hh[4 * c + 1]),
+                         "r"(hh[4 * c + 2]), "r"(hh[4 * c + 3]) : "memory");
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int head = zc * (p.ncols >> 5) + (n >> 5);
+            tma_store_4d(&tmap_out, stg_s, 0, 0, ow + 1, head);
+            tma_store_4d(&tmap_out, stg_s, 0, 1, ow, head);
+            bulk_commit();
+          }
+          continue;
+        }
         uint32_t o[32];
         if (p.out_fmt == 0) {
 #pragma unroll
@@ -748,6 +777,7 @@ struct MapDesc {  // everything that determines a tensor map (POD, zero-initiali
   unsigned long long dim[4], stride[3];
   unsigned box[4], estr[4];
   int dtype, rank;
+  int swizzle64;  // 0: SWIZZLE_128B (every operand / fp32 / P32 map), 1: SWIZZLE_64B (the 64-byte rows of the H16 pair-record output)
 };
 struct MapDescHash {
   size_t operator()(const MapDesc& d) const {
@@ -782,11 +812,13 @@ int cached_map(const MapDesc& d, CUtensorMap* out) {
   const CUtensorMapL2promotion promo = l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                        : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(&m, (CUtensorMapDataType)d.dtype, (cuuint32_t)d.rank, const_cast<void*>(d.ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, d.swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA,
              "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u)",
              (int)r, d.rank, d.dim[0], d.dim[1], d.dim[2], d.dim[3], d.stride[0], d.stride[1], d.stride[2], d.box[0], d.box[1],
              d.box[2], d.box[3]);
+  if (cache.size() >= (1u << 15)) cache.clear();  // bounded: maps are passed to kernels by value, re-encoding is cheap
   cache.emplace(d, m);
   *out = m;
   return EGTR_OK;
@@ -825,7 +857,10 @@ int* device_error_flag_p32() {
   return flag;
 }
 
-float* partial_buffer_p32(size_t floats) {  // grow-only per scratch slot; older buffers stay alive for captured graphs
+// Grow-only per scratch slot.  A replaced buffer is NOT freed: CUDA graphs captured earlier hold its address.  Growth is geometric
+// (x1.5 over the request), so everything ever left behind by a slot sums to less than twice its final capacity — bounded by the
+// largest shape the process sees, not by the number of shapes.
+float* partial_buffer_p32(size_t floats) {
   static float* buf[32] = {};
   static size_t cap[32] = {};
   const int slot = scratch_slot();
@@ -889,7 +924,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     if (splits > splitk_cap) splits = splitk_cap;
     if (splits < 1) splits = 1;
   }
-  if (WS || ep.ln_gamma != nullptr) splits = 1;  // (the LayerNorm epilogue needs the complete row sums in one tile)
+  if (WS || ep.ln_gamma != nullptr || ep.out_fmt == EGTR_FMT_H16PAIR) splits = 1;  // (the LayerNorm epilogue needs the complete row sums in one tile)
   const int kbps = cdiv(k_blocks, splits);
   splits = cdiv(k_blocks, kbps);
   p.splits = splits; p.kb_per_split = kbps;
@@ -925,8 +960,16 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     const unsigned long long bstride = ep.rows_per_b > 0 ? (unsigned long long)ep.bstride : (unsigned long long)rows_per_b;
     const uint8_t* obase = (const uint8_t*)ep.out + 4ll * ep.off * ep.ldo;
     const unsigned long long opitch = 4ull * ep.ldo;
-    rc = cached_map(desc4(obase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, out_w, out_h, p.nb, opitch, opitch * out_w, opitch * bstride, 32,
-                          box_w, box_h), &to);
+    if (ep.out_fmt == EGTR_FMT_H16PAIR) {
+      // [nb * N/32 heads][rows_per_b + 1 records][2 slots][32 fp16]: box = 32 records of one slot
+      MapDesc d = desc4(ep.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 32, 2, (unsigned long long)rows_per_b + 1,
+                        (unsigned long long)p.nb * (N / 32), 64, 128, 128ull * (rows_per_b + 1), 32, 1, 32);
+      d.swizzle64 = 1;
+      rc = cached_map(d, &to);
+    } else {
+      rc = cached_map(desc4(obase, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, N, out_w, out_h, p.nb, opitch, opitch * out_w, opitch * bstride, 32,
+                            box_w, box_h), &to);
+    }
     if (rc != EGTR_OK) return rc;
     tr = to;
     if (ep.res != nullptr) {
@@ -991,6 +1034,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
 // Entry used by egtr_gemm_sbf16 when the operand source is P32 (a.fmt == 1): mode 0 rows or mode 1 NHWC convolution.
 int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                       cudaStream_t st) {
+  EGTR_ONE_DEVICE();
   EGTR_CHECK(a.a2 == nullptr && (a.mode == 0 || a.mode == 1), EGTR_ERR_UNSUPPORTED,
              "P32 operand: plain rows or NHWC convolution only (fold addends into the producer)");
   EGTR_CHECK(N % 32 == 0 && K % 64 == 0 && ep.ldo % 4 == 0 && ep.ldo >= N, EGTR_ERR_ARG,
@@ -1007,6 +1051,8 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
              EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32): 128-byte aligned buffers required");
   EGTR_CHECK(!ep.res || (ep.ldr % 4 == 0 && ep.ldr >= N), EGTR_ERR_ARG, "egtr_gemm_sbf16 (P32): ldr=%d", ep.ldr);
   EGTR_CHECK(ep.pair_n == 0 && !ep.fin && !ep.dot_w, EGTR_ERR_UNSUPPORTED, "egtr_gemm_sbf16 (P32): relation epilogues are not built here");
+  EGTR_CHECK(ep.out_fmt != EGTR_FMT_H16PAIR || (a.mode == 0 && !ep.res && !ep.ln_gamma && ep.rows_per_b <= 0 && !ep.relu), EGTR_ERR_UNSUPPORTED,
+             "egtr_gemm_sbf16 (P32): H16 pair-record output takes plain rows (one batch = M rows), bias and row_keep only");
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   int bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N >= 192 ? 128 : 64));
   if (bn == 256) {

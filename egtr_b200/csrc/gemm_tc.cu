@@ -662,6 +662,7 @@ int weight_tensor_map(const void* planes, int Npad, int K, int block_n, CUtensor
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (cache.size() >= (1u << 15)) cache.clear();  // bounded: maps are passed to kernels by value, re-encoding is cheap
   cache.emplace(key, m);
   *out = m;
   return EGTR_OK;
@@ -784,6 +785,7 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, i
 // only where the epilogue descriptor asks for them.
 int dispatch(const ASrc& a, const void* planes, int M, int N, int Npad, int K, const Epilogue& ep, cudaStream_t st, int groups,
              int plane_rows, const GroupTab* gtab) {
+  EGTR_ONE_DEVICE();
   static const int forced_bn = [] { const char* e = getenv("EGTR_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // dev experiments only
   int bn = (Npad % 256 == 0) ? 256 : (Npad % 128 == 0 ? 128 : 64);
   if (forced_bn == 64 || (forced_bn == 128 && Npad % 128 == 0)) bn = forced_bn;

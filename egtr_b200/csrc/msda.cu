@@ -15,6 +15,8 @@
 //            16-lane shuffles, turn each sample into 4 corner offsets (32-bit elements) + 4 combined weights in smem;
 //   phase 2: 32 groups of 8 lanes: stream the 16 samples of one query, 4 LDG.128 each (unconditional in the fused form:
 //            absent corners carry weight 0 and point at token 0).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace egtr {
@@ -45,6 +47,10 @@ struct MsdaArgs {
   int out_fmt;                            // 1: P32 rows (one head = one 32-channel group: hi 64 B | lo 64 B)
   int B, S, M, Lq;
   int enc_patches;                        // 1: queries are the S tokens, enumerated in 8x4 patches
+  // H16 form: value as fp16 pair records [heads][records][2 slots][32] (include/egtr_b200.h, EGTR_FMT_H16PAIR)
+  const uint8_t* value_h16;
+  long long h16_records;                  // records per head = B*S + 1
+  int head0;                              // first head of this launch inside the record tensor (decoder: layer * M)
 };
 
 // QPB queries per CTA, 8 threads each: 32 for the encoder's 8x4 pixel patches, 8 for the decoder's few hundred queries
@@ -59,7 +65,7 @@ constexpr int kMsdaUnroll = EGTR_MSDA_UNROLL;
 #ifndef EGTR_MSDA_ENC_QPB  // encoder patch: 32 = 8x4 pixels (256 threads), 64 = 8x8 pixels (512 threads)
 #define EGTR_MSDA_ENC_QPB 32
 #endif
-template <bool FUSED, int QPB, bool BYPASS_L1 = false>
+template <bool FUSED, int QPB, bool BYPASS_L1 = false, bool H16 = false>
 __global__ void __launch_bounds__(QPB * 8, QPB == 32 ? EGTR_MSDA_MINB : (QPB == 64 ? EGTR_MSDA_MINB / 2 : 8))
 msda_kernel(const MsdaArgs a, const Levels lv_in) {
   pdl_entry();
@@ -180,13 +186,25 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
         const float hh = 1.f - lh, hw = 1.f - lw;
         // corners are stored as 32-bit ELEMENT offsets into this image's value rows (token * row stride; the host entry points
         // guarantee S * ld_value < 2^31), so phase 2 forms each gather address with one IMAD.WIDE instead of a 64-bit multiply
-        const int ld = a.ld_value;
-        const int base_off = (lvS[l] + hl * W + wl) * ld;
         const bool y0 = hl >= 0, y1 = hl + 1 <= H - 1, x0 = wl >= 0, x1 = wl + 1 <= W - 1;
-        if (y0 && x0) { idx[0] = base_off;               cw[0] = hh * hw * wgt; }
-        if (y0 && x1) { idx[1] = base_off + ld;          cw[1] = hh * lw * wgt; }
-        if (y1 && x0) { idx[2] = base_off + W * ld;      cw[2] = lh * hw * wgt; }
-        if (y1 && x1) { idx[3] = base_off + W * ld + ld; cw[3] = lh * lw * wgt; }
+        if (H16) {
+          // pair records: tokens (t, t+1) of one map row are record t + 1 (wl = -1 -> the record whose slot 1 is the row's
+          // first token); idx[0] / idx[1] = records of the top / bottom row, cw = (top-left, top-right, bottom-left, bottom-right)
+          const int rec = b * a.S + lvS[l] + hl * W + wl + 1;
+          if (y0) idx[0] = rec;
+          if (y1) idx[1] = rec + W;
+          if (y0 && x0) cw[0] = hh * hw * wgt;
+          if (y0 && x1) cw[1] = hh * lw * wgt;
+          if (y1 && x0) cw[2] = lh * hw * wgt;
+          if (y1 && x1) cw[3] = lh * lw * wgt;
+        } else {
+          const int ld = a.ld_value;
+          const int base_off = (lvS[l] + hl * W + wl) * ld;
+          if (y0 && x0) { idx[0] = base_off;               cw[0] = hh * hw * wgt; }
+          if (y0 && x1) { idx[1] = base_off + ld;          cw[1] = hh * lw * wgt; }
+          if (y1 && x0) { idx[2] = base_off + W * ld;      cw[2] = lh * hw * wgt; }
+          if (y1 && x1) { idx[3] = base_off + W * ld + ld; cw[3] = lh * lw * wgt; }
+        }
       }
     }
     *(int4*)slot = make_int4(idx[0], idx[1], idx[2], idx[3]);
@@ -198,6 +216,53 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
   const int g = tid >> 3, c4 = (tid & 7) * 4;
   const int q = q_of[g];
   if (q < 0) return;
+  if constexpr (H16) {
+    // 8 lanes per query: lanes 0-3 read slot 0 (the left corner), lanes 4-7 slot 1 (the right corner) of the SAME 128-byte
+    // record — one L1 wavefront per row of the bilinear footprint; lane j & 3 owns channels 8j .. 8j+7
+    const int half = (tid >> 2) & 1, j8 = (tid & 3) * 8;
+    const uint8_t* hb = a.value_h16 + ((long long)(a.head0 + m) * a.h16_records) * 128 + half * 64 + j8 * 2;
+    unsigned long long vb;
+    asm("mov.b64 %0, %1;" : "=l"(vb) : "l"(hb));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* myslots = &slots[g * Q_STRIDE];
+#pragma unroll (QPB >= 32 ? kMsdaUnroll : 8)
+    for (int ss = 0; ss < 16; ++ss) {
+      const int2 id = *(const int2*)(myslots + ss * SLOT_WORDS);
+      const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
+      const float wt = half ? w.y : w.x, wb = half ? w.w : w.z;
+      const uint4 t4 = __ldg((const uint4*)(vb + (unsigned long long)(uint32_t)id.x * 128ull));
+      const uint4 b4 = __ldg((const uint4*)(vb + (unsigned long long)(uint32_t)id.y * 128ull));
+      const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&tw[k]));
+        const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+        acc[2 * k] = fmaf(wt, tf.x, acc[2 * k]); acc[2 * k + 1] = fmaf(wt, tf.y, acc[2 * k + 1]);
+        acc[2 * k] = fmaf(wb, bf.x, acc[2 * k]); acc[2 * k + 1] = fmaf(wb, bf.y, acc[2 * k + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffu << (threadIdx.x & 24), acc[k], 4);  // left + right corners (lanes j, j + 4 of this query's 8; other queries of the warp may have exited)
+    float* orow = a.out + ((long long)b * a.Lq + q) * (a.M * 32) + m * 32;
+    if (a.out_fmt == 0) {
+      *(float4*)(orow + j8 + half * 4) = half ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {  // P32 row: lanes 0-3 store the hi halves (16 B each), lanes 4-7 the lo halves 64 bytes further
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+        const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+        if (half) {
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(acc[2 * k] - __uint_as_float(hbits << 16), acc[2 * k + 1] - __uint_as_float(hbits & 0xffff0000u));
+          o[k] = *reinterpret_cast<const uint32_t*>(&l2);
+        } else {
+          o[k] = hbits;
+        }
+      }
+      *(uint4*)((uint8_t*)orow + half * 64 + j8 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
   const float* vbase = a.value + (long long)b * a.S * a.ld_value + m * 32 + c4;
   // keep the per-thread base opaque in one register pair: address = IMAD.WIDE.U32(offset, 4, base), one instruction per gather
   // (left to itself the compiler re-associates base = uniform pointer + 64-bit element offset: four instructions per address)
@@ -325,6 +390,45 @@ extern "C" int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const in
   } else {
     dim3 grid(cdiv(Lq, 32), M, B);
     launch_pdl(msda_kernel<true, 32>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
+  }
+  count_launch();
+  EGTR_CUDA(cudaGetLastError());
+  return EGTR_OK;
+}
+
+extern "C" int egtr_msda_fused_fwd_h16(const void* value_h16, long long records, int head0, int heads_total, const int* shapes_hw,
+                                       const float* offaw, int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                                       int B, int S, int M, int D, int L, int Lq, int P, void* out_v, int out_fmt, egtr_stream_t s) {
+  float* out = (float*)out_v;
+  EGTR_CHECK(value_h16 && shapes_hw && offaw && out, EGTR_ERR_ARG, "egtr_msda_fused_fwd_h16: null pointer");
+  EGTR_CHECK(valid_ratios != nullptr && (enc_ref || ref_points != nullptr), EGTR_ERR_ARG, "egtr_msda_fused_fwd_h16: reference points missing");
+  EGTR_CHECK(D == 32 && L * P == 16 && P == 4 && L <= MAX_L, EGTR_ERR_UNSUPPORTED,
+             "egtr_msda_fused_fwd_h16: built for head_dim 32 and L*P = 4*4 (got D=%d L=%d P=%d)", D, L, P);
+  EGTR_CHECK(records == (long long)B * S + 1 && records < (1LL << 25) && head0 >= 0 && head0 + M <= heads_total, EGTR_ERR_ARG,
+             "egtr_msda_fused_fwd_h16: records must be B*S + 1 (< 2^25), heads [%d, %d) of %d", head0, head0 + M, heads_total);
+  EGTR_CHECK(((uintptr_t)value_h16 & 127) == 0 && ld_offaw >= M * L * P * 3 && ld_offaw % 2 == 0, EGTR_ERR_ARG,
+             "egtr_msda_fused_fwd_h16: alignment / leading dimension");
+  EGTR_CHECK(B <= 65535 && M <= 65535, EGTR_ERR_ARG, "egtr_msda_fused_fwd_h16: grid limits");
+  Levels lv = {};
+  int S_chk = 0;
+  constexpr int kEncQ = EGTR_MSDA_ENC_QPB;
+  const int patches = fill_levels(shapes_hw, L, &lv, &S_chk, kEncQ / 8);
+  EGTR_CHECK(S_chk == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_h16: sum(H*W)=%d != S=%d", S_chk, S);
+  EGTR_CHECK(!enc_ref || Lq == S, EGTR_ERR_ARG, "egtr_msda_fused_fwd_h16: encoder form needs Lq == S");
+  MsdaArgs a = {};
+  a.value_h16 = (const uint8_t*)value_h16; a.h16_records = records; a.head0 = head0;
+  a.offaw = offaw; a.ld_offaw = ld_offaw;
+  a.ref_points = ref_points; a.valid_ratios = valid_ratios;
+  a.out = out; a.out_fmt = out_fmt; a.B = B; a.S = S; a.M = M; a.Lq = Lq; a.enc_patches = enc_ref ? 1 : 0;
+  if (!enc_ref && (long long)Lq * B <= 4096) {
+    dim3 grid(cdiv(Lq, 8), M, B);
+    launch_pdl(msda_kernel<true, 8, false, true>, dim3(grid), dim3(64), (size_t)(0), (cudaStream_t)s, a, lv);
+  } else if (enc_ref) {
+    dim3 grid(patches, M, B);
+    launch_pdl(msda_kernel<true, kEncQ, false, true>, dim3(grid), dim3(kEncQ * 8), (size_t)(0), (cudaStream_t)s, a, lv);
+  } else {
+    dim3 grid(cdiv(Lq, 32), M, B);
+    launch_pdl(msda_kernel<true, 32, false, true>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)s, a, lv);
   }
   count_launch();
   EGTR_CUDA(cudaGetLastError());

@@ -36,28 +36,35 @@ void count_launch();
 namespace {
 
 constexpr int RH_THREADS = 576;
-constexpr int EPI_WARPS = 8, PROD_WARP0 = 8, TMA_WARP = 16, MMA_WARP = 17;
-constexpr int SW = 4;   // layer-2 weight stages (16 KB each: this CTA's 128 weight rows x one 32-channel group)
-constexpr int SH = 3;   // h1 operand stages (16 KB each: 128 pairs x one 32-channel group, hi 64 B | lo 64 B per row)
-constexpr int SU = 3;   // U/V staging buffers
+constexpr int PROD_WARP0 = 8, TMA_WARP = 16, MMA_WARP = 17;
+constexpr int MAX_SW = 4, MAX_SH = 3, MAX_SU = 3;  // barrier arrays are sized for the larger variant
 constexpr int TILE_BYTES = 128 * 128;
-constexpr int W3_BYTES = 32 * 128;  // this CTA's 32 layer-3 weight rows x one group
 constexpr int U_ROWS = 8, V_ROWS = 16, MAX_LR = 7;
 constexpr int UV_BYTES = (U_ROWS + V_ROWS) * MAX_LR * 128;
 constexpr int GROUPS = 8;  // 32-channel groups per 256-wide MLP input
 
-// shared memory map (offsets from a 1024-aligned base)
-constexpr int OFF_W2 = 0;
-constexpr int OFF_H1 = OFF_W2 + SW * TILE_BYTES;
-constexpr int OFF_H2 = OFF_H1 + SH * TILE_BYTES;
-constexpr int OFF_W3 = OFF_H2 + 2 * TILE_BYTES;
-constexpr int OFF_UV = OFF_W3 + 2 * W3_BYTES;
-constexpr int OFF_GATE = OFF_UV + SU * UV_BYTES;      // [128 rows][8] gate values of the current item
-constexpr int OFF_XCH = OFF_GATE + 128 * 8 * 4;       // [2][8 warps][32] connectivity partial dots
-constexpr int OFF_B3 = OFF_XCH + 2 * 8 * 32 * 4;      // [64] b3 - tau log rel_dist
-constexpr int OFF_BAR = OFF_B3 + 64 * 4;
-constexpr int RH_SMEM = OFF_BAR + 512 + 1024 /*align slack*/;
-static_assert(RH_SMEM <= 227 * 1024, "shared memory budget");
+// BIG == false: P <= 64.  Two 256-column layer-2 accumulators in TMEM (the epilogue of item k overlaps the MMAs of item k + 1); the
+//   layer-3 accumulators (two N = 32 halves) alias the already drained columns [0,32) and [128,160) of the item's own buffer.
+// BIG == true: 64 < P <= 256 (stress config E: 200 predicates).  One layer-2 accumulator (columns 0..255) and one layer-3
+//   accumulator of P3 = 64 * ceil(P / 64) columns (256..); layer 3 is one N = P3 MMA per k-step, its weight stage P3 / 2 rows per CTA.
+template <bool BIG>
+struct RhCfg {
+  static constexpr int SW = BIG ? 3 : 4;   // layer-2 weight stages (16 KB each: this CTA's 128 weight rows x one 32-channel group)
+  static constexpr int SH = 3;             // h1 operand stages (16 KB each: 128 pairs x one group, hi 64 B | lo 64 B per row)
+  static constexpr int SU = BIG ? 2 : 3;   // U/V staging buffers
+  static constexpr int W3_BYTES = BIG ? 128 * 128 : 32 * 128;  // this CTA's layer-3 weight rows x one group
+  static constexpr int OFF_W2 = 0;
+  static constexpr int OFF_H1 = OFF_W2 + SW * TILE_BYTES;
+  static constexpr int OFF_H2 = OFF_H1 + SH * TILE_BYTES;
+  static constexpr int OFF_W3 = OFF_H2 + 2 * TILE_BYTES;
+  static constexpr int OFF_UV = OFF_W3 + 2 * W3_BYTES;
+  static constexpr int OFF_GATE = OFF_UV + SU * UV_BYTES;    // [128 rows][8] gate values of the current item
+  static constexpr int OFF_XCH = OFF_GATE + 128 * 8 * 4;     // [2][8 warps][32] connectivity partial dots
+  static constexpr int OFF_B3 = OFF_XCH + 2 * 8 * 32 * 4;    // [P3] b3 - tau log rel_dist
+  static constexpr int OFF_BAR = OFF_B3 + (BIG ? 256 : 64) * 4;
+  static constexpr int SMEM = OFF_BAR + 512 + 1024 /*align slack*/;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 
 struct RelArgs {
   const float* U;        // [B*N, Lr, ldu]  subject-side partials: rel 0..255 | conn 256..511 | gate logit at 512
@@ -74,6 +81,7 @@ struct RelArgs {
   float b3c, tau;
   int B, N, P, Lr, ldu, k1;
   int tiles_i, tiles_j;  // pair tiles per image (16 x 16)
+  int P3;                // BIG: layer-3 columns, 64 * ceil(P / 64)
 };
 
 struct Item {
@@ -93,33 +101,47 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {  // low 16 bi
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
-// (x0, x1) + (y0, y1) in one FADD2
-__device__ __forceinline__ float2 add2(float2 x, float2 y) {
-  unsigned long long a, b, r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x.x), "f"(x.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(y.x), "f"(y.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  float2 o;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
-  return o;
+// packed f32x2 arithmetic (Blackwell FADD2 / FFMA2) on 64-bit register pairs: low word = first element
+__device__ __forceinline__ unsigned long long pack_f32x2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long x, unsigned long long y) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long x, unsigned long long y, unsigned long long z) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  return r;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(RH_THREADS, 1)
 relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_w3,
                const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v, const RelArgs a,
                int* __restrict__ err) {
   pdl_launch_dependents();
+  using Cfg = RhCfg<BIG>;
+  constexpr int SW = Cfg::SW, SH = Cfg::SH, SU = Cfg::SU, W3_BYTES = Cfg::W3_BYTES;
+  constexpr int OFF_W2 = Cfg::OFF_W2, OFF_H1 = Cfg::OFF_H1, OFF_H2 = Cfg::OFF_H2, OFF_W3 = Cfg::OFF_W3, OFF_UV = Cfg::OFF_UV;
+  constexpr int OFF_GATE = Cfg::OFF_GATE, OFF_XCH = Cfg::OFF_XCH, OFF_B3 = Cfg::OFF_B3, OFF_BAR = Cfg::OFF_BAR;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_s = ptx::smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
-  uint64_t* w_full = bars;             // [SW]  leader: both CTAs' weight boxes of the stage have landed
-  uint64_t* w_empty = w_full + SW;     // [SW]  the MMAs that read the stage have completed (commit, both CTAs)
-  uint64_t* h1_full = w_empty + SW;    // [SH]  leader: 16 producer warps of the pair have stored the stage
-  uint64_t* h1_empty = h1_full + SH;   // [SH]
-  uint64_t* uv_full = h1_empty + SH;   // [SU]  local
-  uint64_t* uv_empty = uv_full + SU;   // [SU]  local: 8 producer warps
-  uint64_t* l2_full = uv_empty + SU;   // [2]   layer-2 accumulator of buffer b complete (commit, both CTAs)
+  uint64_t* w_full = bars;                 // [SW]  leader: both CTAs' weight boxes of the stage have landed
+  uint64_t* w_empty = w_full + MAX_SW;     // [SW]  the MMAs that read the stage have completed (commit, both CTAs)
+  uint64_t* h1_full = w_empty + MAX_SW;    // [SH]  leader: 16 producer warps of the pair have stored the stage
+  uint64_t* h1_empty = h1_full + MAX_SH;   // [SH]
+  uint64_t* uv_full = h1_empty + MAX_SH;   // [SU]  local
+  uint64_t* uv_empty = uv_full + MAX_SU;   // [SU]  local: 8 producer warps
+  uint64_t* l2_full = uv_empty + MAX_SU;   // [2]   layer-2 accumulator of buffer b complete (commit, both CTAs)
   uint64_t* acc_free = l2_full + 2;    // [2]   leader: 16 epilogue warps have read everything they need from buffer b
   uint64_t* h2_full = acc_free + 2;    // [2]   leader: restaged hidden group (8 warps of the pair) + layer-3 weights (tx)
   uint64_t* h2_empty = h2_full + 2;    // [2]
@@ -210,8 +232,9 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
           const int set = c3 & 1, use = c3 >> 1;
           if (ptx::mbar_try_wait(&h2_empty[set], (use & 1) ^ 1)) {
             const int group = set * 4 + (use & 3);
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&h2_full[set], 2 * W3_BYTES);
-            ptx::tma_load_2d_2cta(smem_s + OFF_W3 + set * W3_BYTES, &tmap_w3, &h2_full[set], group * 64, rank * 32);
+            const int rows3 = BIG ? a.P3 / 2 : 32;  // layer-3 weight rows this CTA stages (the map's box height)
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&h2_full[set], 2 * rows3 * 128);
+            ptx::tma_load_2d_2cta(smem_s + OFF_W3 + set * W3_BYTES, &tmap_w3, &h2_full[set], group * 64, rank * rows3);
             ++c3;
             progress = true;
           }
@@ -224,33 +247,50 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
     // ------------------------------------------------------------------ MMA issue (leader CTA)
     if (rank == 0) {
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(256, 256);
-      constexpr uint32_t idesc3 = ptx::umma_idesc_bf16(256, 32);
-      int n = 0, u3[2] = {0, 0};
+      const uint32_t idesc3 = BIG ? ptx::umma_idesc_bf16(256, a.P3) : ptx::umma_idesc_bf16(256, 32);
+      int n = 0, u3[2] = {0, 0}, n_l3 = 0;
       int prev_rel = 0, prev_buf = 0;
-      // layer 3 of the previous relation item, one 32-channel group per step, in the order the two column sets restage them
+      // layer 3 of a relation item, one 32-channel group of the hidden layer per step, in the order the two column sets restage them
       auto l3_step = [&](int idx) {
         const int set = idx & 1;
-        if (idx == 0) {  // columns [0,32) and [128,160) of the buffer are overwritten: both first chunks must be drained
-          ptx::mbar_wait(&h2_full[0], u3[0] & 1, err, 311);
-          ptx::mbar_wait(&h2_full[1], u3[1] & 1, err, 312);
-        } else if (idx >= 2) {
+        if (idx == 0) {
+          if (BIG) {  // the layer-3 accumulator is its own buffer: the previous relation item's result has been read
+            ptx::mbar_wait(&acc_free[1], (n_l3 & 1) ^ 1, err, 317);
+            ptx::mbar_wait(&h2_full[0], u3[0] & 1, err, 311);
+          } else {    // columns [0,32) and [128,160) of the item's buffer are overwritten: both first chunks must be drained
+            ptx::mbar_wait(&h2_full[0], u3[0] & 1, err, 311);
+            ptx::mbar_wait(&h2_full[1], u3[1] & 1, err, 312);
+          }
+        } else if (idx >= 2 || BIG) {
           ptx::mbar_wait(&h2_full[set], u3[set] & 1, err, 313);
         }
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t a0 = smem_s + OFF_H2 + set * TILE_BYTES, b0 = smem_s + OFF_W3 + set * W3_BYTES;
-          const uint32_t d0 = tmem_base + prev_buf * 256;
+          if (BIG) {
+            const uint32_t d = tmem_base + 256;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t dah = ptx::umma_desc_sw128(a0 + j * 32), dal = ptx::umma_desc_sw128(a0 + j * 32 + 64);
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint32_t bb = b0 + hf * 2048 + j * 32;
-              const uint64_t dbh = ptx::umma_desc_sw128(bb), dbl = ptx::umma_desc_sw128(bb + 64);
-              const uint32_t d = d0 + hf * 128;
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t dah = ptx::umma_desc_sw128(a0 + j * 32), dal = ptx::umma_desc_sw128(a0 + j * 32 + 64);
+              const uint64_t dbh = ptx::umma_desc_sw128(b0 + j * 32), dbl = ptx::umma_desc_sw128(b0 + j * 32 + 64);
               ptx::umma_bf16_2cta(d, dal, dbh, idesc3, (idx != 0) || (j != 0));
               ptx::umma_bf16_2cta(d, dah, dbl, idesc3, 1);
               ptx::umma_bf16_2cta(d, dah, dbh, idesc3, 1);
+            }
+          } else {
+            const uint32_t d0 = tmem_base + prev_buf * 256;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t dah = ptx::umma_desc_sw128(a0 + j * 32), dal = ptx::umma_desc_sw128(a0 + j * 32 + 64);
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint32_t bb = b0 + hf * 2048 + j * 32;
+                const uint64_t dbh = ptx::umma_desc_sw128(bb), dbl = ptx::umma_desc_sw128(bb + 64);
+                const uint32_t d = d0 + hf * 128;
+                ptx::umma_bf16_2cta(d, dal, dbh, idesc3, (idx != 0) || (j != 0));
+                ptx::umma_bf16_2cta(d, dah, dbl, idesc3, 1);
+                ptx::umma_bf16_2cta(d, dah, dbh, idesc3, 1);
+              }
             }
           }
           ptx::umma_commit_2cta(&h2_empty[set]);
@@ -258,11 +298,12 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
         }
         __syncwarp();
         ++u3[set];
+        if (idx == 7) ++n_l3;
       };
       for (int k = 0; k < n_items; ++k) {
         const int w = me + k * slots;
-        const int buf = k & 1;
-        ptx::mbar_wait(&acc_free[buf], ((k >> 1) & 1) ^ 1, err, 314);
+        const int buf = BIG ? 0 : (k & 1);
+        ptx::mbar_wait(&acc_free[buf], (BIG ? (k & 1) : ((k >> 1) & 1)) ^ 1, err, 314);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256;
         for (int g = 0; g < GROUPS; ++g, ++n) {
@@ -285,13 +326,20 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
             if (g == GROUPS - 1) ptx::umma_commit_2cta(&l2_full[buf]);
           }
           __syncwarp();
-          if (prev_rel && g >= 1) l3_step(g - 1);
+          if (!BIG && prev_rel && g >= 1) l3_step(g - 1);  // layer 3 of the previous item rides behind this item's layer 2
         }
-        if (prev_rel) l3_step(7);
-        prev_rel = w < T;
-        prev_buf = buf;
+        if (BIG) {
+          // one accumulator: the next item's layer 2 cannot start before this item's hidden layer has left TMEM, and the restage
+          // of chunk c waits for the layer-3 MMAs of chunk c - 1 — so layer 3 of THIS item runs here, paced by the epilogue
+          if (w < T)
+            for (int s = 0; s < 8; ++s) l3_step(s);
+        } else {
+          if (prev_rel) l3_step(7);
+          prev_rel = w < T;
+          prev_buf = buf;
+        }
       }
-      if (prev_rel)
+      if (!BIG && prev_rel)
         for (int s = 0; s < 8; ++s) l3_step(s);
     }
   } else if (warp >= PROD_WARP0) {
@@ -336,34 +384,37 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
       for (int g = 0; g < GROUPS; ++g, ++n) {
         const int bf = n % SU, sh = n % SH;
         const float4 bias = __ldg((const float4*)(a.b1 + it.phase * 256 + g * 32 + c4 * 4));
-        float2 acc[4][2];
+        // accumulators and operands stay packed as f32x2 register pairs: one FADD2 + one FFMA2 per two channels
+        unsigned long long acc[4][2];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) { acc[p][0] = make_float2(bias.x, bias.y); acc[p][1] = make_float2(bias.z, bias.w); }
+        for (int p = 0; p < 4; ++p) { acc[p][0] = pack_f32x2(bias.x, bias.y); acc[p][1] = pack_f32x2(bias.z, bias.w); }
         ptx::mbar_wait(&uv_full[bf], (n / SU) & 1, err, 321);
         const uint32_t ub = smem_s + OFF_UV + bf * UV_BYTES + u_off, vb = smem_s + OFF_UV + bf * UV_BYTES + v_off;
+        // software-pipelined over the MAX_LR layer slots: the loads of slot l + 1 are in flight behind the arithmetic of slot l
+        // (slots >= Lr re-read the last layer with gate 0 — no data-dependent branch, so the loads can be hoisted)
+        unsigned long long U[2][2][2], V[2][2][2];  // [buffer][query of the 2 x 2 block][channel pair]
+        auto ld_layer = [&](int l, int bsel) {
+          const uint32_t lo = (uint32_t)min(l, a.Lr - 1) * 128u;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(U[bsel][d][0]), "=l"(U[bsel][d][1]) : "r"(ub + d * row_stride + lo));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(V[bsel][d][0]), "=l"(V[bsel][d][1]) : "r"(vb + d * row_stride + lo));
+          }
+        };
+        ld_layer(0, 0);
 #pragma unroll
         for (int l = 0; l < MAX_LR; ++l) {
-          if (l < a.Lr) {
-            float4 u[2], v[2];
+          if (l + 1 < MAX_LR) ld_layer(l + 1, (l + 1) & 1);
+          const int bsel = l & 1;
 #pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(u[d].x), "=f"(u[d].y), "=f"(u[d].z), "=f"(u[d].w)
-                           : "r"(ub + d * row_stride + l * 128));
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[d].x), "=f"(v[d].y), "=f"(v[d].z), "=f"(v[d].w)
-                           : "r"(vb + d * row_stride + l * 128));
+          for (int ds = 0; ds < 2; ++ds)
+#pragma unroll
+            for (int dd = 0; dd < 2; ++dd) {
+              const int p = ds * 2 + dd;
+              const unsigned long long gg = pack_f32x2(gt[p][l], gt[p][l]);
+              acc[p][0] = fma2(gg, add2(U[bsel][ds][0], V[bsel][dd][0]), acc[p][0]);
+              acc[p][1] = fma2(gg, add2(U[bsel][ds][1], V[bsel][dd][1]), acc[p][1]);
             }
-#pragma unroll
-            for (int ds = 0; ds < 2; ++ds)
-#pragma unroll
-              for (int dd = 0; dd < 2; ++dd) {
-                const int p = ds * 2 + dd;
-                const float2 t0 = add2(make_float2(u[ds].x, u[ds].y), make_float2(v[dd].x, v[dd].y));
-                const float2 t1 = add2(make_float2(u[ds].z, u[ds].w), make_float2(v[dd].z, v[dd].w));
-                const float gv = gt[p][l];
-                acc[p][0].x = fmaf(gv, t0.x, acc[p][0].x); acc[p][0].y = fmaf(gv, t0.y, acc[p][0].y);
-                acc[p][1].x = fmaf(gv, t1.x, acc[p][1].x); acc[p][1].y = fmaf(gv, t1.y, acc[p][1].y);
-              }
-          }
         }
         __syncwarp();  // every lane has read the staged slices
         if (lane == 0) ptx::mbar_arrive(&uv_empty[bf]);
@@ -372,7 +423,9 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
         for (int p = 0; p < 4; ++p)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const float x0 = fmaxf(acc[p][h].x, 0.f), x1 = fmaxf(acc[p][h].y, 0.f);
+            float a0, a1;
+            unpack_f32x2(acc[p][h], a0, a1);
+            const float x0 = fmaxf(a0, 0.f), x1 = fmaxf(a1, 0.f);
             const uint32_t hh = pack2_bf16(x0, x1);
             hi[p][h] = hh;
             lo[p][h] = pack2_bf16(x0 - __uint_as_float(hh << 16), x1 - __uint_as_float(hh & 0xffff0000u));
@@ -394,7 +447,7 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int q = warp & 3, set = warp >> 2;
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < (BIG ? 256 : 64)) {
       float v = 0.f;
       if ((int)threadIdx.x < a.P) v = a.b3[threadIdx.x] - (a.rel_dist ? a.tau * logf(a.rel_dist[threadIdx.x]) : 0.f);  // egtr.py:509-512
       b3adj[threadIdx.x] = v;
@@ -407,11 +460,11 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
     int u3 = 0, n_r = 0, n_c = 0;
     for (int k = 0; k < n_items; ++k) {
       const Item it = decode(me + k * slots);
-      const int buf = k & 1;
+      const int buf = BIG ? 0 : (k & 1);
       const int i = it.i0 + s_loc, j = it.j0 + o_loc;
       const bool valid = i < a.N && j < a.N;
       const long long pair = ((long long)it.b * a.N + i) * a.N + j;
-      ptx::mbar_wait(&l2_full[buf], (k >> 1) & 1, err, 331);
+      ptx::mbar_wait(&l2_full[buf], BIG ? (k & 1) : ((k >> 1) & 1), err, 331);
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
       uint32_t r[32];
@@ -444,19 +497,18 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_leader(&h2_full[set]);
         }
+        if (BIG) {  // the hidden layer has left the layer-2 accumulator: the next item's MMAs may overwrite it
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_leader(&acc_free[0]);
+        }
         ptx::mbar_wait(l3_full, n_r & 1, err, 333);
         ++n_r;
         ptx::tc_fence_after();
-        ptx::tmem_ld_32x32(t_acc + set * 128, r);  // predicates set*32 .. set*32+31
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_leader(&acc_free[buf]);
-        if (valid) {
-          const float* trip = nullptr;
-          if (a.cls != nullptr) trip = a.triplet + ((long long)a.cls[(long long)it.b * a.N + i] * a.k1 + a.cls[(long long)it.b * a.N + j]) * a.P;  // egtr.py:405-413
-          float* out = a.pred_rel + pair * a.P;
-          const int p0 = set * 32;
+        const float* trip = nullptr;
+        if (valid && a.cls != nullptr) trip = a.triplet + ((long long)a.cls[(long long)it.b * a.N + i] * a.k1 + a.cls[(long long)it.b * a.N + j]) * a.P;  // egtr.py:405-413
+        float* out = a.pred_rel + pair * a.P;
+        auto finish32 = [&](int p0) {  // r = logits of predicates p0 .. p0 + 31 of this lane's pair
+          if (!valid) return;
           if ((a.P & 1) == 0) {
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 2) {
@@ -478,6 +530,27 @@ relhead_kernel(const __grid_constant__ CUtensorMap tmap_w2, const __grid_constan
               }
             }
           }
+        };
+        if (BIG) {
+          // this warp's half of the P3 layer-3 columns, 32 at a time; the accumulator is released after the last read
+          const int half3 = a.P3 >> 1, nch3 = half3 >> 5;
+          for (int c = 0; c < nch3; ++c) {
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + set * half3 + c * 32, r);
+            ptx::tmem_ld_wait();
+            if (c == nch3 - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_leader(&acc_free[1]);
+            }
+            finish32(set * half3 + c * 32);
+          }
+        } else {
+          ptx::tmem_ld_32x32(t_acc + set * 128, r);  // predicates set*32 .. set*32+31
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_leader(&acc_free[buf]);
+          finish32(set * 32);
         }
       } else {
         // ---- connectivity MLP: last layer (256 -> 1) as a dot product over this warp's 128 columns
@@ -591,6 +664,7 @@ int rh_map(const void* ptr, int dtype, int rank, unsigned long long d0, unsigned
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled (relation head) failed with CUresult %d", (int)r);
+  if (cache.size() >= (1u << 15)) cache.clear();  // bounded: maps are passed to kernels by value, re-encoding is cheap
   cache.emplace(key, m);
   *out = m;
   return EGTR_OK;
@@ -625,11 +699,12 @@ extern "C" int egtr_pack_weight_p32g(const float* w, int N, int K, int rows_out,
 extern "C" int egtr_relation_pairs_fused_f32(const float* U, const float* V, int ldu, int layers, const egtr_relhead_weights_t* w,
                                              const int* cls, const float* triplet_dist, int k1, const float* rel_dist, float tau,
                                              int B, int N, int P, float* pred_rel, float* pred_conn, egtr_stream_t s) {
+  EGTR_ONE_DEVICE();
   EGTR_CHECK(U && V && w && pred_rel && pred_conn && w->b1 && w->w2g && w->b2 && w->w3g && w->b3 && w->w3c, EGTR_ERR_ARG,
              "egtr_relation_pairs_fused_f32: null pointer");
   EGTR_CHECK(B > 0 && N > 0 && P > 0 && layers >= 1, EGTR_ERR_ARG, "egtr_relation_pairs_fused_f32: empty shape");
-  EGTR_CHECK(P <= 64 && layers <= MAX_LR && ldu >= 513 && ldu % 4 == 0, EGTR_ERR_UNSUPPORTED,
-             "egtr_relation_pairs_fused_f32: built for P <= 64 predicates and <= 7 layers (P=%d layers=%d ldu=%d)", P, layers, ldu);
+  EGTR_CHECK(P <= 256 && layers <= MAX_LR && ldu >= 513 && ldu % 4 == 0, EGTR_ERR_UNSUPPORTED,
+             "egtr_relation_pairs_fused_f32: built for P <= 256 predicates and <= 7 layers (P=%d layers=%d ldu=%d)", P, layers, ldu);
   EGTR_CHECK(cls == nullptr || triplet_dist != nullptr, EGTR_ERR_ARG, "egtr_relation_pairs_fused_f32: triplet_dist missing");
   EGTR_CHECK(((uintptr_t)U & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)w->w2g & 127) == 0 && ((uintptr_t)w->w3g & 127) == 0 &&
                  ((uintptr_t)w->b1 & 15) == 0 && ((uintptr_t)w->b2 & 15) == 0 && ((uintptr_t)w->w3c & 15) == 0 &&
@@ -641,10 +716,12 @@ extern "C" int egtr_relation_pairs_fused_f32(const float* U, const float* V, int
   a.pred_rel = pred_rel; a.pred_conn = pred_conn; a.b3c = w->b3c; a.tau = tau;
   a.B = B; a.N = N; a.P = P; a.Lr = layers; a.ldu = ldu; a.k1 = k1;
   a.tiles_i = cdiv(N, 16); a.tiles_j = cdiv(N, 16);
+  const bool big = P > 64;
+  a.P3 = big ? 64 * cdiv(P, 64) : 64;  // rows of w3g
   CUtensorMap tw2, tw3, tu, tv;
   int rc = rh_map(w->w2g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 512, 512, 1, 1024, 0, 64, 128, 1, 1, &tw2);
   if (rc != EGTR_OK) return rc;
-  rc = rh_map(w->w3g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 512, 64, 1, 1024, 0, 64, 32, 1, 1, &tw3);
+  rc = rh_map(w->w3g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 512, (unsigned long long)a.P3, 1, 1024, 0, 64, big ? (unsigned)a.P3 / 2 : 32u, 1, 1, &tw3);
   if (rc != EGTR_OK) return rc;
   const unsigned long long rows = (unsigned long long)B * N;
   rc = rh_map(U, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (unsigned long long)ldu, (unsigned long long)layers, rows, 4ull * ldu, 4ull * ldu * layers,
@@ -655,14 +732,21 @@ extern "C" int egtr_relation_pairs_fused_f32(const float* U, const float* V, int
   if (rc != EGTR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(relhead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_SMEM));
+    EGTR_CUDA(cudaFuncSetAttribute(relhead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RhCfg<false>::SMEM));
+    EGTR_CUDA(cudaFuncSetAttribute(relhead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RhCfg<true>::SMEM));
     attr_set = true;
   }
   const long long items = 2ll * B * a.tiles_i * a.tiles_j;
   int slots = num_sms() / 2 / grid_div();
   if (slots < 1) slots = 1;
   const int grid = balanced_grid(items, slots) * 2;
-  EGTR_CUDA(launch_cluster_pdl(relhead_kernel, dim3(grid), dim3(RH_THREADS), (size_t)RH_SMEM, (cudaStream_t)s, 2, tw2, tw3, tu, tv, a, rh_error_flag()));
+  if (big) {
+    EGTR_CUDA(launch_cluster_pdl(relhead_kernel<true>, dim3(grid), dim3(RH_THREADS), (size_t)RhCfg<true>::SMEM, (cudaStream_t)s, 2, tw2, tw3, tu,
+                                 tv, a, rh_error_flag()));
+  } else {
+    EGTR_CUDA(launch_cluster_pdl(relhead_kernel<false>, dim3(grid), dim3(RH_THREADS), (size_t)RhCfg<false>::SMEM, (cudaStream_t)s, 2, tw2, tw3, tu,
+                                 tv, a, rh_error_flag()));
+  }
   count_launch();
   return EGTR_OK;
 }

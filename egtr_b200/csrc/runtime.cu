@@ -20,6 +20,18 @@ void set_last_error(const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// The library keeps a few per-process device objects (error flags, split-K scratch, SM count) that belong to the device that was
+// current at first use: one process drives ONE GPU (the path's multi-GPU model).  A call issued with another
+// device current would hand kernels pointers of the wrong GPU — refuse it loudly instead.
+int bound_device_ok() {
+  static std::atomic<int> bound{-1};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int expected = -1;
+  if (bound.compare_exchange_strong(expected, dev)) return 1;
+  return expected == dev;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -71,98 +71,145 @@ triplet_scores_kernel(const float* __restrict__ rel, const float* __restrict__ c
   out[t] = v * so;
 }
 
-// ---------------------------------------------------------------- radix select (two 16-bit passes)
+// ---------------------------------------------------------------- radix select (three passes: 11 + 11 + 10 bits)
+// Scores are >= 0, so their IEEE bit patterns order like unsigned integers.  Pass p histograms the next digit of the elements
+// that match the digits chosen so far, in SHARED memory (2048 bins per CTA, warp-aggregated adds: scores cluster in a few
+// exponents, so most lanes of a warp hit the same bin), flushes the non-empty bins to the image's global histogram, and the
+// NEXT kernel picks the digit that holds the k-th largest element (every CTA repeats the 2048-bin suffix scan: cheaper than a
+// launch).  sel[b] = {digits chosen so far, elements still needed inside that prefix}.
+constexpr int BINS = 2048;
+struct Pick { unsigned prefix, need, count; };
+
+// suffix scan over hist[BINS] from the top: the bin where the running count first reaches `need`; 256 threads
+__device__ __forceinline__ Pick pick_digit(const unsigned* __restrict__ hist, unsigned need, unsigned* sm /* [256 + 4] */) {
+  const int t = threadIdx.x;
+  unsigned loc[8], s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { loc[j] = hist[BINS - 1 - (t * 8 + j)]; s += loc[j]; }  // thread t owns the 8 bins below BINS - 8t
+  sm[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {  // inclusive scan over threads (counts from the top)
+    const unsigned v = t >= o ? sm[t - o] : 0;
+    __syncthreads();
+    sm[t] += v;
+    __syncthreads();
+  }
+  const unsigned incl = sm[t], excl = incl - s;
+  if (excl < need && incl >= need) {  // exactly one thread (need >= 1 and the total is >= need)
+    unsigned acc = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (acc + loc[j] >= need) { sm[256] = BINS - 1 - (t * 8 + j); sm[257] = need - acc; sm[258] = loc[j]; break; }
+      acc += loc[j];
+    }
+  }
+  __syncthreads();
+  Pick p = {sm[256], sm[257], sm[258]};
+  __syncthreads();
+  return p;
+}
+
+template <int PASS>
 __global__ void __launch_bounds__(256)
-hist_hi_kernel(const float* __restrict__ sc, long long n, unsigned* __restrict__ hist) {
-  pdl_entry();  // hist [B][65536]
+select_pass_kernel(const float* __restrict__ sc, long long n, int k, unsigned* __restrict__ hist /* [B][3][BINS] */, unsigned* __restrict__ sel /* [B][8] */) {
+  pdl_entry();
+  __shared__ unsigned h[BINS];
+  __shared__ unsigned sm[260];
   const int b = blockIdx.y;
   const float* x = sc + (long long)b * n;
-  unsigned* h = hist + (long long)b * 65536;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&h[__float_as_uint(x[i]) >> 16], 1u);
+  unsigned* H = hist + (long long)b * 3 * BINS;
+  unsigned prefix = 0;
+  if (PASS > 0) {  // digit(s) chosen by the previous pass(es)
+    const unsigned need = PASS == 1 ? (unsigned)k : sel[b * 8 + 1];
+    const Pick p = pick_digit(H + (PASS - 1) * BINS, need, sm);
+    prefix = PASS == 1 ? p.prefix : ((sel[b * 8 + 0] << 11) | p.prefix);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sel[b * 8 + (PASS == 1 ? 0 : 2)] = prefix; sel[b * 8 + (PASS == 1 ? 1 : 3)] = p.need; }
+    // (PASS 1 writes sel[0..1] = first digit / need; PASS 2 writes sel[2..3] = first two digits / need: distinct words, so CTAs of
+    //  this launch that still read sel[0..1] are not disturbed)
+  }
+  for (int i = threadIdx.x; i < BINS; i += 256) h[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i0 = blockIdx.x * 256ll; i0 < n; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    unsigned key = 0xffffffffu;  // sentinel: not counted
+    if (i < n) {
+      const unsigned u = __float_as_uint(x[i]);
+      if (PASS == 0) key = u >> 21;
+      else if (PASS == 1) { if ((u >> 21) == prefix) key = (u >> 10) & 2047u; }
+      else { if ((u >> 10) == prefix) key = u & 1023u; }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[key], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS; i += 256)
+    if (h[i]) atomicAdd(&H[PASS * BINS + i], h[i]);
 }
-// one CTA per image: walk the histogram from the top, find the bin holding the k-th largest
-__global__ void __launch_bounds__(1024)
-pick_bin_kernel(const unsigned* __restrict__ hist, int k, unsigned* __restrict__ sel) {
-  pdl_entry();  // sel [B][4]: bin, need_in_bin, (lo passes reuse)
-  const int b = blockIdx.x;
-  const unsigned* h = hist + (long long)b * 65536;
-  __shared__ unsigned part[1024];
-  // thread t owns bins [64 t, 64 t + 64) counted from the TOP (bin index 65535 - ...)
-  unsigned s = 0;
-  for (int j = 0; j < 64; ++j) s += h[65535 - (threadIdx.x * 64 + j)];
-  part[threadIdx.x] = s;
+
+// Elements equal to the threshold, counted per CTA chunk (contiguous index ranges): the compaction below takes the `ties`
+// SMALLEST flat indices among them, so the selected set — not only its order — is the same on every run and equals a stable
+// descending argsort (atomics used to pick ties by arrival order).
+__global__ void __launch_bounds__(256)
+tie_count_kernel(const float* __restrict__ sc, long long n, int k, const unsigned* __restrict__ hist, unsigned* __restrict__ sel,
+                 unsigned* __restrict__ tie_counts /* [B][gridDim.x] */) {
+  pdl_entry();
+  __shared__ unsigned sm[260];
+  const int b = blockIdx.y;
+  const Pick p = pick_digit(hist + ((long long)b * 3 + 2) * BINS, sel[b * 8 + 3], sm);
+  const unsigned thr = (sel[b * 8 + 2] << 10) | p.prefix;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sel[b * 8 + 4] = thr; sel[b * 8 + 5] = p.need; sel[b * 8 + 6] = p.count; }
+  const float* x = sc + (long long)b * n;
+  const long long chunk = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  unsigned c = 0;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) c += __float_as_uint(x[i]) == thr;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned acc = 0;
-    int t = 0;
-    while (t < 1024 && acc + part[t] < (unsigned)k) acc += part[t++];
-    unsigned bin = 0, need = 0;
-    if (t < 1024) {
-      for (int j = 0; j < 64; ++j) {
-        const unsigned c = h[65535 - (t * 64 + j)];
-        if (acc + c >= (unsigned)k) { bin = 65535 - (t * 64 + j); need = k - acc; break; }
-        acc += c;
-      }
-    }
-    sel[b * 4 + 0] = bin;   // all elements in higher bins are selected
-    sel[b * 4 + 1] = need;  // plus the `need` largest of this bin
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    tie_counts[(long long)b * gridDim.x + blockIdx.x] = t;
   }
 }
+
+// compaction: everything above the threshold, plus the `ties` lowest-index elements equal to it
 __global__ void __launch_bounds__(256)
-hist_lo_kernel(const float* __restrict__ sc, long long n, const unsigned* __restrict__ sel, unsigned* __restrict__ hist) {
+collect_kernel(const float* __restrict__ sc, long long n, const unsigned* __restrict__ sel, const unsigned* __restrict__ tie_counts, int k,
+               unsigned* __restrict__ counters, float* __restrict__ cand_score, long long* __restrict__ cand_idx) {
   pdl_entry();
+  __shared__ unsigned sm[16];
   const int b = blockIdx.y;
   const float* x = sc + (long long)b * n;
-  const unsigned bin = sel[b * 4];
-  unsigned* h = hist + (long long)b * 65536;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned u = __float_as_uint(x[i]);
-    if ((u >> 16) == bin) atomicAdd(&h[u & 0xffffu], 1u);
-  }
-}
-__global__ void __launch_bounds__(1024)
-pick_lo_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ sel) {
-  pdl_entry();  // -> sel[2] = exact threshold bits, sel[3] = ties to take
-  const int b = blockIdx.x;
-  const unsigned* h = hist + (long long)b * 65536;
-  const unsigned need = sel[b * 4 + 1];
-  __shared__ unsigned part[1024];
-  unsigned s = 0;
-  for (int j = 0; j < 64; ++j) s += h[65535 - (threadIdx.x * 64 + j)];
-  part[threadIdx.x] = s;
+  const unsigned thr = sel[b * 8 + 4], ties = sel[b * 8 + 5];
+  // rank of this chunk's first tie among all ties of the image (ascending index)
+  unsigned before = 0;
+  for (int c = threadIdx.x; c < (int)blockIdx.x; c += 256) before += tie_counts[(long long)b * gridDim.x + c];
+  before = __reduce_add_sync(0xffffffffu, before);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sm[warp] = before;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned acc = 0, lo = 0, ties = 0;
-    int t = 0;
-    while (t < 1024 && acc + part[t] < need) acc += part[t++];
-    if (t < 1024) {
-      for (int j = 0; j < 64; ++j) {
-        const unsigned c = h[65535 - (t * 64 + j)];
-        if (acc + c >= need) { lo = 65535 - (t * 64 + j); ties = need - acc; break; }
-        acc += c;
-      }
-    }
-    sel[b * 4 + 2] = (sel[b * 4] << 16) | lo;
-    sel[b * 4 + 3] = ties;
-  }
-}
-// compaction: everything above the threshold, plus `ties` elements equal to it
-__global__ void __launch_bounds__(256)
-collect_kernel(const float* __restrict__ sc, long long n, const unsigned* __restrict__ sel, int k, unsigned* __restrict__ counters,
-               float* __restrict__ cand_score, long long* __restrict__ cand_idx) {
-  pdl_entry();
-  const int b = blockIdx.y;
-  const float* x = sc + (long long)b * n;
-  const unsigned thr = sel[b * 4 + 2], ties = sel[b * 4 + 3];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned u = __float_as_uint(x[i]);
-    bool take = u > thr;
-    if (u == thr) take = atomicAdd(&counters[b * 2 + 1], 1u) < ties;
+  unsigned base = 0;
+  for (int w = 0; w < 8; ++w) base += sm[w];
+  __syncthreads();
+  const long long chunk = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+  for (long long i0 = lo; i0 < hi; i0 += 256) {
+    const long long i = i0 + threadIdx.x;
+    const unsigned u = i < hi ? __float_as_uint(x[i]) : 0u;
+    const bool eq = i < hi && u == thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) sm[8 + warp] = __popc(bal);
+    __syncthreads();
+    unsigned wbase = 0, tile = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) wbase += sm[8 + w]; tile += sm[8 + w]; }
+    const bool take = (i < hi && u > thr) || (eq && base + wbase + __popc(bal & ((1u << lane) - 1u)) < ties);
     if (take) {
       const unsigned slot = atomicAdd(&counters[b * 2], 1u);
       if (slot < (unsigned)k) { cand_score[(long long)b * k + slot] = x[i]; cand_idx[(long long)b * k + slot] = i; }
     }
+    base += tile;
+    __syncthreads();
   }
 }
 // rank the k survivors (score descending, flat index ascending) and emit indices / relation scores
@@ -211,9 +258,12 @@ emit_kernel(const float* __restrict__ cand_score, const long long* __restrict__ 
 
 using namespace egtr;
 
+constexpr int SELECT_GRID = 592;  // CTAs per image of the select / tie / collect passes (4 x 148)
+
 extern "C" long long egtr_triplets_scratch_bytes(int B, int N, int P, int single, int k) {
   const long long n = (long long)N * N * (single ? 1 : P);
-  return (long long)B * n * 4 + (long long)B * 65536 * 4 * 2 + (long long)B * 16 + (long long)B * 8 + (long long)B * k * 12 + 256;
+  return (long long)B * n * 4 + (long long)B * 3 * BINS * 4 + (long long)B * 32 + (long long)B * 8 + (long long)B * SELECT_GRID * 4 +
+         (long long)B * k * 12 + 256;
 }
 
 extern "C" int egtr_triplets_f32(const float* logits, const float* pred_rel, const float* pred_conn, int B, int N, int K,
@@ -227,24 +277,25 @@ extern "C" int egtr_triplets_f32(const float* logits, const float* pred_rel, con
   EGTR_CHECK(n >= k, EGTR_ERR_ARG, "egtr_triplets_f32: fewer candidates (%lld) than k (%d)", n, k);
   unsigned char* base = (unsigned char*)scratch;
   float* scores = (float*)base;                       base += (long long)B * n * 4;
-  unsigned* hist_hi = (unsigned*)base;                base += (long long)B * 65536 * 4;
-  unsigned* hist_lo = (unsigned*)base;                base += (long long)B * 65536 * 4;
-  unsigned* sel = (unsigned*)base;                    base += (long long)B * 16;
+  unsigned* hist = (unsigned*)base;                   base += (long long)B * 3 * BINS * 4;
+  unsigned* sel = (unsigned*)base;                    base += (long long)B * 32;
   unsigned* counters = (unsigned*)base;               base += (long long)B * 8;
+  unsigned* tie_counts = (unsigned*)base;             base += (long long)B * SELECT_GRID * 4;
   base = (unsigned char*)(((uintptr_t)base + 7) & ~(uintptr_t)7);
   long long* cand_idx = (long long*)base;             base += (long long)B * k * 8;
   float* cand_score = (float*)base;
-  EGTR_CUDA(cudaMemsetAsync(hist_hi, 0, (size_t)B * 65536 * 4 * 2 + (size_t)B * 24, st));
+  EGTR_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * 3 * BINS * 4 + (size_t)B * 40, st));  // histograms, sel, counters
   launch_pdl(obj_scores_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), (size_t)(0), st, logits, K, num_labels, B * N, obj_scores, pred_classes);
   const long long total = (long long)B * n;
   launch_pdl(triplet_scores_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), st, pred_rel, pred_conn, obj_scores, N, P, single, total, scores);
   int gx = cdiv(n, 256 * 8);
-  if (gx > 592) gx = 592;
-  launch_pdl(hist_hi_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, hist_hi);
-  launch_pdl(pick_bin_kernel, dim3(B), dim3(1024), (size_t)(0), st, hist_hi, k, sel);
-  launch_pdl(hist_lo_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, sel, hist_lo);
-  launch_pdl(pick_lo_kernel, dim3(B), dim3(1024), (size_t)(0), st, hist_lo, sel);
-  launch_pdl(collect_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, sel, k, counters, cand_score, cand_idx);
+  if (gx > SELECT_GRID) gx = SELECT_GRID;
+  launch_pdl(select_pass_kernel<0>, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, k, hist, sel);
+  launch_pdl(select_pass_kernel<1>, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, k, hist, sel);
+  launch_pdl(select_pass_kernel<2>, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, k, hist, sel);
+  launch_pdl(tie_count_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, k, (const unsigned*)hist, sel, tie_counts);
+  launch_pdl(collect_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(0), st, scores, n, (const unsigned*)sel, (const unsigned*)tie_counts, k, counters,
+             cand_score, cand_idx);
   launch_pdl(emit_kernel, dim3(B), dim3(128), (size_t)(((k * 4 + 7) / 8) * 8 + k * 8), st, cand_score, cand_idx, counters, k, N, P, single, pred_rel, pred_conn, rel_inds, rel_scores);
   for (int i = 0; i < 8; ++i) count_launch();
   EGTR_CUDA(cudaGetLastError());

@@ -115,7 +115,7 @@ class BasicSceneGraphEvaluator:
 
 
 def evaluate_from_dict(gt_entry, pred_entry, mode, result_dict, multiple_preds=False, viz_dict=None, iou_thresh=0.5, **kwargs):
-    """sg_eval.py:74-139 for the box-predicting modes (sgdet / phrdet) and the ground-truth-box modes (predcls / sgcls)."""
+    """sg_eval.py:74-139: the box-predicting modes (sgdet / phrdet), the ground-truth-box modes (predcls / sgcls) and preddet."""
     gt_rels = np.asarray(gt_entry["gt_relations"])
     gt_boxes = np.asarray(gt_entry["gt_boxes"]).astype(float)
     gt_classes = np.asarray(gt_entry["gt_classes"])
@@ -128,6 +128,8 @@ def evaluate_from_dict(gt_entry, pred_entry, mode, result_dict, multiple_preds=F
     elif mode.startswith("sgdet") or mode == "phrdet":
         pred_boxes = np.asarray(pred_entry["pred_boxes"]).astype(float)
         pred_classes, obj_scores = np.asarray(pred_entry["pred_classes"]), np.asarray(pred_entry["obj_scores"])
+    elif mode == "preddet":
+        return _preddet(gt_rels, pred_rel_inds, rel_scores, result_dict)
     else:
         raise ValueError("invalid mode")
     if multiple_preds:
@@ -144,6 +146,28 @@ def evaluate_from_dict(gt_entry, pred_entry, mode, result_dict, multiple_preds=F
             matched.update(lst)
         result_dict[mode + "_recall"][k].append(float(len(matched)) / n_gt)
     return pred_to_gt, pred_5ples, scores
+
+
+def _preddet(gt_rels, pred_rel_inds, rel_scores, result_dict):
+    """Predicate detection (sg_eval.py:107-131): only the predicted (subject, object) pairs that appear in the ground truth are
+    kept — the first prediction per ground-truth pair — and their per-predicate scores [pairs, P] are ranked jointly;
+    recall@k = fraction of ground-truth triplets among the k best (pair, predicate) entries.  `pred_rel_inds` [n, 2],
+    `rel_scores` [n, P].  Returns (None, None, None) like the reference."""
+    key = "preddet_recall"
+    pairs_equal = (pred_rel_inds[:, None, :2] == gt_rels[None, :, :2]).all(-1)  # [pred, gt]
+    if pairs_equal.size == 0:
+        for k in result_dict[key]:
+            result_dict[key][k].append(0.0)
+        return None, None, None
+    first = pairs_equal.argmax(0)  # first matching prediction of every ground-truth pair (0 when none: the reference's argmax too)
+    kept_pairs, kept_scores = pred_rel_inds[first, :2], rel_scores[first]
+    order = np.argsort(-kept_scores.ravel())  # the reference's argsort_desc (quicksort: tie order unspecified)
+    row, pred = np.unravel_index(order, kept_scores.shape)
+    ranked = np.column_stack((kept_pairs[row], pred))  # (subject, object, predicate), best first
+    hits = (ranked[:, None, :] == gt_rels[None, :, :]).all(-1)  # [ranked, gt]
+    for k in result_dict[key]:
+        result_dict[key][k].append(float(hits[:k].any(0).sum()) / float(gt_rels.shape[0]))
+    return None, None, None
 
 
 def calculate_mR_from_evaluator_list(evaluator_list, mode, multiple_preds=False):

@@ -108,21 +108,19 @@ class DeformableDetrFeatureExtractor:
         return {"pixel_values": px, "pixel_mask": mask}
 
     def post_process(self, outputs, target_sizes):
-        out_logits, out_bbox = outputs.logits, outputs.pred_boxes
-        if len(out_logits) != len(target_sizes):
-            raise ValueError("Make sure that you pass in as many target sizes as the batch dimension of the logits")
-        if target_sizes.shape[1] != 2:
-            raise ValueError("Each element of target_sizes must contain the size (h, w) of each image of the batch")
-        prob = out_logits.sigmoid()
-        topk_values, topk_indexes = torch.topk(prob.view(out_logits.shape[0], -1), 100, dim=1)
-        topk_boxes = torch.div(topk_indexes, out_logits.shape[2], rounding_mode="trunc")
-        labels = topk_indexes % out_logits.shape[2]
-        boxes = center_to_corners_format(out_bbox)
-        boxes = torch.gather(boxes, 1, topk_boxes.unsqueeze(-1).repeat(1, 1, 4))
-        img_h, img_w = target_sizes.unbind(1)
-        scale_fct = torch.stack([img_w, img_h, img_w, img_h], dim=1)
-        boxes = boxes * scale_fct[:, None, :]
-        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(topk_values, labels, boxes)]
+        """Detections per image from raw outputs (role of `deformable_detr.py:273-319`): the 100 best (query, class) pairs by
+        sigmoid score over all N*K pairs, their boxes as absolute (x0, y0, x1, y1) in the image sizes `target_sizes` [B,2] = (h, w)."""
+        logits, cxcywh = outputs.logits, outputs.pred_boxes
+        target_sizes = torch.as_tensor(target_sizes, device=logits.device)
+        if target_sizes.dim() != 2 or target_sizes.shape != (logits.shape[0], 2):
+            raise ValueError(f"target_sizes must be [batch, 2] = (height, width) per image; got {tuple(target_sizes.shape)} for batch {logits.shape[0]}")
+        B, N, K = logits.shape
+        scores, flat = logits.sigmoid().flatten(1).topk(min(100, N * K), dim=1)
+        query, label = flat // K, flat % K
+        corners = center_to_corners_format(cxcywh)[torch.arange(B, device=logits.device)[:, None], query]  # [B,100,4]
+        wh = target_sizes.to(corners.dtype).flip(1).repeat(1, 2)  # (w, h, w, h)
+        corners = corners * wh[:, None, :]
+        return [dict(scores=scores[b], labels=label[b], boxes=corners[b]) for b in range(B)]
 
 
 def _attach(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool):
@@ -172,10 +170,70 @@ class _WeightTree(nn.Module):
             self._modules[name].add_module(idx, self._modules[name]._modules["0"])
 
 
-class DeformableDetrModel(nn.Module):
-    """Placeholder for import compatibility: the bare encoder-decoder is only reachable through
-    `DetrForSceneGraphGeneration` on the B200 path (`egtr_b200/model/egtr.py`)."""
+class DeformableDetrModel(_WeightTree):
+    """The bare encoder-decoder (`/root/reference/model/deformable_detr.py:1978-2390`) as its own entry point: same state-dict
+    keys as the reference module (the `model.*` subtree of the scene-graph model without the prefix), same forward keywords,
+    `DeformableDetrModelOutput` out — served by the same engine launches as `DetrForSceneGraphGeneration` up to the decoder."""
+
+    config_class = DeformableDetrConfig
 
     def __init__(self, config):
-        super().__init__()
-        raise NotImplementedError("use egtr_b200.model.egtr.DetrForSceneGraphGeneration; the bare model is not a separate entry point here")
+        nn.Module.__init__(self)
+        from ..synth import synth_state_dict
+        self.config = config
+        for k, v in synth_state_dict(config, seed=0).items():
+            if k.startswith("model."):
+                k = k[len("model."):]
+                _attach(self, k, v.clone(), buffer=k.endswith(_BUFFER_SUFFIXES) or _is_frozen_bn_key(k))
+        self._engine = None
+        self.use_cuda_graph = False
+
+    @property
+    def device(self):
+        return self.level_embed.device
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        out = super().load_state_dict(dict(state_dict), strict=strict)
+        self._engine = None
+        return out
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self):
+        from ..engine import Engine
+        if self._engine is None:
+            if self.device.type != "cuda":
+                raise _lib.EgtrError("model is on %s: call .cuda() first — the B200 path has no CPU fallback" % self.device)
+            self._engine = Engine(self.config, {"model." + k: v for k, v in self.state_dict().items()}, self.device, model_only=True)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, pixel_values, pixel_mask=None, decoder_attention_mask=None, encoder_outputs=None, inputs_embeds=None,
+                decoder_inputs_embeds=None, output_attentions=None, output_attention_states=None, output_hidden_states=None,
+                return_dict=None):
+        if encoder_outputs is not None or inputs_embeds is not None or decoder_inputs_embeds is not None or decoder_attention_mask is not None:
+            raise NotImplementedError("encoder_outputs / *_embeds / decoder_attention_mask are unused by the EGTR path and not built")
+        if output_attentions:
+            raise NotImplementedError("output_attentions=True (attention maps) is not built; the EGTR path captures queries / keys instead")
+        if self.use_cuda_graph:
+            B, _, H, W = pixel_values.shape
+            with torch.cuda.device(self.device):
+                o = self.engine().graph_runner(B, H, W)(pixel_values, pixel_mask)
+        else:
+            o = self.engine().forward(pixel_values, pixel_mask)
+        inter = o["intermediate_hidden_states"]
+        dec_states = None
+        if output_hidden_states:
+            tgt = self.engine().query_tgt.unsqueeze(0).expand(inter.shape[0], -1, -1)
+            dec_states = (tgt,) + tuple(inter[:, i] for i in range(inter.shape[1]))
+        out = DeformableDetrModelOutput(
+            init_reference_points=o["init_reference_points"], last_hidden_state=o["last_hidden_state"],
+            intermediate_hidden_states=inter, intermediate_reference_points=o["intermediate_reference_points"],
+            decoder_hidden_states=dec_states, encoder_last_hidden_state=o["encoder_last_hidden_state"],
+            decoder_attention_queries=o["decoder_attention_queries"] if output_attention_states else None,
+            decoder_attention_keys=o["decoder_attention_keys"] if output_attention_states else None,
+        )
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        return out if return_dict else out.to_tuple()

@@ -37,18 +37,17 @@ def extract_triplets(outputs, num_labels: int, single: bool = False, topk: int =
     return dict(obj_scores=obj, pred_classes=cls, pred_rel_inds=inds, rel_scores=scores)
 
 
-class TripletRecords:
-    """Static-buffer triplet extraction for CUDA-graph capture and for the image-parallel all-gather:
-    what `evaluate_batch` (`/root/reference/train_egtr.py:56-94, 120-128`) needs of one forward — boxes, object scores /
-    classes, the top-k (s, o, p) indices and their scores — as ONE flat buffer of 4-byte words per rank:
+class TripletLayout:
+    """Flat per-rank record of what `evaluate_batch` (`/root/reference/train_egtr.py:56-94, 120-128`) needs of one forward —
+    boxes, object scores / classes, the top-k (s, o, p) indices and their scores — as 4-byte words:
 
         [ pred_boxes B*N*4 f32 | obj_scores B*N f32 | pred_classes B*N i32 | pred_rel_inds B*k*W i32 | rel_scores B*k*(1|P) f32 ]
 
-    (field-major inside a rank; the gathered [world, words] buffer decodes to image order because ranks hold contiguous image
-    ranges).  ~6.4 KB per image at N = 200, k = 100 instead of the 8.3 MB of raw logits / pred_rel / pred_connectivity."""
+    Field-major inside a rank; a gathered [world, words] buffer decodes to image order because ranks hold contiguous image
+    ranges.  ~6.4 KB per image at N = 200, k = 100 instead of 8.3 MB of raw logits / pred_rel / pred_connectivity."""
 
-    def __init__(self, B: int, N: int, K: int, P: int, num_labels: int, device, topk: int = 100, single: bool = False):
-        self.B, self.N, self.K, self.P, self.num_labels, self.topk, self.single = B, N, K, P, num_labels, topk, single
+    def __init__(self, B: int, N: int, P: int, topk: int = 100, single: bool = False):
+        self.B, self.N, self.P, self.topk, self.single = B, N, P, topk, single
         W = 2 if single else 3
         sizes = [("pred_boxes", B * N * 4, torch.float32, (B, N, 4)), ("obj_scores", B * N, torch.float32, (B, N)),
                  ("pred_classes", B * N, torch.int32, (B, N)), ("pred_rel_inds", B * topk * W, torch.int32, (B, topk, W)),
@@ -58,14 +57,9 @@ class TripletRecords:
             self.fields[name] = (off, n, dt, shp)
             off += (n + 3) // 4 * 4  # 16-byte aligned fields
         self.words = off
-        self.device = torch.device(device)
-        with torch.cuda.device(self.device):
-            self.flat = torch.zeros(self.words, dtype=torch.int32, device=self.device)
-            nbytes = int(_lib.call("egtr_triplets_scratch_bytes", B, N, P, int(single), topk))
-            self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
-        """Field `name` of a flat record buffer [words] or of a gathered one [world, words] (-> [world*B, ...])."""
+        """Field `name` of a flat int32 record buffer [words], or of a gathered one [world, words] (-> [world*B, ...])."""
         off, n, dt, shp = self.fields[name]
         if flat.dim() == 1:
             return flat[off:off + n].view(dt).view(*shp)
@@ -73,6 +67,21 @@ class TripletRecords:
 
     def decode(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {k: self.view(flat, k) for k in self.fields}
+
+
+class TripletRecords(TripletLayout):
+    """Static-buffer triplet extraction (CUDA-graph capturable): `enqueue(outputs)` fills `self.flat` on the current stream."""
+
+    def __init__(self, B: int, N: int, K: int, P: int, num_labels: int, device, topk: int = 100, single: bool = False):
+        super().__init__(B, N, P, topk, single)
+        self.K, self.num_labels = K, num_labels
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.EgtrError("triplet extraction runs on CUDA devices only (no CPU fallback)")
+        with torch.cuda.device(self.device):
+            self.flat = torch.zeros(self.words, dtype=torch.int32, device=self.device)
+            nbytes = int(_lib.call("egtr_triplets_scratch_bytes", B, N, P, int(single), topk))
+            self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def enqueue(self, outputs) -> torch.Tensor:
         """Launch the extraction of `outputs` (device tensors of one forward) into `self.flat` on the current stream."""

@@ -39,10 +39,12 @@ RESULT_FIELDS = ("logits", "pred_boxes", "pred_rel", "pred_connectivity")
 
 class PipelinedRunner:
     def __init__(self, model, batch: int, height: int, width: int, depth: int = 2, post=None, concurrency: int = 1,
-                 input_format: str = "f32", output: str = "raw", raw_hw: Optional[Tuple[int, int]] = None, topk: int = 100,
-                 single: bool = False, gather: bool = False):
+                 input_format: str = "f32", output: str = "raw", raw_hw: Optional[Tuple[int, int]] = None,
+                 resize: Optional[Tuple[int, int]] = None, topk: int = 100, single: bool = False, gather: bool = False):
         """`post(outputs) -> dict of device tensors` (optional, output "raw" only) runs on the compute stream after each
-        replay and its result is what gets copied to the host."""
+        replay and its result is what gets copied to the host.  input_format "u8": images arrive at `raw_hw` (default: the
+        model size) and are resized on the device to DetrFeatureExtractor's target size for `resize` = (size, max_size), or to
+        (height, width) when `resize` is None; the result must fit the (height, width) batch tensor (zero padded)."""
         if input_format not in ("f32", "u8") or output not in ("raw", "triplets"):
             raise ValueError("input_format is 'f32' or 'u8', output is 'raw' or 'triplets'")
         if output == "triplets" and post is not None:
@@ -65,8 +67,10 @@ class PipelinedRunner:
             self.records: List[Optional[TripletRecords]] = []
             self.slots: List[GraphRunner] = []
             for i in range(depth):
-                stager = StaticStager(batch, raw_hw or (height, width), (height, width), self.dev,
-                                      out_hw=None if raw_hw else (height, width)) if input_format == "u8" else None
+                stager = None
+                if input_format == "u8":
+                    kw = dict(size=resize[0], max_size=resize[1]) if resize is not None else dict(out_hw=(height, width))
+                    stager = StaticStager(batch, raw_hw or (height, width), (height, width), self.dev, **kw)
                 rec = TripletRecords(batch, cfg.num_queries, cfg.num_labels, cfg.num_rel_labels, cfg.num_labels, self.dev, topk=topk,
                                      single=single) if output == "triplets" else None
                 pro = (lambda r, s=stager: s.enqueue(r.px, r.pm)) if stager is not None else None

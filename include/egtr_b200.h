@@ -92,7 +92,12 @@ typedef struct {
  * 4*C-byte row pitch; every group of 32 channels occupies 128 bytes = 32 bf16 `hi` values then 32 bf16 `lo` values with
  * hi = bf16_rn(x), lo = bf16_rn(x - hi), i.e. x == hi + lo to 2^-17 relative.  It is what the bf16x3 tensor-core product
  * consumes, written once by the producing kernel instead of being re-split by every consumer. */
-enum { EGTR_FMT_F32 = 0, EGTR_FMT_P32 = 1 };
+enum { EGTR_FMT_F32 = 0, EGTR_FMT_P32 = 1, EGTR_FMT_H16PAIR = 2 };
+/* H16 pair records — the MSDeformAttn `value` tensor laid out for the bilinear gather (output of the value_proj GEMM, input of
+ * egtr_msda_fused_fwd_h16): fp16, head-major, [heads = N/32][rows + 1 records][2 slots][32 channels]; record r holds token r-1 in
+ * slot 0 and token r in slot 1 (record 0 slot 0 and record `rows` slot 1 are padding and must hold finite values — allocate the
+ * buffer zeroed).  The two x-neighbours (t, t+1) of a bilinear sample are then ONE 128-byte line (record t+1) instead of two
+ * lines of an fp32 [rows, heads*32] matrix: half the L1 wavefronts per sample, the same bytes. */
 
 /* out[orow(m)*ldo + n] = keep(act(acc + bias[n] + res[orow(m)*ldr + n]));
  * orow(m) = (m / rows_per_b)*bstride + off + m % rows_per_b when rows_per_b > 0, else m;
@@ -190,6 +195,14 @@ int egtr_msda_fused_fwd_f32(const float* value, int ld_value, const int* shapes_
 int egtr_msda_fused_fwd_ex(const float* value, int ld_value, const int* shapes_hw, const float* offaw,
                            int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
                            int B, int S, int M, int D, int L, int Lq, int P, void* out, int out_fmt, egtr_stream_t s);
+
+/* The fused form on a `value` tensor stored as H16 pair records (EGTR_FMT_H16PAIR, written by the value_proj GEMM's epilogue):
+ * value_h16 [heads_total][records = B*S + 1][2][32] fp16; this launch reads heads head0 .. head0 + M - 1 (decoder: the six
+ * layers' value projections are one GEMM, layer i = heads 8i .. 8i+7).  Every bilinear sample costs two 128-byte L1 wavefronts
+ * (top pair, bottom pair) instead of four; accumulation stays fp32. */
+int egtr_msda_fused_fwd_h16(const void* value_h16, long long records, int head0, int heads_total, const int* shapes_hw,
+                            const float* offaw, int ld_offaw, const float* ref_points, const float* valid_ratios, int enc_ref,
+                            int B, int S, int M, int D, int L, int Lq, int P, void* out, int out_fmt, egtr_stream_t s);
 
 /* ---------------------------------------------------------------- row-wise / image ops --- */
 /* out = LayerNorm(x + res) over the last dim C (== 256), eps 1e-5; res may be NULL. */

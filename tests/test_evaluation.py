@@ -56,3 +56,18 @@ def test_mean_recall_over_predicates(capsys):
         mr = calculate_mR_from_evaluator_list(evs, "sgdet")
     capsys.readouterr()
     assert mr == {"mR@20": 0.25, "mR@50": 0.25, "mR@100": 0.25}  # the never-seen predicate (NaN) adds 0 but counts in the mean
+
+
+def test_preddet_matches_reference():
+    """`vrd_modes()` builds a preddet evaluator; the mode is pinned against the unmodified reference
+    (tests/golden/make_golden_preddet.py), including a scene without predictions."""
+    P = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sgeval_preddet.npz"))
+    evs = BasicSceneGraphEvaluator.vrd_modes()
+    assert set(evs) == {"preddet", "phrdet"} and evs["preddet"].multiple_preds
+    ev = evs["preddet"]
+    for si in range(int(P["n_scenes"])):
+        gt = {k: P[f"s{si}_{k}"] for k in ("gt_relations", "gt_boxes", "gt_classes")}
+        pred = {k: P[f"s{si}_{k}"] for k in ("pred_rel_inds", "rel_scores", "pred_boxes", "pred_classes", "obj_scores")}
+        assert ev.evaluate_scene_graph_entry(gt, pred) == (None, None, None)
+    for k in (20, 50, 100):
+        assert ev.result_dict["preddet_recall"][k] == P[f"recall{k}"].tolist()

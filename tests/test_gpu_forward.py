@@ -134,8 +134,11 @@ def test_fused_relation_stage_matches_unfused_kernels(cuda, wl, batch, monkeypat
     monkeypatch.setenv("EGTR_B200_GEMM", "simt")
     want = Engine(cfg, sd, cuda).forward(px.to(cuda), mask.to(cuda))
     torch.cuda.synchronize()
-    for k in ("pred_rel", "pred_connectivity", "logits"):
-        assert relerr(got[k], want[k]) < 2e-4, k
+    # (the unfused cross-check path keeps `value` in fp32 rows; the product path stores it as fp16 pair records: 5e-4, not 2e-4)
+    from tests.util import forward_errors, worst
+    errs = forward_errors(got, want)
+    print(wl, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert worst(errs) < 5e-4, errs
 
 
 @pytest.mark.parametrize("wl,hw,batch", [("D", (224, 320), 2), ("E", (256, 256), 2)])
@@ -187,14 +190,50 @@ def test_forward_full_size_configs(cuda, name):
     assert float(out["pred_rel"].min()) >= 0.0 and float(out["pred_rel"].max()) <= 1.0
     last = batch - 1
     want = orc.forward(sd, cfg, px[last:], mask[last:])
-    errs = {k: relerr(out[k][last:], want[k]) for k in keys}
+    from tests.util import forward_errors, worst
+    errs = forward_errors({k: out[k][last:] for k in keys}, want, keys)
     print(name, "vs oracle", {k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) < TOL, errs
+    assert worst(errs) < TOL, errs
     if batch > 1:
         for b in sorted({0, last}):
             alone = model(pixel_values=px[b:b + 1].to(cuda), pixel_mask=mask[b:b + 1].to(cuda), output_attentions=False,
                           output_attention_states=True, output_hidden_states=True)
             torch.cuda.synchronize()
-            inv = {k: relerr(out[k][b:b + 1], alone[k]) for k in keys}
+            inv = forward_errors({k: out[k][b:b + 1] for k in keys}, alone, keys)
             print(name, f"image {b} batched vs alone", {k: f"{v:.2e}" for k, v in inv.items()})
-            assert max(inv.values()) < TOL / 10, (b, inv)
+            # two runs of the same arithmetic on different tilings: fp32 summation-order noise, amplified where a `value` element
+            # rounds to the other fp16 neighbour (EGTR_FMT_H16PAIR) — a fifth of the parity bar
+            assert worst(inv) < TOL / 5, (b, inv)
+
+
+def test_workspace_cache_is_bounded_and_eviction_is_safe(cuda, monkeypatch):
+    """the per-shape workspace cache must not grow without bound over a dataset pass (every batch pads to its own
+    H, W).  With a small byte cap, old shapes are evicted (their graph runners too) and re-created on demand with identical results;
+    a runner held by the caller survives the eviction of its workspace."""
+    from egtr_b200.config import workload_config
+    from egtr_b200.engine import Engine, GraphRunner
+    from egtr_b200.synth import synth_images, synth_state_dict
+    cfg = workload_config("tiny")
+    sd = synth_state_dict(cfg, 31)
+    monkeypatch.setenv("EGTR_WS_CAP_GB", "0.02")  # ~20 MB: two or three tiny workspaces
+    eng = Engine(cfg, sd, cuda)
+    shapes = [(96, 128), (64, 96), (128, 96), (80, 112), (96, 160), (112, 112)]
+    first = {}
+    held = GraphRunner(eng, 1, 96, 128)  # captured on the (1, 96, 128, 0) workspace
+    px0, pm0 = synth_images(1, 96, 128, seed=900)
+    want_held = {k: v.clone() for k, v in held(px0.to(cuda), pm0.to(cuda)).items() if k in ("logits", "pred_rel")}
+    for rnd in range(2):
+        for i, (h, w) in enumerate(shapes):
+            px, pm = synth_images(1, h, w, seed=900 + i)
+            o = eng.forward(px.to(cuda), pm.to(cuda))
+            torch.cuda.synchronize()
+            if rnd == 0:
+                first[(h, w)] = o["pred_rel"].clone()
+            else:
+                assert torch.equal(first[(h, w)], o["pred_rel"]), (h, w)
+            assert eng.workspace_bytes() <= eng.ws_cap_bytes + max(eng._ws_bytes.values())
+    assert len([k for k in eng._ws if k[0] != "graph"]) < len(shapes)  # something was evicted
+    got = held(px0.to(cuda), pm0.to(cuda))
+    torch.cuda.synchronize()
+    for k in want_held:
+        assert torch.equal(got[k], want_held[k]), k

@@ -15,6 +15,17 @@ def w3_perm(dev):
     return (32 * ((r % 32) // 16) + 16 * (r // 32) + r % 16).to(torch.int32).contiguous()
 
 
+def pack_w3(w3, P, dev):
+    """Layer-3 weights as the fused kernel wants them (include/egtr_b200.h): P <= 64 -> 64 permuted rows, else 64*ceil(P/64) rows."""
+    from egtr_b200 import _lib
+    from egtr_b200.engine import _ptr, _stream
+    rows = 64 if P <= 64 else 64 * ((P + 63) // 64)
+    out = torch.empty(rows, 512, dtype=torch.bfloat16, device=dev)
+    perm = w3_perm(dev) if P <= 64 else None
+    _lib.call("egtr_pack_weight_p32g", _ptr(w3), P, 256, rows, _ptr(perm), _ptr(out), _stream())
+    return out, perm
+
+
 def make_case(dev, B, N, Lr, P, K1, seed):
     g = torch.Generator(device="cpu").manual_seed(seed)
     rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)  # noqa: E731
@@ -54,6 +65,10 @@ def reference(U, V, w, cls, triplet, rel_dist, tau, B, N, Lr, P):
     (1, 16, 7, 64, False, False),   # exactly one tile, all 64 predicate columns
     (3, 100, 7, 51, True, True),    # odd P: scalar store path
     (1, 1, 1, 1, False, True),      # degenerate
+    (1, 300, 7, 200, True, False),  # stress config E: N_q = 300, 200 predicates (one N = 256 layer-3 MMA, own accumulator)
+    (2, 50, 7, 65, True, True),     # just past the small-P variant, odd P
+    (1, 33, 4, 128, False, True),   # P3 = 128
+    (1, 20, 7, 256, True, False),   # every layer-3 column in use
 ])
 def test_relation_pairs_fused_matches_fp64(cuda, B, N, Lr, P, freq, adj):
     from egtr_b200 import _lib
@@ -61,10 +76,9 @@ def test_relation_pairs_fused_matches_fp64(cuda, B, N, Lr, P, freq, adj):
     K1, tau = 11, 0.3
     U, V, w, cls, triplet, rel_dist = make_case(cuda, B, N, Lr, P, K1, seed=B * 1000 + N)
     bf16 = dict(dtype=torch.bfloat16, device=cuda)
-    w2g, w3g = torch.empty(512, 512, **bf16), torch.empty(64, 512, **bf16)
-    perm = w3_perm(cuda)
+    w2g = torch.empty(512, 512, **bf16)
     _lib.call("egtr_pack_weight_p32g", _ptr(w["w2"]), 512, 256, 512, None, _ptr(w2g), _stream())
-    _lib.call("egtr_pack_weight_p32g", _ptr(w["w3"]), P, 256, 64, _ptr(perm), _ptr(w3g), _stream())
+    w3g, perm = pack_w3(w["w3"], P, cuda)
     hw = _lib.RelheadWeights()
     hw.layers = Lr
     hw.b1, hw.w2g, hw.b2, hw.w3g, hw.b3, hw.w3c, hw.b3c = _ptr(w["b1"]), _ptr(w2g), _ptr(w["b2"]), _ptr(w3g), _ptr(w["b3"]), _ptr(w["w3c"]), w["b3c"]
@@ -90,17 +104,17 @@ def test_relation_pairs_fused_matches_fp64(cuda, B, N, Lr, P, freq, adj):
     _lib.call("egtr_set_grid_div", 1)
 
 
-def test_relation_pairs_fused_is_deterministic(cuda):
+@pytest.mark.parametrize("N,P", [(200, 50), (150, 200)])
+def test_relation_pairs_fused_is_deterministic(cuda, N, P):
     """Repeated launches are bit-identical (no atomics, fixed summation order) — full and partial grids alike."""
     from egtr_b200 import _lib
     from egtr_b200.engine import _ptr, _stream
-    B, N, Lr, P, K1 = 2, 200, 7, 50, 151
+    B, Lr, K1 = 2, 7, 151
     U, V, w, cls, triplet, rel_dist = make_case(cuda, B, N, Lr, P, K1, seed=5)
     bf16 = dict(dtype=torch.bfloat16, device=cuda)
-    w2g, w3g = torch.empty(512, 512, **bf16), torch.empty(64, 512, **bf16)
-    perm = w3_perm(cuda)
+    w2g = torch.empty(512, 512, **bf16)
     _lib.call("egtr_pack_weight_p32g", _ptr(w["w2"]), 512, 256, 512, None, _ptr(w2g), _stream())
-    _lib.call("egtr_pack_weight_p32g", _ptr(w["w3"]), P, 256, 64, _ptr(perm), _ptr(w3g), _stream())
+    w3g, perm = pack_w3(w["w3"], P, cuda)
     hw = _lib.RelheadWeights()
     hw.layers = Lr
     hw.b1, hw.w2g, hw.b2, hw.w3g, hw.b3, hw.w3c, hw.b3c = _ptr(w["b1"]), _ptr(w2g), _ptr(w["b2"]), _ptr(w3g), _ptr(w["b3"]), _ptr(w["w3c"]), w["b3c"]
@@ -124,6 +138,10 @@ def test_relation_pairs_fused_rejects_unsupported(cuda):
     from egtr_b200.engine import _ptr, _stream
     U = torch.zeros(4, 7, 516, device=cuda)
     hw = _lib.RelheadWeights()
-    out = torch.zeros(4, 4, 80, device=cuda)
-    with pytest.raises(_lib.EgtrError):
+    out = torch.zeros(4, 4, 300, device=cuda)
+    with pytest.raises(_lib.EgtrError):  # null weights
         _lib.call("egtr_relation_pairs_fused_f32", _ptr(U), _ptr(U), 516, 7, C.byref(hw), None, None, 0, None, 0.3, 1, 4, 80, _ptr(out), _ptr(out), _stream())
+    z = torch.zeros(512, 512, device=cuda)
+    hw.b1 = hw.w2g = hw.b2 = hw.w3g = hw.b3 = hw.w3c = _ptr(z)
+    with pytest.raises(_lib.EgtrError):  # more predicates than layer-3 columns
+        _lib.call("egtr_relation_pairs_fused_f32", _ptr(U), _ptr(U), 516, 7, C.byref(hw), None, None, 0, None, 0.3, 1, 4, 300, _ptr(out), _ptr(out), _stream())

@@ -81,3 +81,28 @@ def test_output_object_supports_attr_key_and_in():
     o = DetrSceneGraphGenerationOutput(logits=torch.zeros(1), pred_connectivity=torch.ones(1))
     assert o.logits is o["logits"] and "pred_connectivity" in o and "pred_rel" not in o and o.loss is None
     assert len(o.to_tuple()) == 2
+
+
+def test_argmax_tie_policy_of_the_parity_comparison():
+    """tests/util.py::class_flips excuses an arg-max class change only inside the reference's own error bar."""
+    from tests.util import class_flips, forward_errors, worst
+    g = torch.Generator().manual_seed(0)
+    ref = dict(logits=torch.randn(1, 6, 5, generator=g), pred_boxes=torch.rand(1, 6, 4, generator=g),
+               pred_rel=torch.rand(1, 6, 6, 3, generator=g), pred_connectivity=torch.rand(1, 6, 6, 1, generator=g))
+    ref["logits"][0, 2, 1] = ref["logits"][0, 2].max() + 1.0
+    ref["logits"][0, 2, 3] = ref["logits"][0, 2, 1] - 1e-6  # query 2: classes 1 and 3 tie to 1e-6
+    out = {k: v.clone() for k, v in ref.items()}
+    out["logits"][0, 2, 3] += 3e-6                            # ... and resolve the other way
+    out["pred_rel"][0, 2, :, :] = 0.9                         # its pairs take another frequency-bias row
+    out["pred_rel"][0, :, 2, :] = 0.1
+    flipped = class_flips(out["logits"], ref["logits"])
+    assert flipped.tolist() == [[False, False, True, False, False, False]]
+    errs = forward_errors(out, ref)
+    assert errs["_class_flips"] == 1 and worst(errs) < 1e-5
+    out["pred_rel"][0, 0, 1, 0] += 0.5                        # a pair of unflipped queries is still compared
+    assert worst(forward_errors(out, ref)) > 0.1
+    bad = {k: v.clone() for k, v in ref.items()}
+    bad["logits"][0, 4] = bad["logits"][0, 4].flip(0) * 3     # a class change with a real margin is a failure
+    if bad["logits"][0, 4].argmax() != ref["logits"][0, 4].argmax():
+        with pytest.raises(AssertionError):
+            class_flips(bad["logits"], ref["logits"])

@@ -37,7 +37,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "golden":  # the inputs of tests/golden/
     sd = synth_state_dict(cfg, seed=32)
     px, mask = synth_images(1, 800, 1333, seed=33)
 else:
-    cfg, sd, px, mask, _ = build_case(1)
+    cfg, sd, px, mask, _ = build_case("B", 1)
 model = DetrForSceneGraphGeneration(cfg)
 model.load_state_dict(sd)
 model.cuda().eval()

@@ -9,7 +9,7 @@ from bench import build_case
 from egtr_b200.model.egtr import DetrForSceneGraphGeneration
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-cfg, sd, px, mask, _ = build_case(batch)
+cfg, sd, px, mask, _ = build_case("B", batch)
 model = DetrForSceneGraphGeneration(cfg)
 model.load_state_dict(sd)
 model.cuda().eval()
