@@ -130,18 +130,30 @@ select_pass_kernel(const float* __restrict__ sc, long long n, int k, unsigned* _
   for (int i = threadIdx.x; i < BINS; i += 256) h[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * 256;
-  for (long long i0 = blockIdx.x * 256ll; i0 < n; i0 += stride) {
-    const long long i = i0 + threadIdx.x;
-    unsigned key = 0xffffffffu;  // sentinel: not counted
-    if (i < n) {
-      const unsigned u = __float_as_uint(x[i]);
-      if (PASS == 0) key = u >> 21;
-      else if (PASS == 1) { if ((u >> 21) == prefix) key = (u >> 10) & 2047u; }
-      else { if ((u >> 10) == prefix) key = u & 1023u; }
+  const long long stride = (long long)gridDim.x * 1024;
+  for (long long i0 = blockIdx.x * 1024ll; i0 < n; i0 += stride) {
+    // four coalesced loads in flight per thread before the (serialising) warp votes
+    unsigned u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i0 + e * 256 + threadIdx.x;
+      u[e] = i < n ? __float_as_uint(x[i]) : 0xffffffffu;  // 0xffffffff: a NaN pattern no score has
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[key], (unsigned)__popc(peers));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unsigned key = 0xffffffffu;  // sentinel: not counted
+      if (u[e] != 0xffffffffu) {
+        if (PASS == 0) key = u[e] >> 21;
+        else if (PASS == 1) { if ((u[e] >> 21) == prefix) key = (u[e] >> 10) & 2047u; }
+        else { if ((u[e] >> 10) == prefix) key = u[e] & 1023u; }
+      }
+      if (PASS == 0) {  // every element counts and scores cluster in a few bins: one add per distinct bin of the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[key], (unsigned)__popc(peers));
+      } else if (key != 0xffffffffu) {  // later passes see only the elements inside the chosen digit: rare, plain adds
+        atomicAdd(&h[key], 1u);
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < BINS; i += 256)
@@ -163,7 +175,16 @@ tie_count_kernel(const float* __restrict__ sc, long long n, int k, const unsigne
   const float* x = sc + (long long)b * n;
   const long long chunk = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
   unsigned c = 0;
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) c += __float_as_uint(x[i]) == thr;
+  for (long long i0 = lo; i0 < hi; i0 += 1024) {
+    unsigned u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = i0 + e * 256 + threadIdx.x;
+      u[e] = i < hi ? __float_as_uint(x[i]) : ~thr;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c += u[e] == thr;
+  }
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
   __syncthreads();

@@ -258,6 +258,14 @@ class Engine:
         self.box2_w = sd[f"bbox_embed.{last}.layers.2.weight"].contiguous()
         self.box2_b = sd[f"bbox_embed.{last}.layers.2.bias"].contiguous()
 
+        self._prepare_relation_head(sd)
+        torch.cuda.current_stream().synchronize()
+
+    def _prepare_relation_head(self, sd):
+        """Weights of the relation head (egtr.py:322-418, 507-516); also used on its own by `egtr_b200.relation_head.RelationHead`."""
+        cfg, dev = self.cfg, self.device
+        d, heads = cfg.d_model, cfg.decoder_attention_heads
+        L = lambda w, b=None: Lin(w, b, dev)  # noqa: E731
         # relation head (egtr.py:322-418): un-scaling of the captured q folded into proj_q
         unscale = (d // heads) ** 0.5
         r1, c1, g = sd["rel_predictor.layers.0.weight"], sd["connectivity_layer.layers.0.weight"], sd["rel_predictor_gate.weight"]
@@ -319,7 +327,6 @@ class Engine:
             hw.b1, hw.w2g, hw.b2 = _ptr(self.rel_b1), _ptr(self.rel_w2g), _ptr(self.rel_w2both.b)
             hw.w3g, hw.b3, hw.w3c, hw.b3c = _ptr(self.rel_w3g), _ptr(self.rel_w3.b), _ptr(self.con_w3_w), self.con_w3_b_host
             self.rel_head_w = hw
-        torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------ CUDA-graph replay
     def graph_runner(self, B: int, H: int, W: int, slot: int = 0, throughput: bool = False) -> "GraphRunner":

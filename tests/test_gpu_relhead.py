@@ -145,3 +145,27 @@ def test_relation_pairs_fused_rejects_unsupported(cuda):
     hw.b1 = hw.w2g = hw.b2 = hw.w3g = hw.b3 = hw.w3c = _ptr(z)
     with pytest.raises(_lib.EgtrError):  # more predicates than layer-3 columns
         _lib.call("egtr_relation_pairs_fused_f32", _ptr(U), _ptr(U), 516, 7, C.byref(hw), None, None, 0, None, 0.3, 1, 4, 300, _ptr(out), _ptr(out), _stream())
+
+
+@pytest.mark.parametrize("wl,overrides", [("small", {}), ("small", dict(logit_adjustment=True, use_freq_bias=False)), ("A", {})])
+def test_relation_head_operator_matches_oracle_relation_head(cuda, wl, overrides):
+    """`RelationHead` (egtr_relation_head_fwd_f32) fed with the ORACLE's captured queries / keys / hidden state / logits against
+    the oracle's own relation head: the operator boundary of SURVEY §8b on its own, no other kernel of the library involved."""
+    from egtr_b200.config import WORKLOADS, workload_config
+    from egtr_b200.relation_head import RelationHead
+    from egtr_b200.synth import synth_images, synth_state_dict
+    from oracle import egtr_oracle as orc
+    from tests.util import class_flips, pred_rel_err
+    cfg = workload_config(wl, **overrides)
+    H, W = WORKLOADS[wl]["image"]
+    sd = synth_state_dict(cfg, 91)
+    px, mask = synth_images(2, H, W, seed=92)
+    ref = orc.forward(sd, cfg, px, mask)
+    head = RelationHead(cfg, sd, cuda)
+    pred_rel, pred_con = head(ref["decoder_attention_queries"], ref["decoder_attention_keys"], ref["last_hidden_state"], ref["logits"])
+    torch.cuda.synchronize()
+    flipped = class_flips(ref["logits"], ref["logits"])  # same logits in and out: no flips by construction
+    assert not flipped.any()
+    e_rel, e_con = pred_rel_err(pred_rel, ref["pred_rel"], flipped), relerr(pred_con, ref["pred_connectivity"])
+    print(wl, overrides, f"pred_rel {e_rel:.2e} pred_connectivity {e_con:.2e}")
+    assert e_rel < 1e-4 and e_con < 1e-4

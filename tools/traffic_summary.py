@@ -14,7 +14,7 @@ for r in csv.DictReader(rows):
     m = re.search(r"(\w+_kernel)", name)
     k = m.group(1) if m else name[:30]
     if k == "msda_kernel":
-        k = "msda_enc" if "32>" in name else "msda_dec"
+        k = "msda_enc" if re.search(r"msda_kernel<\w+, 32", name) else "msda_dec"
     v = float(r["Metric Value"].replace(",", ""))
     u = r["Metric Unit"]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}.get(u, 1)
