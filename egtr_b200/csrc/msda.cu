@@ -113,6 +113,25 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
 
   // ---- phase 1: one thread per (query, sample); two passes cover the 32 queries
   const int s = tid & 15;          // sample index = l*P + p   (L*P == 16)
+  // the raw offsets / logits of BOTH passes are requested before any of the softmax shuffles: one exposed load latency per CTA
+  float2 off_in[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float logit_in[2] = {0.f, 0.f};
+  if (FUSED) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int q = q_of[(tid >> 4) + pass * (QPB / 2)];
+      if (q >= 0) {
+        const float* row = a.offaw + ((long long)b * a.Lq + q) * a.ld_offaw;
+        if (BYPASS_L1) {
+          off_in[pass] = __ldcg((const float2*)(row + (m * 16 + s) * 2));
+          logit_in[pass] = __ldcg(row + a.M * 32 + m * 16 + s);
+        } else {
+          off_in[pass] = *(const float2*)(row + (m * 16 + s) * 2);
+          logit_in[pass] = row[a.M * 32 + m * 16 + s];
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     const int qi = (tid >> 4) + pass * (QPB / 2);
@@ -126,22 +145,12 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     float cw[4] = {0.f, 0.f, 0.f, 0.f};
     // L*P == 16 with P == 4 is asserted on the host.
     const int l = s >> 2;
-    float2 off = make_float2(0.f, 0.f);
+    const float2 off = off_in[pass];
     float wgt = 0.f;
     if (FUSED) {
       // softmax over the 16 samples of this (query, head): 16-lane butterflies, executed by every
       // lane (absent queries feed zeros) so the full-mask shuffles stay convergent.
-      float logit = 0.f;
-      if (q >= 0) {
-        const float* row = a.offaw + ((long long)b * a.Lq + q) * a.ld_offaw;
-        if (BYPASS_L1) {
-          off = __ldcg((const float2*)(row + (m * 16 + s) * 2));
-          logit = __ldcg(row + a.M * 32 + m * 16 + s);
-        } else {
-          off = *(const float2*)(row + (m * 16 + s) * 2);
-          logit = row[a.M * 32 + m * 16 + s];
-        }
-      }
+      const float logit = logit_in[pass];
       float mx = logit;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));

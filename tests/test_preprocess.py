@@ -72,3 +72,34 @@ def test_device_stager_workload_b_size(cuda):
     px, mask, sizes = DeviceImageStager(device=cuda).stage([im])
     want_px, want_mask, _ = po.stage_batch([im])
     assert sizes == [(800, 1066)] and torch.equal(px.cpu(), torch.from_numpy(want_px)) and bool(mask.all())
+
+
+def test_size_rule_and_constants_against_installed_transformers():
+    """f2 remainder: transformers 4.18 — the version the reference pins — is not installed, but its successor is.
+    The DETR size rule of the installed version equals ours whenever the `max_size` cap is not hit; when it is, newer versions
+    derive the long side from the UNROUNDED short side (`raw_size`, a later upstream fix) while 4.18 — restated here — rounds the
+    short side first.  The normalisation constants are the same objects in both."""
+    tr = pytest.importorskip("transformers.models.detr.image_processing_detr")
+    from transformers.utils.constants import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+    from egtr_b200.preprocess import IMAGE_MEAN, IMAGE_STD, target_size
+    assert tuple(IMAGENET_DEFAULT_MEAN) == IMAGE_MEAN and tuple(IMAGENET_DEFAULT_STD) == IMAGE_STD
+    assert tuple(IMAGENET_DEFAULT_MEAN) == tuple(po.IMAGE_MEAN) and tuple(IMAGENET_DEFAULT_STD) == tuple(po.IMAGE_STD)
+    rng = np.random.default_rng(4)
+    n_uncapped = n_capped = n_capped_equal = 0
+    for _ in range(4000):
+        h, w = int(rng.integers(50, 2000)), int(rng.integers(50, 2000))
+        size, mx = int(rng.choice([480, 600, 800])), int(rng.choice([800, 1000, 1333]))
+        theirs, ours = tr.get_size_with_aspect_ratio((h, w), size, mx), target_size(h, w, size, mx)
+        assert ours == po.target_size(h, w, size, mx)
+        if max(h, w) / min(h, w) * size > mx:
+            n_capped += 1
+            n_capped_equal += ours == theirs
+            # same short side; the long sides differ by at most the rounding of the short side times the aspect ratio
+            assert min(ours) == min(theirs) and abs(max(ours) - max(theirs)) <= 0.5 * max(h, w) / min(h, w) + 1
+        else:
+            n_uncapped += 1
+            assert ours == theirs, (h, w, size, mx)
+    assert n_uncapped > 1000 and n_capped > 1000
+    # the VG evaluation size (800 / 1333) on the dataset's common 4:3 and 3:2 images never hits the cap
+    for h, w in ((480, 640), (600, 800), (768, 1024), (500, 375), (333, 500)):
+        assert target_size(h, w, 800, 1333) == tr.get_size_with_aspect_ratio((h, w), 800, 1333)
