@@ -39,6 +39,13 @@ class RelheadWeights(C.Structure):
                 ("w3c", C.c_void_p), ("b3c", C.c_float)]
 
 
+class DecoderWeights(C.Structure):
+    """egtr_decoder_weights_t (include/egtr_b200.h)."""
+    _fields_ = [("layers", C.c_int), ("n_queries", C.c_int), ("w_qkv", C.c_void_p), ("w_o", C.c_void_p), ("w_offaw", C.c_void_p),
+                ("w_out", C.c_void_p), ("w_fc1", C.c_void_p), ("w_fc2", C.c_void_p), ("vec", C.c_void_p), ("qkv_pos", C.c_void_p),
+                ("off_pos", C.c_void_p), ("tgt", C.c_void_p), ("ref_points", C.c_void_p)]
+
+
 FMT_F32, FMT_P32, FMT_H16PAIR = 0, 1, 2
 
 
@@ -91,6 +98,9 @@ SIGNATURES = {
     "egtr_relation_pairs_fused_f32": [_p, _p, _i, _i, C.POINTER(RelheadWeights), _p, _p, _i, _p, _f, _i, _i, _i, _p, _p, _p],
     "egtr_relation_head_fwd_f32": [_p, _p, _i, _p, _i, _p, _i, C.POINTER(RelheadWeights), _p, _p, _f, _i, _i, _i, _i, _i,
                                    _p, _p, _p, _p, _p, _p],
+    "egtr_decoder_scratch_bytes": [_i, _i],
+    "egtr_decoder_fault": [],
+    "egtr_decoder_fused_f32": [C.POINTER(DecoderWeights), _p, _p, _ll, C.POINTER(_i), _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {
@@ -99,8 +109,9 @@ _RESTYPES = {
     "egtr_launch_count_reset": None,
     "egtr_groupnorm_scratch_doubles": _ll,
     "egtr_triplets_scratch_bytes": _ll,
+    "egtr_decoder_scratch_bytes": _ll,
 }
-_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version"}
+_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version", "egtr_decoder_fault"}
 
 _lib = None
 

@@ -1031,6 +1031,19 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
 
 }  // namespace
 
+// Tensor maps for the other TMA-fed kernels of the library (decoder.cu), from the same cache.
+// P32 rows [nb][rows_per_b][channels] (fp32 pitch): box = 64 bf16 (one group's hi | lo = 128 bytes) x box_rows rows; rows beyond
+// rows_per_b of an image read as zeros.
+int tmap_p32_rows(const void* ptr, int channels, int rows_per_b, int nb, int box_rows, CUtensorMap* out) {
+  const unsigned long long pitch = 4ull * channels;
+  return cached_map(desc4(ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2ull * channels, rows_per_b, 1, nb, pitch, pitch * rows_per_b,
+                          pitch * rows_per_b, 64, box_rows, 1), out);
+}
+// bf16 matrix [rows][K] (K-major: weight planes, transposed P32 operands): box = 64 elements x box_rows rows.
+int tmap_weight_planes(const void* planes, int K, long long rows, int box_rows, CUtensorMap* out) {
+  return cached_map(desc2(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, rows, 2ull * K, BLOCK_K, box_rows), out);
+}
+
 // Entry used by egtr_gemm_sbf16 when the operand source is P32 (a.fmt == 1): mode 0 rows or mode 1 NHWC convolution.
 int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                       cudaStream_t st) {

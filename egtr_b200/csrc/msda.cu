@@ -62,6 +62,22 @@ struct MsdaArgs {
 #define EGTR_MSDA_UNROLL 4
 #endif
 constexpr int kMsdaUnroll = EGTR_MSDA_UNROLL;
+#ifndef EGTR_MSDA_FMA2   // H16 form: accumulate channel pairs with packed fma.rn.f32x2 (same IEEE result per lane)
+#define EGTR_MSDA_FMA2 1
+#endif
+__device__ __forceinline__ unsigned long long pack_f32x2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long x, unsigned long long y, unsigned long long z) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  return r;
+}
 #ifndef EGTR_MSDA_ENC_QPB  // encoder patch: 32 = 8x4 pixels (256 threads), 64 = 8x8 pixels (512 threads)
 #define EGTR_MSDA_ENC_QPB 32
 #endif
@@ -234,6 +250,10 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
     asm("mov.b64 %0, %1;" : "=l"(vb) : "l"(hb));
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float* myslots = &slots[g * Q_STRIDE];
+#if EGTR_MSDA_FMA2
+    // channel pairs stay packed as f32x2 register pairs: one FFMA2 per corner row per two channels (the kernel is issue-bound)
+    unsigned long long acc2[4] = {0ull, 0ull, 0ull, 0ull};
+#endif
 #pragma unroll (QPB >= 32 ? kMsdaUnroll : 8)
     for (int ss = 0; ss < 16; ++ss) {
       const int2 id = *(const int2*)(myslots + ss * SLOT_WORDS);
@@ -242,14 +262,26 @@ msda_kernel(const MsdaArgs a, const Levels lv_in) {
       const uint4 t4 = __ldg((const uint4*)(vb + (unsigned long long)(uint32_t)id.x * 128ull));
       const uint4 b4 = __ldg((const uint4*)(vb + (unsigned long long)(uint32_t)id.y * 128ull));
       const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#if EGTR_MSDA_FMA2
+      const unsigned long long wt2 = pack_f32x2(wt, wt), wb2 = pack_f32x2(wb, wb);
+#endif
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&tw[k]));
         const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+#if EGTR_MSDA_FMA2
+        acc2[k] = fma2(wt2, pack_f32x2(tf.x, tf.y), acc2[k]);
+        acc2[k] = fma2(wb2, pack_f32x2(bf.x, bf.y), acc2[k]);
+#else
         acc[2 * k] = fmaf(wt, tf.x, acc[2 * k]); acc[2 * k + 1] = fmaf(wt, tf.y, acc[2 * k + 1]);
         acc[2 * k] = fmaf(wb, bf.x, acc[2 * k]); acc[2 * k + 1] = fmaf(wb, bf.y, acc[2 * k + 1]);
+#endif
       }
     }
+#if EGTR_MSDA_FMA2
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack_f32x2(acc2[k], acc[2 * k], acc[2 * k + 1]);
+#endif
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffu << (threadIdx.x & 24), acc[k], 4);  // left + right corners (lanes j, j + 4 of this query's 8; other queries of the warp may have exited)
     float* orow = a.out + ((long long)b * a.Lq + q) * (a.M * 32) + m * 32;

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ASrc, Epilogue, RelheadWeights, call
+from ._lib import ASrc, DecoderWeights, Epilogue, RelheadWeights, call
 
 RESNET_BLOCKS = (3, 4, 6, 3)
 SKINNY_M = 512  # GEMMs with at most this many rows may take the fp32 skinny kernel (decoder, detection heads)
@@ -147,6 +147,9 @@ class Engine:
         # MSDeformAttn `value` storage: "h16" = fp16 pair records written by the value_proj GEMM's epilogue (half the L1 wavefronts
         # of the bilinear gather, include/egtr_b200.h EGTR_FMT_H16PAIR), "f32" = fp32 rows [S, 256] (round 1; dev A/B)
         self.msda_value = os.environ.get("EGTR_MSDA_VALUE", "h16")
+        # decoder stack for small query sets: "fused" = ONE cluster kernel for all layers (decoder.cu), "layers" = the round-1/2
+        # sequence of skinny CUDA-core GEMMs (ten launches per layer; dev A/B and the cross-check of the fused kernel)
+        self.decoder_mode = os.environ.get("EGTR_DECODER", "fused")
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
@@ -248,6 +251,8 @@ class Engine:
         self.refpt_w = sd["model.reference_points.weight"].contiguous()
         self.refpt_b = sd["model.reference_points.bias"].contiguous()
 
+        self._prepare_fused_decoder(sd, scaling)
+
         if self.model_only:
             torch.cuda.current_stream().synchronize()
             return
@@ -260,6 +265,57 @@ class Engine:
 
         self._prepare_relation_head(sd)
         torch.cuda.current_stream().synchronize()
+
+    def _prepare_fused_decoder(self, sd, scaling: float):
+        """Weights of the one-kernel decoder stack (decoder.cu, `egtr_decoder_weights_t`): every projection stacked over the
+        layers as bf16 hi/lo planes; q|k|v rows head-major (CTA r of the cluster owns head r); the `query_pos` halves of
+        `(h + query_pos) . W` (deformable_detr.py:1404-1409, 1040) are weight-only terms, composed here in fp64."""
+        cfg, dev = self.cfg, self.device
+        nl, N, d = cfg.decoder_layers, cfg.num_queries, cfg.d_model
+        self.dec_fused_ok = N <= 256 and cfg.decoder_ffn_dim == 1024 and d == 256
+        if not self.dec_fused_ok:
+            return
+        qpos = self.query_pos.double()
+        wq, wo, woff, wout, w1, w2, vec, qkv_pos, off_pos = [], [], [], [], [], [], [], [], []
+        for i in range(nl):
+            p = f"model.decoder.layers.{i}."
+            q_w, q_b = sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.q_proj.bias"] * scaling
+            k_w, k_b = sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"]
+            v_w, v_b = sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"]
+            wq.append(torch.stack([q_w.view(8, 32, d), k_w.view(8, 32, d), v_w.view(8, 32, d)], 1).reshape(768, d))
+            qkv_pos.append(torch.cat([qpos @ q_w.double().t() + q_b.double(), qpos @ k_w.double().t() + k_b.double(),
+                                      v_b.double().expand(N, -1)], 1).float())
+            wo.append(sd[p + "self_attn.out_proj.weight"])
+            ow = torch.cat([sd[p + "encoder_attn.sampling_offsets.weight"], sd[p + "encoder_attn.attention_weights.weight"]], 0)
+            ob = torch.cat([sd[p + "encoder_attn.sampling_offsets.bias"], sd[p + "encoder_attn.attention_weights.bias"]], 0)
+            woff.append(ow)
+            off_pos.append((qpos @ ow.double().t() + ob.double()).float())
+            wout.append(sd[p + "encoder_attn.output_proj.weight"])
+            w1.append(sd[p + "fc1.weight"])
+            w2.append(sd[p + "fc2.weight"])
+            vec.append(torch.cat([sd[p + "self_attn.out_proj.bias"], sd[p + "encoder_attn.output_proj.bias"], sd[p + "fc2.bias"],
+                                  sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"],
+                                  sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"],
+                                  sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], sd[p + "fc1.bias"]]))
+
+        def planes(ws):
+            w = torch.cat(ws, 0).to(device=dev, dtype=torch.float32).contiguous()
+            out = torch.empty(2 * w.shape[0] * w.shape[1], dtype=torch.bfloat16, device=dev)
+            call("egtr_split_weight_bf16", _ptr(w), w.shape[0], w.shape[1], w.shape[0], _ptr(out), _stream())
+            return out
+
+        keep = dict(w_qkv=planes(wq), w_o=planes(wo), w_offaw=planes(woff), w_out=planes(wout), w_fc1=planes(w1), w_fc2=planes(w2),
+                    vec=torch.stack(vec).to(dev, torch.float32).contiguous(), qkv_pos=torch.stack(qkv_pos).to(dev).contiguous(),
+                    off_pos=torch.stack(off_pos).to(dev).contiguous(), tgt=self.query_tgt.to(dev, torch.float32).contiguous(),
+                    ref_points=torch.empty(N, 2, dtype=torch.float32, device=dev))
+        call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
+             None, 0, 0, _ptr(keep["ref_points"]), 2, _stream())
+        self._dec_fused_tensors = keep  # the struct holds raw pointers
+        wst = DecoderWeights()
+        wst.layers, wst.n_queries = nl, N
+        for k, t in keep.items():
+            setattr(wst, k, _ptr(t))
+        self.dec_fused_w = wst
 
     def _prepare_relation_head(self, sd):
         """Weights of the relation head (egtr.py:322-418, 507-516); also used on its own by `egtr_b200.relation_head.RelationHead`."""
@@ -492,6 +548,13 @@ class Engine:
         ws["doffaw"] = torch.empty(B * N, 384, **f32)
         ws["dffn"] = torch.empty(B * N, 1024, **f32)
         ws["dpart"] = torch.empty(8, B * N, 256, **f32)  # split-K partial sums of the decoder's out_proj / fc2
+        if self.dec_fused_ok and B * N <= SKINNY_M:
+            # fused decoder stack: one zero-initialised, 1 KB aligned scratch block (its first B*N KB are the final hidden state)
+            nbytes = int(call("egtr_decoder_scratch_bytes", B, N))
+            raw = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)
+            off = (-raw.data_ptr()) % 1024
+            ws["dec_scratch"] = raw[off: off + nbytes]
+            ws["dec_h_last"] = ws["dec_scratch"][: B * N * 1024].view(torch.float32).view(B * N, 256)
         ws["box_h"] = [torch.empty(B * N, 256, **f32) for _ in range(2)]
         Lr = cfg.decoder_layers + 1
         ws["U"] = torch.empty(B * N * Lr, 516, **f32)
@@ -688,7 +751,21 @@ class Engine:
         qpos = ws["qpos"]
         hbuf = ws["dh"]
         dpart = ws["dpart"]
-        if "dec0" not in ws:
+        dec_fused = (dec_h16 and self.decoder_mode == "fused" and "dec_scratch" in ws and Lv == 4)
+        if dec_fused:
+            # ONE launch for the whole stack (decoder.cu): a cluster of eight CTAs per image, every GEMM on tcgen05
+            if "ref_done" not in ws:
+                call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
+                     None, 0, 0, _ptr(ws["ref"]), 2, st)
+                ws["ref_done"] = True
+            qkv_all = torch.empty(nl, Md, 768, **f32)
+            inter = torch.empty(B, nl, N, 256, **f32)
+            with self.span("decoder_fused"):
+                call("egtr_decoder_fused_f32", C.byref(self.dec_fused_w), _ptr(ws["dec_scratch"]), _ptr(ws["dec_value_h16"]), M + 1,
+                     ws["shapes_c"], Lv, _ptr(vr), B, S, _ptr(qkv_all), _ptr(inter), 0, nl, 0, 12, 1, st)
+            qkvs = [qkv_all[l] for l in range(nl)]
+            hcur = ws["dec_h_last"]
+        if not dec_fused and "dec0" not in ws:
             # Input-independent prefix (weights only): the reference points and the whole self-attention half of decoder
             # layer 0 — q|k|v of the learned queries, attention, out_proj + LayerNorm, and the sampling_offsets /
             # attention_weights projection of its cross-attention — are computed once per workspace, not per image.
@@ -700,10 +777,11 @@ class Engine:
             offaw0 = torch.empty(Md, 384, **f32)
             self._dec_self_attn(lay, ws, Md, B, N, ws["tgt"], qkv0, t1_0, offaw0)
             ws["dec0"] = (qkv0, t1_0, offaw0)
-        hcur = ws["tgt"]
-        qkvs = []
-        inter = torch.empty(B, nl, N, 256, **f32)
-        for i, lay in enumerate(self.dec):
+        if not dec_fused:
+            hcur = ws["tgt"]
+            qkvs = []
+            inter = torch.empty(B, nl, N, 256, **f32)
+        for i, lay in enumerate(() if dec_fused else self.dec):
             t1, t2, t3 = [b for b in hbuf if b is not hcur][:3]
             if i == 0:
                 qkv, t1, offaw_i = ws["dec0"]

@@ -315,6 +315,41 @@ int egtr_relation_head_fwd_f32(const float* const* q_ptrs, const float* const* k
                                float* U_scratch, float* V_scratch, int* cls_scratch, float* pred_rel, float* pred_conn,
                                egtr_stream_t s);
 
+/* ---------------------------------------------------------------- fused decoder stack (decoder.cu) */
+/* Replaces, for small query sets (N <= 256), the launch sequence of DeformableDetrDecoder.forward
+ * (model/deformable_detr.py:1774-1968; layer 1390-1489; self-attention with Q/K capture 1149-1262) by ONE kernel: a cluster of
+ * eight CTAs per image, every GEMM on tcgen05.  Weights are stacked over the layers as bf16 hi/lo planes [2][L*rows][K]
+ * (egtr_split_weight_bf16 with Npad = L*rows): */
+typedef struct {
+  int layers;              /* L */
+  int n_queries;           /* N */
+  const void* w_qkv;       /* rows per layer 768, head-major: head r = q_r (32 rows, pre-scaled by head_dim^-0.5) | k_r | v_r; K = 256 */
+  const void* w_o;         /* 256 rows: self_attn.out_proj */
+  const void* w_offaw;     /* 384 rows: encoder_attn.sampling_offsets (256) | attention_weights (128) */
+  const void* w_out;       /* 256 rows: encoder_attn.output_proj */
+  const void* w_fc1;       /* 1024 rows */
+  const void* w_fc2;       /* 256 rows, K = 1024 */
+  const float* vec;        /* [L][3328]: out_proj.bias | output_proj.bias | fc2.bias | ln1 w,b | ln2 w,b | ln3 w,b (256 each) | fc1.bias (1024) */
+  const float* qkv_pos;    /* [L][N][768] = query_pos . Wq|Wk^T + bias (v columns: bias only), columns q | k | v as captured */
+  const float* off_pos;    /* [L][N][384] = query_pos . Woffaw^T + bias */
+  const float* tgt;        /* [N][256] learned query embeddings (layer-0 input) */
+  const float* ref_points; /* [N][2] sigmoid'ed reference points */
+} egtr_decoder_weights_t;
+
+long long egtr_decoder_scratch_bytes(int B, int N);
+/* Diagnostic: code of the barrier wait that timed out inside the decoder kernel (0: none); readable after the launch failure. */
+int egtr_decoder_fault(void);
+/* value_h16: the six cross-attention value tensors as fp16 pair records [layers*8 heads][B*S + 1][2][32] (EGTR_FMT_H16PAIR),
+ * head index = layer*8 + head.  Outputs: qkv_out [L][B*N][768] (q scaled | k | v of every layer's self-attention: the captured
+ * states of model/egtr.py:322-345), inter [B][L][N][256] (hidden state after every layer).  scratch: 1 KB aligned,
+ * egtr_decoder_scratch_bytes(B, N) bytes, ZERO-INITIALISED once by the caller.  Layers [layer0, layer1); phase0 / phase1 bound
+ * the phases of the first / last of them (0 .. 12: init, qkv, mha, out_proj, ln1, offsets, msda, output_proj, ln2, fc1, fc2,
+ * ln3) — the full stack is (0, L, 0, 12).  mha_mode 1: self-attention core inside the kernel; 0: skipped (bring-up: the caller
+ * runs egtr_mha_core between two launches and provides attn as P32 rows at scratch offset 7*B*N KB). */
+int egtr_decoder_fused_f32(const egtr_decoder_weights_t* w, void* scratch, const void* value_h16, long long records,
+                           const int* shapes_hw, int n_levels, const float* valid_ratios, int B, int S, float* qkv_out,
+                           float* inter, int layer0, int layer1, int phase0, int phase1, int mha_mode, egtr_stream_t s);
+
 /* ---------------------------------------------------------------- triplet extraction */
 /* Device-side equivalent of the model-output post-processing in train_egtr.py:56-94 (multiple predicates per pair,
  * single == 0) and 56-69 + 120-128 (one entry per pair, single == 1): object scores/classes from softmax(logits)
