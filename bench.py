@@ -204,7 +204,7 @@ def summarize(trace, n_forwards, sms):
         t[0] += 1
         t[1] += us
         # a persistent one-CTA-per-SM grid of g CTAs holds g / sms of the GPU; other kernels (many small CTAs per SM) are charged in full
-        persistent = name.startswith(("gemm_p32_kernel", "gemm_sbf16_kernel", "relhead_kernel"))
+        persistent = name.startswith(("gemm_p32_kernel", "gemm_sbf16_kernel", "relhead_kernel", "decoder_kernel"))
         t[2] += us * (min(1.0, ctas / sms) if persistent else 1.0)
         t[3] += ctas
     return {k: dict(n=v[0] / n_forwards, us=v[1] / n_forwards, us_sm_weighted=v[2] / n_forwards, avg_ctas=v[3] / max(1, v[0])) for k, v in tot.items()}

@@ -100,6 +100,7 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p, _p],
     "egtr_decoder_scratch_bytes": [_i, _i],
     "egtr_decoder_fault": [],
+    "egtr_decoder_debug_profile": [_p],
     "egtr_decoder_fused_f32": [C.POINTER(DecoderWeights), _p, _p, _ll, C.POINTER(_i), _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "egtr_relation_finish_f32": [_p, _i, _p, _i, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p],
 }

@@ -147,9 +147,10 @@ class Engine:
         # MSDeformAttn `value` storage: "h16" = fp16 pair records written by the value_proj GEMM's epilogue (half the L1 wavefronts
         # of the bilinear gather, include/egtr_b200.h EGTR_FMT_H16PAIR), "f32" = fp32 rows [S, 256] (round 1; dev A/B)
         self.msda_value = os.environ.get("EGTR_MSDA_VALUE", "h16")
-        # decoder stack for small query sets: "fused" = ONE cluster kernel for all layers (decoder.cu), "layers" = the round-1/2
-        # sequence of skinny CUDA-core GEMMs (ten launches per layer; dev A/B and the cross-check of the fused kernel)
-        self.decoder_mode = os.environ.get("EGTR_DECODER", "fused")
+        # decoder stack for small query sets: "fused" = ONE cluster kernel for all layers (decoder.cu: 8 SMs for ~0.9 ms),
+        # "layers" = the sequence of skinny CUDA-core GEMMs (ten launches per layer over the whole GPU: 0.76 ms alone, but 10 % of
+        # the step once eight forwards are in flight); "auto" (default) = fused for forwards in flight, layers for a lone forward
+        self.decoder_mode = os.environ.get("EGTR_DECODER", "auto")
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
@@ -288,7 +289,8 @@ class Engine:
             wo.append(sd[p + "self_attn.out_proj.weight"])
             ow = torch.cat([sd[p + "encoder_attn.sampling_offsets.weight"], sd[p + "encoder_attn.attention_weights.weight"]], 0)
             ob = torch.cat([sd[p + "encoder_attn.sampling_offsets.bias"], sd[p + "encoder_attn.attention_weights.bias"]], 0)
-            woff.append(ow)
+            # kernel weight rows head-major: head r = its 32 offset rows (columns 32r..) | its 16 logit rows (columns 256 + 16r..)
+            woff.append(torch.cat([torch.cat([ow[32 * r: 32 * r + 32], ow[256 + 16 * r: 256 + 16 * r + 16]], 0) for r in range(8)], 0))
             off_pos.append((qpos @ ow.double().t() + ob.double()).float())
             wout.append(sd[p + "encoder_attn.output_proj.weight"])
             w1.append(sd[p + "fc1.weight"])
@@ -751,7 +753,8 @@ class Engine:
         qpos = ws["qpos"]
         hbuf = ws["dh"]
         dpart = ws["dpart"]
-        dec_fused = (dec_h16 and self.decoder_mode == "fused" and "dec_scratch" in ws and Lv == 4)
+        dec_fused = (dec_h16 and "dec_scratch" in ws and Lv == 4 and
+                     (self.decoder_mode == "fused" or (self.decoder_mode == "auto" and throughput)))
         if dec_fused:
             # ONE launch for the whole stack (decoder.cu): a cluster of eight CTAs per image, every GEMM on tcgen05
             if "ref_done" not in ws:

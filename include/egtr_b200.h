@@ -325,7 +325,7 @@ typedef struct {
   int n_queries;           /* N */
   const void* w_qkv;       /* rows per layer 768, head-major: head r = q_r (32 rows, pre-scaled by head_dim^-0.5) | k_r | v_r; K = 256 */
   const void* w_o;         /* 256 rows: self_attn.out_proj */
-  const void* w_offaw;     /* 384 rows: encoder_attn.sampling_offsets (256) | attention_weights (128) */
+  const void* w_offaw;     /* 384 rows, head-major: head r = its 32 encoder_attn.sampling_offsets rows | its 16 attention_weights rows */
   const void* w_out;       /* 256 rows: encoder_attn.output_proj */
   const void* w_fc1;       /* 1024 rows */
   const void* w_fc2;       /* 256 rows, K = 1024 */
@@ -339,6 +339,8 @@ typedef struct {
 long long egtr_decoder_scratch_bytes(int B, int N);
 /* Diagnostic: code of the barrier wait that timed out inside the decoder kernel (0: none); readable after the launch failure. */
 int egtr_decoder_fault(void);
+/* Diagnostic: device buffer of 1 + layers*12 uint64 that receives %globaltimer at kernel start and after every phase (NULL: off). */
+int egtr_decoder_debug_profile(unsigned long long* dev_buf);
 /* value_h16: the six cross-attention value tensors as fp16 pair records [layers*8 heads][B*S + 1][2][32] (EGTR_FMT_H16PAIR),
  * head index = layer*8 + head.  Outputs: qkv_out [L][B*N][768] (q scaled | k | v of every layer's self-attention: the captured
  * states of model/egtr.py:322-345), inter [B][L][N][256] (hidden state after every layer).  scratch: 1 KB aligned,
