@@ -58,6 +58,7 @@ struct DecMaps {
 struct DecArgs {
   int B, N, L, S, Lv, MT;
   int layer0, layer1, phase0, phase1, mha_mode;
+  int zsplit;  // 1: cluster of 8 (CTA r = head / column slice r); 2: cluster of 16, CTA rank = 8 z + r owns m-tile z
   int plane_rows[6];  // rows of one bf16 plane per weight tensor (qkv, o, offaw, out, fc1, fc2)
   const float* vec;
   const float* qkv_pos;
@@ -65,7 +66,7 @@ struct DecArgs {
   const float* tgt;
   const float* ref;
   const float* valid_ratios;
-  float *hf, *t1f, *t2f, *o, *offaw;
+  float *hf, *t1f, *t2f, *o, *offaw, *part;
   uint8_t *hp, *t1p, *t2p, *attn_p, *attn2_p, *f_p, *qk_p, *vt_p;
   float* qkv;    // [L][B*N][768]
   float* inter;  // [B][L][N][256]
@@ -92,6 +93,8 @@ struct Ctx {
   uint64_t *full, *empty, *acc_full, *mha_bar;
   uint32_t tmem;
   int warp, lane, r, b;
+  int mt_lo, nmt;          // this CTA's m-tiles [mt_lo, mt_lo + nmt): all of them, or one when a 16-CTA cluster splits the rows
+  int row_lo, row_hi;      // ... = its rows for the row-wise phases
   Pipe pt, pm;     // operand ring position of the TMA thread / the MMA warp (identical sequences)
   uint32_t gp;     // parity of acc_full: flips with every GEMM phase
   uint32_t mp;     // parity of the MHA barriers: flips with every MHA phase
@@ -159,47 +162,100 @@ __device__ __forceinline__ unsigned long long gtime() {
 // instantiations, rolled loops with explicit software prefetch — the layer loop's whole footprint stays cache-resident.
 __device__ __noinline__ void mbar_wait_ni(uint64_t* bar, uint32_t parity, int* err, int code) { ptx::mbar_wait(bar, parity, err, code); }
 
+// ------------------------------------------------------------------------------------------------ warp row transposition
+// The TMEM read hands every lane one ROW of a 32-column chunk (128 contiguous bytes).  Written (or read) straight from there, each
+// vector instruction touches 32 different cache lines and the load/store unit serialises them (the first version spent ~7 of the
+// QKV phase's 18 us there).  A 4 KB per-warp staging tile (chunk index XOR row, conflict-free both ways) turns that into
+// instructions that cover 4 rows x 128 bytes.
+constexpr int STG_BYTES = 4 * 4096;  // four epilogue warps; the top of the ring region (a GEMM phase's stages stay below it)
+__device__ __forceinline__ void warp_store_rows(uint32_t stg, int lane, const uint32_t (&o)[32], uint8_t* base, long long stride, int nrows, int nbytes) {
+  const uint32_t mine = stg + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + ((ch ^ sw) << 4)), "r"(o[4 * ch]), "r"(o[4 * ch + 1]), "r"(o[4 * ch + 2]),
+                 "r"(o[4 * ch + 3]) : "memory");
+  __syncwarp();
+  const int c16 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + row * 128 + ((c16 ^ (row & 7)) << 4)) : "memory");
+    if (row < nrows && c16 * 16 < nbytes) *(uint4*)(base + row * stride + c16 * 16) = v;
+  }
+  __syncwarp();
+}
+// v[32] += the lane's row of a [rows x nbytes] fp32 block read the same way (weights-derived data: the nc path is fine)
+__device__ __forceinline__ void warp_add_rows(uint32_t stg, int lane, float (&v)[32], const uint8_t* base, long long stride, int nrows, int nbytes) {
+  const int c16 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (row < nrows && c16 * 16 < nbytes) x = __ldg((const uint4*)(base + row * stride + c16 * 16));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + row * 128 + ((c16 ^ (row & 7)) << 4)), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+  }
+  __syncwarp();
+  const uint32_t mine = stg + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 x;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(mine + ((ch ^ sw) << 4)) : "memory");
+    v[4 * ch] += __uint_as_float(x.x); v[4 * ch + 1] += __uint_as_float(x.y); v[4 * ch + 2] += __uint_as_float(x.z); v[4 * ch + 3] += __uint_as_float(x.w);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM phase
-// D[rows of image b, this CTA's ncols columns] = A[rows, K] . W[w_row0 .. w_row0 + ncols, K]^T, K = 64 * kblocks, ncols in
-// {32, 48, 96, 128}.  Epilogue kinds (32-column chunks of one row):
-enum GemmKind { GK_QKV = 0, GK_O, GK_OFFAW, GK_FC1 };
+// D[this CTA's rows of image b, its ncols columns] = A[rows, a_col0 + K] . W[w_row0 .. w_row0 + ncols, w_col0 + K]^T, K = 64 * kblocks,
+// ncols in {32, 48, 96, 128, 256}.  Epilogue kinds (32-column chunks of 32 rows per warp):
+//   GK_QKV   + row bias -> fp32 q|k|v rows (captured), q / k also as P32 operand rows, v transposed (the PV product's B operand)
+//   GK_O     + bias -> fp32 `o` columns (out_proj / output_proj; the LayerNorm phase follows)
+//   GK_OFFAW + row bias -> fp32 offsets | logits
+//   GK_FC1   + bias, ReLU -> P32 rows of this CTA's 128 hidden columns
+//   GK_PART  raw partial sums of fc2 over this CTA's 128 hidden columns (split-K: the A operand is what THIS CTA wrote in FC1 —
+//            no cluster barrier, 1/4 of the operand bytes, 24 MMAs of N = 256 instead of 192 of N = 32); LN3 adds the eight planes
+enum GemmKind { GK_QKV = 0, GK_O, GK_OFFAW, GK_FC1, GK_PART };
 struct GemmJob {
   const CUtensorMap* ta;
   const CUtensorMap* tw;
-  int w_row0, plane_rows, ncols, kblocks, kind, layer;
+  int a_col0, w_row0, w_col0, plane_rows, ncols, kblocks, kind, layer;
   const float* bias;  // GK_O: 32 bias values of this CTA's columns; GK_FC1: 128
 };
 
 __device__ __forceinline__ void gemm_phase(Ctx& c, const DecArgs& a, const GemmJob& j) {
   const int ncols = j.ncols, kblocks = j.kblocks;
   const int stage_bytes = 2 * GROUP_BYTES + ncols * 256;
-  const int nstages = min(MAX_STAGES, RING_BYTES / stage_bytes);
+  const int nstages = min(MAX_STAGES, (RING_BYTES - STG_BYTES) / stage_bytes);
+  const int acc_stride = ncols > 128 ? 256 : 128;  // TMEM columns between the accumulators of two m-tiles
   c.pt.stage = c.pm.stage = 0;
   if (c.warp == TMA_WARP) {
     if (c.lane == 0) {
 #pragma unroll 1
-      for (int i = 0; i < a.MT * kblocks; ++i) {
-        const int mt = i / kblocks, kb = i - mt * kblocks;
+      for (int i = 0; i < c.nmt * kblocks; ++i) {
+        const int lm = i / kblocks, kb = i - lm * kblocks, mt = c.mt_lo + lm;
         mbar_wait_ni(&c.empty[c.pt.stage], c.pt.parity() ^ 1, a.err, 301);
         const uint32_t st = ptx::smem_u32(c.ring + c.pt.stage * stage_bytes);
         uint64_t* bar = &c.full[c.pt.stage];
         ptx::mbar_arrive_expect_tx(bar, 2 * GROUP_BYTES + 2 * ncols * 128);
-        tma_load_4d(st, j.ta, bar, kb * 128, mt * 128, 0, c.b);
-        tma_load_4d(st + GROUP_BYTES, j.ta, bar, kb * 128 + 64, mt * 128, 0, c.b);
-        tma_load_2d_s(st + 2 * GROUP_BYTES, j.tw, bar, kb * BK, j.w_row0);
-        tma_load_2d_s(st + 2 * GROUP_BYTES + ncols * 128, j.tw, bar, kb * BK, j.plane_rows + j.w_row0);
+        tma_load_4d(st, j.ta, bar, 2 * j.a_col0 + kb * 128, mt * 128, 0, c.b);
+        tma_load_4d(st + GROUP_BYTES, j.ta, bar, 2 * j.a_col0 + kb * 128 + 64, mt * 128, 0, c.b);
+        tma_load_2d_s(st + 2 * GROUP_BYTES, j.tw, bar, j.w_col0 + kb * BK, j.w_row0);
+        tma_load_2d_s(st + 2 * GROUP_BYTES + ncols * 128, j.tw, bar, j.w_col0 + kb * BK, j.plane_rows + j.w_row0);
         c.pt.advance(nstages);
       }
     }
   } else if (c.warp == MMA_WARP) {
     const uint32_t idesc = ptx::umma_idesc_bf16(128, ncols);
 #pragma unroll 1
-    for (int i = 0; i < a.MT * kblocks; ++i) {
-      const int mt = i / kblocks, kb = i - mt * kblocks;
+    for (int i = 0; i < c.nmt * kblocks; ++i) {
+      const int lm = i / kblocks, kb = i - lm * kblocks;
       mbar_wait_ni(&c.full[c.pm.stage], c.pm.parity(), a.err, 302);
       ptx::tc_fence_after();
       if (c.lane == 0) {
-        const uint32_t d_tmem = c.tmem + mt * 128;
+        const uint32_t d_tmem = c.tmem + lm * acc_stride;
         const uint32_t a0 = ptx::smem_u32(c.ring + c.pm.stage * stage_bytes);
         const uint32_t b_hi = a0 + 2 * GROUP_BYTES, b_lo = b_hi + ncols * 128;
 #pragma unroll 1
@@ -212,75 +268,81 @@ __device__ __forceinline__ void gemm_phase(Ctx& c, const DecArgs& a, const GemmJ
           ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
         }
         ptx::umma_commit(&c.empty[c.pm.stage]);
-        if (kb == kblocks - 1) ptx::umma_commit(&c.acc_full[mt]);
+        if (kb == kblocks - 1) ptx::umma_commit(&c.acc_full[lm]);
       }
       __syncwarp();
       c.pm.advance(nstages);
     }
   } else if (c.warp < 4) {
     const int N = a.N, r = c.r, l = j.layer, kind = j.kind;
+    const uint32_t stg = ptx::smem_u32(c.ring + RING_BYTES - STG_BYTES + c.warp * 4096);
 #pragma unroll 1
-    for (int mt = 0; mt < a.MT; ++mt) {
-      mbar_wait_ni(&c.acc_full[mt], c.gp, a.err, 303);
+    for (int lm = 0; lm < c.nmt; ++lm) {
+      mbar_wait_ni(&c.acc_full[lm], c.gp, a.err, 303);
       ptx::tc_fence_after();
-      const int row = mt * 128 + c.warp * 32 + c.lane;
-      const long long grow = (long long)c.b * N + row;
-      const uint32_t t_addr = c.tmem + ((uint32_t)(c.warp * 32) << 16) + mt * 128;
+      const int row0 = (c.mt_lo + lm) * 128 + c.warp * 32;  // this warp's first row; lane = row0 + lane
+      const long long grow0 = (long long)c.b * N + row0;
+      const int nrows = max(0, min(32, N - row0));
+      const uint32_t t_addr = c.tmem + ((uint32_t)(c.warp * 32) << 16) + lm * acc_stride;
 #pragma unroll 1
       for (int ch = 0; ch < ((ncols + 31) >> 5); ++ch) {  // a 16-column tail chunk reads 16 junk columns: ignored below
         uint32_t rr[32];
         ptx::tmem_ld_32x32(t_addr + ch * 32, rr);
         ptx::tmem_ld_wait();
-        if (row >= N) continue;
-        // where this chunk goes: additive term (row bias or bias), fp32 destination, P32 destination, V^T destination
-        const float* addp;
-        float* dstf = nullptr;
-        uint8_t* dstp = nullptr;
-        uint8_t* dstvt = nullptr;
-        int nvalid = 32;
+        if (nrows == 0) continue;  // warp-uniform
+        // where this chunk goes: additive term (row bias block or bias vector), fp32 / P32 / V^T destinations of the warp's rows
+        const uint8_t* addrows = nullptr;
+        const float* addvec = nullptr;
+        uint8_t *dstf = nullptr, *dstp = nullptr, *dstvt = nullptr;
+        long long add_stride = 0, f_stride = 0, p_stride = 0;
+        int nbytes = 128;
         float floor_v = -INFINITY;
         if (kind == GK_QKV) {          // head-major weight rows q_r | k_r | v_r -> the standard q | k | v row layout
           const int gcol = ch * 256 + r * 32;
-          addp = a.qkv_pos + ((long long)l * N + row) * 768 + gcol;
-          dstf = a.qkv + ((long long)l * a.B * N + grow) * 768 + gcol;
+          addrows = (const uint8_t*)(a.qkv_pos + ((long long)l * N + row0) * 768 + gcol); add_stride = 3072;
+          dstf = (uint8_t*)(a.qkv + ((long long)l * a.B * N + grow0) * 768 + gcol); f_stride = 3072;
           if (a.mha_mode) {
-            if (ch < 2) dstp = a.qk_p + grow * 2048 + (ch * 8 + r) * 128;  // P32 groups r (q) and 8 + r (k) of [B*N, 512]
-            else dstvt = a.vt_p + ((long long)c.b * 256 + r * 32) * 1024 + (row >> 5) * 128 + (row & 31) * 2;
+            if (ch < 2) { dstp = a.qk_p + grow0 * 2048 + (ch * 8 + r) * 128; p_stride = 2048; }  // P32 groups r (q), 8 + r (k) of [B*N, 512]
+            else dstvt = a.vt_p + ((long long)c.b * 256 + r * 32) * 1024 + ((row0 + c.lane) >> 5) * 128 + ((row0 + c.lane) & 31) * 2;
           }
         } else if (kind == GK_O) {
-          addp = j.bias;
-          dstf = a.o + grow * 256 + r * 32;
+          addvec = j.bias;
+          dstf = (uint8_t*)(a.o + grow0 * 256 + r * 32); f_stride = 1024;
         } else if (kind == GK_OFFAW) {  // head r: 32 sampling offsets | 16 attention logits -> [256 offsets | 128 logits] rows
           const int gcol = ch == 0 ? r * 32 : 256 + r * 16;
-          nvalid = ch == 0 ? 32 : 16;
-          addp = a.off_pos + ((long long)l * N + row) * 384 + gcol;
-          dstf = a.offaw + grow * 384 + gcol;
-        } else {                        // GK_FC1: ReLU, P32 rows
-          addp = j.bias + ch * 32;
+          nbytes = ch == 0 ? 128 : 64;
+          addrows = (const uint8_t*)(a.off_pos + ((long long)l * N + row0) * 384 + gcol); add_stride = 1536;
+          dstf = (uint8_t*)(a.offaw + grow0 * 384 + gcol); f_stride = 1536;
+        } else if (kind == GK_FC1) {    // ReLU, P32 rows
+          addvec = j.bias + ch * 32;
           floor_v = 0.f;
-          dstp = a.f_p + grow * 4096 + (r * 4 + ch) * 128;
+          dstp = a.f_p + grow0 * 4096 + (r * 4 + ch) * 128; p_stride = 4096;
+        } else {                        // GK_PART: plane r of the fc2 partial sums
+          dstf = (uint8_t*)(a.part + ((long long)r * a.B * N + grow0) * 256 + ch * 32); f_stride = 1024;
         }
         float v[32];
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (4 * q4 < nvalid) b4 = __ldg((const float4*)addp + q4);
-          v[4 * q4] = fmaxf(__uint_as_float(rr[4 * q4]) + b4.x, floor_v);
-          v[4 * q4 + 1] = fmaxf(__uint_as_float(rr[4 * q4 + 1]) + b4.y, floor_v);
-          v[4 * q4 + 2] = fmaxf(__uint_as_float(rr[4 * q4 + 2]) + b4.z, floor_v);
-          v[4 * q4 + 3] = fmaxf(__uint_as_float(rr[4 * q4 + 3]) + b4.w, floor_v);
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rr[k]);
+        if (addrows != nullptr) warp_add_rows(stg, c.lane, v, addrows, add_stride, nrows, nbytes);
+        if (addvec != nullptr) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = __ldg((const float4*)addvec + q4);
+            v[4 * q4] += b4.x; v[4 * q4 + 1] += b4.y; v[4 * q4 + 2] += b4.z; v[4 * q4 + 3] += b4.w;
+          }
         }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], floor_v);
         if (dstf != nullptr) {
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4)
-            if (4 * q4 < nvalid) *((float4*)dstf + q4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+          for (int k = 0; k < 32; ++k) rr[k] = __float_as_uint(v[k]);
+          warp_store_rows(stg, c.lane, rr, dstf, f_stride, nrows, nbytes);
         }
         if (dstp != nullptr) {
-          uint32_t o[32];
-          split_group(v, o);
-          store_group_global(dstp, o);
+          split_group(v, rr);
+          warp_store_rows(stg, c.lane, rr, dstp, p_stride, nrows, 128);
         }
-        if (dstvt != nullptr) {  // v_r transposed: row (b, 32 r + d) of the [B*256, 256-key] P32 matrix, key = this query
+        if (dstvt != nullptr && c.lane < nrows) {  // v_r transposed: row (b, 32 r + d) of the [B*256, 256-key] P32 matrix, key = this query
 #pragma unroll
           for (int d = 0; d < 32; ++d) {
             const __nv_bfloat16 h = __float2bfloat16_rn(v[d]);
@@ -316,8 +378,9 @@ __device__ __forceinline__ void store_row_p32(uint8_t* base, long long grow, int
 
 // out = LayerNorm(o + res) * gamma + beta over 256 channels (deformable_detr.py:1417, 1447, 1477); also the P32 copy the next
 // GEMM streams and, for the layer output, the stacked intermediate state.  `o == nullptr`: out = res (the layer-0 input).
-__device__ __forceinline__ void ln_phase(const Ctx& c, const DecArgs& a, const float* o, const float* res, long long res_bstride, const float* gamma,
-                                      const float* beta, float* outf, uint8_t* outp, float* out2) {
+// `nparts` > 1: `o` holds that many partial-sum planes [nparts][B*N][256] (fc2's split-K) and `obias` their bias.
+__device__ __forceinline__ void ln_phase(const Ctx& c, const DecArgs& a, const float* o, int nparts, const float* obias, const float* res,
+                                      long long res_bstride, const float* gamma, const float* beta, float* outf, uint8_t* outp, float* out2) {
   float4 g0, g1, b0, b1;
   if (o != nullptr) {
     g0 = __ldg((const float4*)gamma + 2 * c.lane); g1 = __ldg((const float4*)gamma + 2 * c.lane + 1);
@@ -331,17 +394,23 @@ __device__ __forceinline__ void ln_phase(const Ctx& c, const DecArgs& a, const f
     nr0 = __ldcg(rp); nr1 = __ldcg(rp + 1);
     no0 = no1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (o != nullptr) {
-      const float4* op = (const float4*)(o + grow * 256) + 2 * c.lane;
-      no0 = __ldcg(op); no1 = __ldcg(op + 1);
+      if (obias != nullptr) { no0 = __ldg((const float4*)obias + 2 * c.lane); no1 = __ldg((const float4*)obias + 2 * c.lane + 1); }
+#pragma unroll 1
+      for (int p = 0; p < nparts; ++p) {  // fixed order: bit-identical from run to run
+        const float4* op = (const float4*)(o + ((long long)p * a.B * a.N + grow) * 256) + 2 * c.lane;
+        const float4 x0 = __ldcg(op), x1 = __ldcg(op + 1);
+        no0.x += x0.x; no0.y += x0.y; no0.z += x0.z; no0.w += x0.w;
+        no1.x += x1.x; no1.y += x1.y; no1.z += x1.z; no1.w += x1.w;
+      }
     }
   };
-  int row = 8 * c.r + c.warp;
-  if (row < a.N) load(row);
+  int row = c.row_lo + 8 * c.r + c.warp;
+  if (row < c.row_hi) load(row);
 #pragma unroll 1
-  for (; row < a.N; row += 64) {
+  for (; row < c.row_hi; row += 64) {
     const long long grow = (long long)c.b * a.N + row;
     float x[8] = {no0.x + nr0.x, no0.y + nr0.y, no0.z + nr0.z, no0.w + nr0.w, no1.x + nr1.x, no1.y + nr1.y, no1.z + nr1.z, no1.w + nr1.w};
-    if (row + 64 < a.N) load(row + 64);
+    if (row + 64 < c.row_hi) load(row + 64);
     if (o != nullptr) {
       float s = 0.f;
 #pragma unroll
@@ -382,15 +451,15 @@ __device__ __forceinline__ void msda_phase(const Ctx& c, const DecArgs& a, int l
   auto load = [&](int q) {
     off_n = make_float2(0.f, 0.f);
     lg_n = 0.f;
-    if (q < a.N) {
+    if (q < c.row_hi) {
       const float* row = a.offaw + ((long long)b * a.N + q) * 384;
       off_n = __ldcg((const float2*)(row + (m * 16 + s) * 2));
       lg_n = __ldcg(row + 256 + m * 16 + s);
     }
   };
-  load(tid >> 4);
+  load(c.row_lo + (tid >> 4));
 #pragma unroll 1
-  for (int q = tid >> 4; q < ((a.N + 15) & ~15); q += 16) {  // warp-uniform trip count: the 16-lane shuffles stay convergent
+  for (int q = c.row_lo + (tid >> 4); q < c.row_lo + ((c.row_hi - c.row_lo + 15) & ~15); q += 16) {  // warp-uniform trip count: the 16-lane shuffles stay convergent
     const float2 off = off_n;
     const float lg = lg_n;
     load(q + 16);
@@ -402,7 +471,7 @@ __device__ __forceinline__ void msda_phase(const Ctx& c, const DecArgs& a, int l
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float wgt = __fdividef(e, sum);
-    if (q < a.N) {
+    if (q < c.row_hi) {
       int idx0 = 0, idx1 = 0;
       float cw[4] = {0.f, 0.f, 0.f, 0.f};
       const float2 rp = __ldg((const float2*)(a.ref + (long long)q * 2));
@@ -422,7 +491,7 @@ __device__ __forceinline__ void msda_phase(const Ctx& c, const DecArgs& a, int l
         if (y1 && x0) cw[2] = lh * hw * wgt;
         if (y1 && x1) cw[3] = lh * lw * wgt;
       }
-      float* slot = &slots[q * Q_STRIDE + s * SLOT_WORDS];
+      float* slot = &slots[(q - c.row_lo) * Q_STRIDE + s * SLOT_WORDS];
       *(int2*)slot = make_int2(idx0, idx1);
       *(float4*)(slot + 4) = make_float4(cw[0], cw[1], cw[2], cw[3]);
     }
@@ -432,10 +501,10 @@ __device__ __forceinline__ void msda_phase(const Ctx& c, const DecArgs& a, int l
   const int half = (tid >> 2) & 1, j8 = (tid & 3) * 8;
   const uint8_t* hb = a.value_h16 + ((long long)(layer * CL + m) * a.records) * 128 + half * 64 + j8 * 2;
 #pragma unroll 1
-  for (int q = tid >> 3; q < a.N; q += THREADS / 8) {
+  for (int q = c.row_lo + (tid >> 3); q < c.row_hi; q += THREADS / 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* myslots = &slots[q * Q_STRIDE];
-#pragma unroll 8
+    const float* myslots = &slots[(q - c.row_lo) * Q_STRIDE];
+#pragma unroll 16
     for (int ss = 0; ss < 16; ++ss) {
       const int2 id = *(const int2*)(myslots + ss * SLOT_WORDS);
       const float4 w = *(const float4*)(myslots + ss * SLOT_WORDS + 4);
@@ -472,8 +541,8 @@ __device__ __forceinline__ void mha_phase(Ctx& c, const DecArgs& a, const DecMap
   if (c.warp == TMA_WARP) {
     if (c.lane == 0) {
       uint64_t* bar = &c.mha_bar[0];
-      ptx::mbar_arrive_expect_tx(bar, (a.MT + 2) * GROUP_BYTES + kg * 4096);
-      for (int mt = 0; mt < a.MT; ++mt) tma_load_4d(ptx::smem_u32(sm + MHA_Q + mt * GROUP_BYTES), &maps.a_qk, bar, c.r * 64, mt * 128, 0, c.b);
+      ptx::mbar_arrive_expect_tx(bar, (c.nmt + 2) * GROUP_BYTES + kg * 4096);
+      for (int lm = 0; lm < c.nmt; ++lm) tma_load_4d(ptx::smem_u32(sm + MHA_Q + lm * GROUP_BYTES), &maps.a_qk, bar, c.r * 64, (c.mt_lo + lm) * 128, 0, c.b);
       for (int t = 0; t < 2; ++t) tma_load_4d(ptx::smem_u32(sm + MHA_K + t * GROUP_BYTES), &maps.a_qk, bar, (8 + c.r) * 64, t * 128, 0, c.b);
 #pragma unroll 1
       for (int g = 0; g < kg; ++g) tma_load_2d_s(ptx::smem_u32(sm + MHA_VT + g * 4096), &maps.a_vt, bar, g * 64, c.b * 256 + c.r * 32);
@@ -485,8 +554,8 @@ __device__ __forceinline__ void mha_phase(Ctx& c, const DecArgs& a, const DecMap
       const uint32_t idesc = ptx::umma_idesc_bf16(128, 256);
       const uint32_t kt = ptx::smem_u32(sm + MHA_K);
 #pragma unroll 1
-      for (int i = 0; i < 2 * a.MT; ++i) {
-        const int mt = i >> 1, ks = i & 1;
+      for (int i = 0; i < 2 * c.nmt; ++i) {
+        const int mt = i >> 1, ks = i & 1;  // local m-tile
         const uint32_t qt = ptx::smem_u32(sm + MHA_Q + mt * GROUP_BYTES);
         const uint64_t dah = ptx::umma_desc_sw128(qt + ks * 32), dal = ptx::umma_desc_sw128(qt + ks * 32 + 64);
         const uint64_t dbh = ptx::umma_desc_sw128(kt + ks * 32), dbl = ptx::umma_desc_sw128(kt + ks * 32 + 64);
@@ -498,7 +567,7 @@ __device__ __forceinline__ void mha_phase(Ctx& c, const DecArgs& a, const DecMap
     }
     __syncwarp();
 #pragma unroll 1
-    for (int mt = 0; mt < a.MT; ++mt) {
+    for (int mt = 0; mt < c.nmt; ++mt) {
       mbar_wait_ni(&c.mha_bar[3], c.pp ^ (uint32_t)(mt & 1), a.err, 312);
       ptx::tc_fence_after();
       if (c.lane == 0) {
@@ -520,10 +589,10 @@ __device__ __forceinline__ void mha_phase(Ctx& c, const DecArgs& a, const DecMap
   } else if (c.warp < 4) {
     const int sw = c.lane & 7;
 #pragma unroll 1
-    for (int mt = 0; mt < a.MT; ++mt) {
+    for (int mt = 0; mt < c.nmt; ++mt) {
       mbar_wait_ni(&c.mha_bar[1 + mt], c.mp, a.err, 313);
       ptx::tc_fence_after();
-      const int row = mt * 128 + c.warp * 32 + c.lane;
+      const int row = (c.mt_lo + mt) * 128 + c.warp * 32 + c.lane;
       const uint32_t t_addr = c.tmem + ((uint32_t)(c.warp * 32) << 16) + mt * 256;
       uint32_t rr[32];
       float mx = -INFINITY;
@@ -562,27 +631,30 @@ __device__ __forceinline__ void mha_phase(Ctx& c, const DecArgs& a, const DecMap
       ptx::tc_fence_after();
       ptx::tmem_ld_32x32(t_addr, rr);
       ptx::tmem_ld_wait();
-      if (row < a.N) {
+      {
+        const int row0 = row - c.lane, nrows = max(0, min(32, a.N - row0));
         const float inv = 1.f / sum;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * inv;
-        uint32_t o[32];
-        split_group(v, o);
-        store_group_global(a.attn_p + ((long long)c.b * a.N + row) * 1024 + c.r * 128, o);
+        split_group(v, rr);
+        // (the P tile's last group may overlap the staging tile: the PV product that read it has completed)
+        if (nrows > 0)
+          warp_store_rows(ptx::smem_u32(sm + RING_BYTES - STG_BYTES + c.warp * 4096), c.lane, rr, a.attn_p + ((long long)c.b * a.N + row0) * 1024 + c.r * 128,
+                          1024, nrows, 128);
       }
       // the next m-tile's softmax rewrites the P tile: its PV product has completed (mha_bar[4 + mt])
     }
   }
   c.mp ^= 1;
-  c.pp ^= (uint32_t)(a.MT & 1);
+  c.pp ^= (uint32_t)(c.nmt & 1);
   ptx::tc_fence_before();
   __syncwarp();
   __syncthreads();
   ptx::tc_fence_after();
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 decoder_kernel(const __grid_constant__ DecMaps maps, const __grid_constant__ DecArgs a) {
   pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -597,8 +669,12 @@ decoder_kernel(const __grid_constant__ DecMaps maps, const __grid_constant__ Dec
   uint32_t* tmem_holder = (uint32_t*)(c.mha_bar + 6);
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
-  c.r = blockIdx.x;  // == %cluster_ctarank: the cluster spans x
+  c.r = blockIdx.x & (CL - 1);  // blockIdx.x == %cluster_ctarank: the cluster spans x
   c.b = blockIdx.y;
+  c.mt_lo = a.zsplit == 2 ? (int)(blockIdx.x >> 3) : 0;
+  c.nmt = a.zsplit == 2 ? 1 : a.MT;
+  c.row_lo = c.mt_lo * 128;
+  c.row_hi = min(a.N, (c.mt_lo + c.nmt) * 128);
   c.pt = {0, 0};
   c.pm = {0, 0};
   c.gp = 0;
@@ -642,6 +718,7 @@ decoder_kernel(const __grid_constant__ DecMaps maps, const __grid_constant__ Dec
       j.layer = l;
       j.kblocks = 4;
       j.bias = nullptr;
+      j.a_col0 = j.w_col0 = 0;
       bool gemm = true;
       if (ph == PH_QKV) {
         j.ta = &maps.a_h; j.tw = &maps.w_qkv; j.w_row0 = l * 768 + r * 96; j.plane_rows = a.plane_rows[0]; j.ncols = 96; j.kind = GK_QKV;
@@ -657,16 +734,17 @@ decoder_kernel(const __grid_constant__ DecMaps maps, const __grid_constant__ Dec
         j.ta = &maps.a_t2; j.tw = &maps.w_fc1; j.w_row0 = l * 1024 + r * 128; j.plane_rows = a.plane_rows[4]; j.ncols = 128; j.kind = GK_FC1;
         j.bias = vec + 2304 + r * 128;
       } else if (ph == PH_FC2) {
-        j.ta = &maps.a_f; j.tw = &maps.w_fc2; j.w_row0 = l * 256 + r * 32; j.plane_rows = a.plane_rows[5]; j.ncols = 32; j.kind = GK_O;
-        j.kblocks = 16;
-        j.bias = vec + 512 + r * 32;
+        // split-K: this CTA's 128 hidden columns (written by itself in FC1) x all 256 output columns -> partial-sum plane r
+        j.ta = &maps.a_f; j.tw = &maps.w_fc2; j.w_row0 = l * 256; j.plane_rows = a.plane_rows[5]; j.ncols = 256; j.kind = GK_PART;
+        j.kblocks = 2;
+        j.a_col0 = j.w_col0 = r * 128;
       } else {
         gemm = false;
       }
       if (gemm) {
         gemm_phase(c, a, j);
       } else if (ph == PH_INIT) {  // h = the learned query embeddings (deformable_detr.py:2290-2292)
-        if (l == 0) ln_phase(c, a, nullptr, a.tgt, 0, nullptr, nullptr, a.hf, a.hp, nullptr);
+        if (l == 0) ln_phase(c, a, nullptr, 0, nullptr, a.tgt, 0, nullptr, nullptr, a.hf, a.hp, nullptr);
       } else if (ph == PH_MHA) {
         if (a.mha_mode) mha_phase(c, a, maps);
       } else if (ph == PH_MSDA) {
@@ -677,9 +755,10 @@ decoder_kernel(const __grid_constant__ DecMaps maps, const __grid_constant__ Dec
         const float* gam = vec + (ph == PH_LN1 ? 768 : (ph == PH_LN2 ? 1280 : 1792));
         float* outf = ph == PH_LN1 ? a.t1f : (ph == PH_LN2 ? a.t2f : a.hf);
         uint8_t* outp = ph == PH_LN1 ? a.t1p : (ph == PH_LN2 ? a.t2p : a.hp);
-        ln_phase(c, a, a.o, res, nb, gam, gam + 256, outf, outp, ph == PH_LN3 ? a.inter + ((long long)b * a.L + l) * N * 256 : nullptr);
+        if (ph == PH_LN3) ln_phase(c, a, a.part, CL, vec + 512, res, nb, gam, gam + 256, outf, outp, a.inter + ((long long)b * a.L + l) * N * 256);
+        else ln_phase(c, a, a.o, 1, nullptr, res, nb, gam, gam + 256, outf, outp, nullptr);
       }
-      phase_end((ph == PH_QKV && a.mha_mode) || ph == PH_OFFAW, a.dbg);
+      phase_end((ph == PH_QKV && a.mha_mode && a.zsplit == 1) || ph == PH_OFFAW || ph == PH_FC1, a.dbg);
       if (a.prof && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.prof[1 + l * PH_END + ph] = gtime();
     }
   }
@@ -722,8 +801,8 @@ extern "C" int egtr_decoder_fault() { return g_fault_host ? *(volatile int*)g_fa
 
 extern "C" long long egtr_decoder_scratch_bytes(int B, int N) {
   const long long R = (long long)B * N;
-  // hf t1f t2f o (fp32 rows) + hp t1p t2p attn_p attn2_p (P32 rows) = 9 KB per row; offaw 1.5 KB; f_p 4 KB; qk_p 2 KB; + V^T 256 KB per image
-  return R * (9 * 1024 + 1536 + 4096 + 2048) + (long long)B * 256 * 1024 + 1024;
+  // hf t1f t2f o (fp32 rows) + hp t1p t2p attn_p attn2_p (P32 rows) = 9 KB per row; offaw 1.5 KB; f_p 4 KB; qk_p 2 KB; fc2 partial sums 8 KB; + V^T 256 KB per image
+  return R * (9 * 1024 + 1536 + 4096 + 2048 + 8 * 1024) + (long long)B * 256 * 1024 + 1024;
 }
 
 extern "C" int egtr_decoder_fused_f32(const egtr_decoder_weights_t* w, void* scratch, const void* value_h16, long long records,
@@ -756,6 +835,7 @@ extern "C" int egtr_decoder_fused_f32(const egtr_decoder_weights_t* w, void* scr
   a.offaw = (float*)take(R * 1536);
   a.f_p = take(R * 4096);
   a.qk_p = take(R * 2048);
+  a.part = (float*)take(R * 1024 * CL);
   p = (uint8_t*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
   a.vt_p = take((long long)B * 256 * 1024);
   a.qkv = qkv_out; a.inter = inter;
@@ -780,13 +860,33 @@ extern "C" int egtr_decoder_fused_f32(const egtr_decoder_weights_t* w, void* scr
   if ((rc = tmap_weight_planes(w->w_offaw, 256, 2ll * L * 384, 48, &m.w_offaw)) != EGTR_OK) return rc;
   if ((rc = tmap_weight_planes(w->w_out, 256, 2ll * L * 256, 32, &m.w_out)) != EGTR_OK) return rc;
   if ((rc = tmap_weight_planes(w->w_fc1, 256, 2ll * L * 1024, 128, &m.w_fc1)) != EGTR_OK) return rc;
-  if ((rc = tmap_weight_planes(w->w_fc2, 1024, 2ll * L * 256, 32, &m.w_fc2)) != EGTR_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if ((rc = tmap_weight_planes(w->w_fc2, 1024, 2ll * L * 256, 256, &m.w_fc2)) != EGTR_OK) return rc;
+  // A lone forward spreads the stack over a 16-CTA cluster (rank = 8 z + r: m-tile z of head / column slice r) — twice the SMs'
+  // worth of operand ingest, load/store and SIMT throughput for the row-local phases; forwards in flight keep the 8-CTA cluster
+  // (16 co-scheduled SMs of one GPC are hard to come by next to other images' persistent GEMMs).  EGTR_DECODER_CLUSTER=8|16 forces.
+  static int max16 = -1;
+  const char* fe = getenv("EGTR_DECODER_CLUSTER");
+  const int forced = fe ? atoi(fe) : 0;
+  if (max16 < 0) {
     EGTR_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    max16 = 0;
+    if (cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16, 1);
+      cfg.blockDim = dim3(THREADS);
+      cfg.dynamicSmemBytes = SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, decoder_kernel, &cfg) == cudaSuccess) max16 = n;
+    }
+    (void)cudaGetLastError();
   }
-  EGTR_CUDA(launch_pdl(decoder_kernel, dim3(CL, B), dim3(THREADS), (size_t)SMEM_BYTES, (cudaStream_t)s, m, a));
+  a.zsplit = (a.MT == 2 && max16 >= 1 && (forced == 16 || (forced == 0 && grid_div() == 1))) ? 2 : 1;
+  EGTR_CUDA(launch_cluster_pdl(decoder_kernel, dim3(CL * a.zsplit, B), dim3(THREADS), (size_t)SMEM_BYTES, (cudaStream_t)s, CL * a.zsplit, m, a));
   count_launch();
   return EGTR_OK;
 }

@@ -147,10 +147,11 @@ class Engine:
         # MSDeformAttn `value` storage: "h16" = fp16 pair records written by the value_proj GEMM's epilogue (half the L1 wavefronts
         # of the bilinear gather, include/egtr_b200.h EGTR_FMT_H16PAIR), "f32" = fp32 rows [S, 256] (round 1; dev A/B)
         self.msda_value = os.environ.get("EGTR_MSDA_VALUE", "h16")
-        # decoder stack for small query sets: "fused" = ONE cluster kernel for all layers (decoder.cu: 8 SMs for ~0.9 ms),
-        # "layers" = the sequence of skinny CUDA-core GEMMs (ten launches per layer over the whole GPU: 0.76 ms alone, but 10 % of
-        # the step once eight forwards are in flight); "auto" (default) = fused for forwards in flight, layers for a lone forward
-        self.decoder_mode = os.environ.get("EGTR_DECODER", "auto")
+        # decoder stack for small query sets: "fused" (default) = ONE cluster kernel for all layers (decoder.cu: 16 CTAs for a lone
+        # forward, 0.57 ms; 8 CTAs per image for forwards in flight), "layers" = the round-1/2 sequence of skinny CUDA-core GEMMs
+        # (ten launches per layer over the whole GPU: 0.76 ms alone, 10 % of the step with eight forwards in flight; kept as the
+        # cross-check of the fused kernel and for shapes it does not take)
+        self.decoder_mode = os.environ.get("EGTR_DECODER", "fused")
         self.probe: Optional[Dict[str, list]] = None  # bench.py: name -> [(start_event, end_event), ...]
         self.probe_flops: Dict[str, int] = {}         # bench.py: name -> algorithmic FLOPs issued under that span
         with torch.cuda.device(self.device):
@@ -753,8 +754,7 @@ class Engine:
         qpos = ws["qpos"]
         hbuf = ws["dh"]
         dpart = ws["dpart"]
-        dec_fused = (dec_h16 and "dec_scratch" in ws and Lv == 4 and
-                     (self.decoder_mode == "fused" or (self.decoder_mode == "auto" and throughput)))
+        dec_fused = dec_h16 and "dec_scratch" in ws and Lv == 4 and self.decoder_mode == "fused"
         if dec_fused:
             # ONE launch for the whole stack (decoder.cu): a cluster of eight CTAs per image, every GEMM on tcgen05
             if "ref_done" not in ws:

@@ -32,12 +32,16 @@ def _engine(cuda, workload, seed, mode, monkeypatch):
 
 
 # N = 40 (one 128-row tile, two key groups), N = 100, N = 200 (two tiles, seven key groups; one image and two)
-CASES = [("small", 2, (160, 224), [(160, 224), (120, 190)]), ("small", 1, (128, 160), None), ("A", 1, (192, 256), None),
-         ("B", 1, (160, 224), None), ("B", 2, (160, 224), [(160, 224), (128, 200)])]
+# ... each N = 200 case on the 8-CTA cluster (forwards in flight) and on the 16-CTA cluster that splits the rows (a lone forward)
+CASES = [("small", 2, (160, 224), [(160, 224), (120, 190)], 0), ("small", 1, (128, 160), None, 0), ("A", 1, (192, 256), None, 0),
+         ("B", 1, (160, 224), None, 8), ("B", 1, (160, 224), None, 16), ("B", 2, (160, 224), [(160, 224), (128, 200)], 8),
+         ("B", 2, (160, 224), [(160, 224), (128, 200)], 16)]
 
 
-@pytest.mark.parametrize("workload,batch,hw,pad_to", CASES)
-def test_fused_stack_matches_layer_sequence(cuda, monkeypatch, workload, batch, hw, pad_to):
+@pytest.mark.parametrize("workload,batch,hw,pad_to,cluster", CASES)
+def test_fused_stack_matches_layer_sequence(cuda, monkeypatch, workload, batch, hw, pad_to, cluster):
+    if cluster:
+        monkeypatch.setenv("EGTR_DECODER_CLUSTER", str(cluster))
     """Every output of the decoder — the stacked intermediate states (per layer: where would a deviation first appear?), the
     captured self-attention queries / keys of every layer, and everything downstream of them."""
     from egtr_b200.synth import synth_images
