@@ -283,9 +283,11 @@ def main():
     # Throughput mode: `conc` forwards in flight, each a captured CUDA graph (forward + triplet extraction) with its own
     # workspace on its own stream (at batch 1 the decoder and the deep backbone layers are latency-bound chains of small
     # kernels; other images fill the SMs they leave idle).  Inputs rotate over NIMG distinct resident batches (> L2 in total).
-    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", str(max(2, 8 // Bl))))
+    # (batch 1: sixteen images in flight on quarter grids measure +5 % over eight on half grids; at batch 4 - 8 the launches are
+    # long enough that two batches on half grids are best: 415 vs 392 images/s at C, 375 vs 283 at E)
+    conc = int(os.environ.get("EGTR_PIPE_CONCURRENCY", str(16 if Bl == 1 else max(2, 8 // Bl))))
     depth = int(os.environ.get("EGTR_PIPE_DEPTH", str(2 * conc)))
-    NIMG = max(2, 8 // Bl)
+    NIMG = max(2, 8 // Bl)  # distinct resident input batches the forwards rotate over
     px_d = [torch.roll(px, shifts=17 * i, dims=3).to(dev) for i in range(NIMG)]
     mask_d = mask.to(dev)
     in_bytes = NIMG * (px_d[0].numel() * 4 + mask_d.numel() * 8)

@@ -142,7 +142,9 @@ class Engine:
         # forwards in flight (serving): each persistent GEMM takes a share of the SMs (egtr_set_grid_div(2)) so that GEMMs of
         # different images run side by side, +10 % at workload B.  Round 1 found a race in this mode (LayerNorm epilogue, a missing
         # proxy fence); fixed, and re-measured in round 2: 0 / 1188 full-size forwards deviate (profiles/r02_race_matrix.txt).
-        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "2"))
+        # The share: 0 = by batch size — a quarter of the SMs at batch 1 (with sixteen images in flight: +5 % over halves with eight),
+        # half of them for larger batches, whose launches are long enough (quarters measured -6 % at C, -24 % at E).
+        self.throughput_grid_div = int(os.environ.get("EGTR_THROUGHPUT_GRID_DIV", "0"))
         self.throughput_splitk = int(os.environ.get("EGTR_THROUGHPUT_SPLITK", "1"))  # split-K cap of forwards in flight (1 = off)
         # MSDeformAttn `value` storage: "h16" = fp16 pair records written by the value_proj GEMM's epilogue (half the L1 wavefronts
         # of the bilinear gather, include/egtr_b200.h EGTR_FMT_H16PAIR), "f32" = fp32 rows [S, 256] (round 1; dev A/B)
@@ -597,7 +599,7 @@ class Engine:
         cfg, dev = self.cfg, self.device
         call("egtr_set_scratch_slot", slot)
         call("egtr_set_splitk_max", self.throughput_splitk if throughput else 64)
-        call("egtr_set_grid_div", self.throughput_grid_div if throughput else 1)
+        call("egtr_set_grid_div", (self.throughput_grid_div or (4 if pixel_values.shape[0] == 1 else 2)) if throughput else 1)
         st = _stream()
         px = pixel_values.to(torch.float32).contiguous()
         B, Cin, H, W = px.shape
