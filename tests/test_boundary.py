@@ -18,6 +18,10 @@ DROPIN_SCRIPT = textwrap.dedent('''
     sys.path.insert(0, {dropin!r})
     from model.deformable_detr import DeformableDetrConfig, DeformableDetrFeatureExtractor
     from model.egtr import DetrForSceneGraphGeneration
+    from lib.evaluation.coco_eval import CocoEvaluator   # evaluate_egtr.py:15-20
+    from lib.evaluation.oi_eval import OIEvaluator
+    from lib.evaluation.sg_eval import BasicSceneGraphEvaluator, calculate_mR_from_evaluator_list
+    from lib.pytorch_misc import argsort_desc
     import model.egtr, egtr_b200.model.egtr
     assert model.egtr.DetrForSceneGraphGeneration is egtr_b200.model.egtr.DetrForSceneGraphGeneration
     artifact_path = {artifact!r}

@@ -71,3 +71,69 @@ def test_preddet_matches_reference():
         assert ev.evaluate_scene_graph_entry(gt, pred) == (None, None, None)
     for k in (20, 50, 100):
         assert ev.result_dict["preddet_recall"][k] == P[f"recall{k}"].tolist()
+
+
+# ---------------------------------------------------------------------------------------------- Open-Images / COCO evaluators
+def _oi_scenes():
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import make_golden_oieval as mk  # the scene generator only (the reference is not imported)
+    return mk, json.load(open(os.path.join(gdir, "oieval.json")))
+
+
+def test_oi_relation_metrics_match_reference_golden():
+    """w_rel_mAP / w_phr_mAP / microR@50 / score of the unmodified reference (`oi_eval.eval_rel_results`, `ap_eval_rel.ap_eval`) on
+    seeded scenes fed through `OIEvaluator.__call__` in `evaluate_batch`'s entry format (train_egtr.py:154-173)."""
+    from egtr_b200.oi_evaluation import OIEvaluator, eval_rel_results
+    mk, golden = _oi_scenes()
+    for seed, want in golden.items():
+        ev = OIEvaluator([f"p{i}" for i in range(mk.N_PRED_CLS)], [f"c{i}" for i in range(mk.N_CLS)])
+        for gt, pred in mk.scenes(int(seed), want["n_images"]):
+            ev(gt, pred)
+        got = eval_rel_results(ev.all_result, ev.predicate_cls_list)
+        for k in ("w_rel_mAP", "w_phr_mAP", "microR@50", "score"):
+            assert abs(got[k] - want[k]) < 1e-12, (seed, k, got[k], want[k])
+        agg = ev.aggregate_metrics()
+        assert {"w_rel_mAP", "w_phr_mAP", "microR@50", "score", "bbox/AP50"} <= set(agg)
+
+
+def test_coco_box_ap_known_answers():
+    """pycocotools is absent (parity unpinned): the bbox algorithm restated in `CocoBoxEval` against hand-computed cases."""
+    from egtr_b200.oi_evaluation import CocoBoxEval
+    gts = [dict(image_id=0, category_id=1, bbox=[10, 10, 100, 100]), dict(image_id=0, category_id=1, bbox=[200, 200, 100, 100])]
+    # TP (0.9), FP (0.8), TP (0.7): precision 1 up to recall 0.5, 2/3 up to recall 1 -> 101-point AP = (51 + 50 * 2/3) / 101
+    ev = CocoBoxEval(gts)
+    ev.add_detections([dict(image_id=0, category_id=1, bbox=[10, 10, 100, 100], score=0.9), dict(image_id=0, category_id=1, bbox=[400, 400, 50, 50], score=0.8),
+                       dict(image_id=0, category_id=1, bbox=[200, 200, 100, 100], score=0.7)])
+    st = ev.summarize()
+    assert abs(st[1] - (51 + 50 * 2 / 3) / 101) < 1e-9 and abs(st[0] - st[1]) < 1e-9 and abs(st[8] - 1.0) < 1e-9
+    assert abs(st[6] - 0.5) < 1e-9  # AR@1: only the best-scored detection counts
+    # one ground truth, one detection at IoU 0.62: a match at the thresholds 0.50, 0.55, 0.60 only
+    ev = CocoBoxEval([dict(image_id=0, category_id=1, bbox=[0, 0, 100, 100])])
+    ev.add_detections([dict(image_id=0, category_id=1, bbox=[0, 0, 100, 62], score=0.5)])
+    st = ev.summarize()
+    assert abs(st[0] - 0.3) < 1e-9 and abs(st[1] - 1.0) < 1e-9 and st[2] == 0.0
+    # a crowd region absorbs detections without counting them; area ranges: a 20 x 20 box is "small" only
+    ev = CocoBoxEval([dict(image_id=0, category_id=1, bbox=[0, 0, 20, 20]), dict(image_id=0, category_id=1, bbox=[100, 100, 200, 200], iscrowd=1)])
+    ev.add_detections([dict(image_id=0, category_id=1, bbox=[0, 0, 20, 20], score=0.9), dict(image_id=0, category_id=1, bbox=[120, 120, 50, 50], score=0.8)])
+    st = ev.summarize()
+    assert abs(st[1] - 1.0) < 1e-9 and abs(st[3] - 1.0) < 1e-9 and st[4] == -1.0 and st[5] == -1.0
+
+
+def test_coco_evaluator_interface():
+    """`CocoEvaluator` as `evaluate_egtr.py:86-103` drives it: xyxy tensors per image id, labels shifted by +1 (coco_eval.py:44-45)."""
+    import torch
+    from egtr_b200.oi_evaluation import CocoEvaluator
+    ds = dict(images=[dict(id=7), dict(id=9)], categories=[dict(id=1), dict(id=2)],
+              annotations=[dict(id=0, image_id=7, category_id=1, bbox=[10, 20, 30, 40], area=1200, iscrowd=0),
+                           dict(id=1, image_id=9, category_id=2, bbox=[50, 50, 80, 60], area=4800, iscrowd=0)])
+    ev = CocoEvaluator(ds, ["bbox"])
+    ev.update({7: dict(boxes=torch.tensor([[10., 20., 40., 60.]]), scores=torch.tensor([0.9]), labels=torch.tensor([0]))})
+    ev.update({9: dict(boxes=torch.tensor([[50., 50., 130., 110.], [0., 0., 10., 10.]]), scores=torch.tensor([0.8, 0.3]), labels=torch.tensor([1, 1]))})
+    ev.synchronize_between_processes()
+    ev.accumulate()
+    ev.summarize()
+    assert abs(ev.coco_eval["bbox"].stats[1] - 1.0) < 1e-9  # AP50, the number evaluate_egtr.py:103 reports
