@@ -614,8 +614,18 @@ class Engine:
         f32 = dict(dtype=torch.float32, device=dev)
 
         # ---- geometry: masks, position embeddings, valid ratios (deformable_detr.py:783-785, 850-876, 2064-2073)
+        # A lone forward runs it on a side stream next to the backbone (it depends on the mask only; its scan kernel is a 30 us
+        # chain on four CTAs) and joins before the first GroupNorm, which adds the position embeddings; forwards in flight have
+        # other images to fill the GPU with.
+        geo_side = None
+        if not throughput and os.environ.get("EGTR_GEOMETRY_STREAM", "1") == "1":
+            geo_side = ws.get("geo_stream")
+            if geo_side is None:
+                geo_side = ws["geo_stream"] = torch.cuda.Stream(device=dev)
+            geo_side.wait_stream(torch.cuda.current_stream())
         call("egtr_levels_geometry_f32", _ptr(pm), B, H, W, ws["shapes_c"], Lv, _ptr(self.level_embed), _ptr(self.dim_t), d,
-             _ptr(ws["mask_flat"]), _ptr(ws["pos"]), _ptr(ws["valid_ratios"]), _ptr(ws["geo_scratch"]), st)
+             _ptr(ws["mask_flat"]), _ptr(ws["pos"]), _ptr(ws["valid_ratios"]), _ptr(ws["geo_scratch"]),
+             geo_side.cuda_stream if geo_side is not None else st)
 
         # ---- backbone (deformable_detr.py:778): stem 7x7/2 as a gather-GEMM over the NCHW image, max-pool, bottlenecks
         h1, w1 = ws["stem_hw"]
@@ -656,6 +666,9 @@ class Engine:
                 # C3/C4/C5 feed input_proj straight away: 1x1 conv + GroupNorm written into the level's
                 # slice of source_flatten [B,S,256] (deformable_detr.py:2221-2241, 2259-2266)
                 lvl = li - 2
+                if geo_side is not None:
+                    torch.cuda.current_stream().wait_stream(geo_side)
+                    geo_side = None
                 lin, gw, gb = self.input_proj[lvl]
                 hw = h * w
                 self.gemm(lin, B * hw, ws["x"][0], a=x, lda=cin, ldo=256, remap=(hw, S, starts[lvl]), a_fmt=p32)

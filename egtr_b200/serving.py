@@ -80,6 +80,10 @@ class PipelinedRunner:
                 self.slots.append(GraphRunner(eng, batch, height, width, slot=i % self.concurrency, throughput=self.concurrency > 1,
                                               prologue=pro, epilogue=epi))
             self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            # the all-gather of the triplet records gets its own high-priority stream: on the compute streams it would hold them
+            # (and the SMs of its spinning kernel) for as long as the slowest peer is late
+            self.s_comm = torch.cuda.Stream(priority=-1) if self.world > 1 else None
+            self.ev_rep = [torch.cuda.Event() for _ in range(depth)]
             self.s_runs = [torch.cuda.Stream() for _ in range(self.concurrency)]
             self.ev_in = [torch.cuda.Event() for _ in range(depth)]
             self.ev_run = [torch.cuda.Event() for _ in range(depth)]
@@ -127,14 +131,19 @@ class PipelinedRunner:
                 s_run.wait_event(self.ev_in[s])
                 s_run.wait_event(self.ev_out[s])  # outputs of this slot have been read back
                 slot.graph.replay()
-                if self.output == "triplets":
-                    if self.world > 1:  # the path's only collective: per-image triplet records of every rank
-                        self._dist.all_gather_into_tensor(self.res[s]["triplets"], self.records[s].flat)
-                elif self.post is not None:
+                if self.output != "triplets" and self.post is not None:
                     self.res[s] = self.post({k: slot.out[k] for k in RESULT_FIELDS})
                     for v in self.res[s].values():
                         v.record_stream(self.s_out)
-                self.ev_run[s].record(s_run)
+                if self.output == "triplets" and self.world > 1:
+                    self.ev_rep[s].record(s_run)
+                else:
+                    self.ev_run[s].record(s_run)
+            if self.output == "triplets" and self.world > 1:  # the path's only collective: per-image triplet records of every rank
+                with torch.cuda.stream(self.s_comm):
+                    self.s_comm.wait_event(self.ev_rep[s])
+                    self._dist.all_gather_into_tensor(self.res[s]["triplets"], self.records[s].flat)
+                    self.ev_run[s].record(self.s_comm)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[s])
                 for k, v in self.res[s].items():
