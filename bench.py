@@ -20,7 +20,7 @@ Prints ONE JSON line (rank 0).
           inside the timed region.  `e2e_raw` is the round-1 boundary (fp32 pixel_values + int64 mask in, raw logits /
           pred_rel / pred_connectivity out).
   roofline : the kernel with the largest share of the step — the TMA-fed tcgen05 GEMM — from a CUPTI trace (torch.profiler) of
-             the TIMED configuration; `roofline_msda_enc` / `roofline_msda_dec` / `roofline_relation` report the kernels
+             the TIMED configuration; `roofline_msda_enc` / `roofline_msda_dec` / `roofline_decoder` / `roofline_relation` report the kernels
              BASELINE.json names (HBM bytes / FLOPs as defined in SURVEY.md §8d).
   reference_gpu : the oracle port (plain torch, the reference's own ops) run eagerly ON THE GPU — the stand-in for the
                   reference's GPU FPS script (`evaluate_egtr.py:26-36`), which cannot travel to the GPU box.
@@ -513,6 +513,16 @@ def main():
         # MSDeformAttn, encoder form: SURVEY.md §8d algorithmic bytes = 4*B*[S*C + Lq*M*L*P*3 + Lq*C] = 3584*S per image
         r_msda = hbm_roof(("msda_kernel<true, 32", "msda_kernel<1, 32"), 3584 * S * Bl, "msda_enc")
         r_msda_dec = hbm_roof(("msda_kernel<true, 8", "msda_kernel<1, 8"), (1024 * S + 2560 * N) * Bl, "msda_dec")
+        # fused decoder stack (decoder.cu, forwards of at most 512 queries): per layer the MSDeformAttn bytes of SURVEY.md §8d's
+        # decoder form plus the layer's weights once (0.95 M parameters as bf16 hi + lo planes = 3.8 MB)
+        nl_dec = cfg.decoder_layers
+        r_dec = hbm_roof(("decoder_kernel",), nl_dec * ((1024 * S + 2560 * N) * Bl + 3.8e6), "decoder_kernel")
+        if r_dec is not None:
+            kt_d = pick(k_timed, "decoder_kernel")
+            r_dec["avg_launch_us_sm_weighted"] = kt_d["us_w"] / kt_d["n"] if kt_d else None
+            r_dec["note"] = ("ONE kernel for the six decoder layers on a cluster of 8 CTAs per image (16 for a lone forward): latency-bound "
+                             "by design (phase chain of ~70 cluster barriers), it holds 8 of the 148 SMs; algorithmic bytes as for the "
+                             "stand-alone decoder MSDeformAttn launches it replaces + the layer weights")
         if r_msda is not None:
             # the binding roof of the gather is the SM's L1 path, not HBM: one 128-byte wavefront per
             # (query, head, level, point, corner) at 128 B/clk/SM — report the fraction of THAT roof beside the HBM one
@@ -622,7 +632,7 @@ def main():
             "output_check": {"forwards_checked": chk_n, "deviating": chk_bad, "worst_rel_err": chk_worst, "tolerance": 1e-3, "class_flips": chk_flips,
                              "what": f"{conc} forwards in flight (the timed configuration) vs the same images run alone, max-norm relative error "
                                      "over logits / boxes / pred_rel / pred_connectivity, all ranks", "error": chk_error},
-            "roofline": r_gemm if r_gemm is not None else r_msda, "roofline_msda_enc": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_relation": r_rel,
+            "roofline": r_gemm if r_gemm is not None else r_msda, "roofline_msda_enc": r_msda, "roofline_msda_dec": r_msda_dec, "roofline_decoder": r_dec, "roofline_relation": r_rel,
             "stage_ms_lone_eager": stage,
         }
         # ---- the reference's GPU path on this box (stand-in: the oracle port, plain torch ops, eager, on the GPU)
