@@ -98,6 +98,10 @@ SIGNATURES = {
     "egtr_relation_pairs_fused_f32": [_p, _p, _i, _i, C.POINTER(RelheadWeights), _p, _p, _i, _p, _f, _i, _i, _i, _p, _p, _p],
     "egtr_relation_head_fwd_f32": [_p, _p, _i, _p, _i, _p, _i, C.POINTER(RelheadWeights), _p, _p, _f, _i, _i, _i, _i, _i,
                                    _p, _p, _p, _p, _p, _p],
+    "egtr_stem_planes_bytes": [_i, _i, _i],
+    "egtr_stem_krow": [],
+    "egtr_stem_pad_split_bf16": [_p, _i, _i, _i, _p, _p],
+    "egtr_stem_conv7x7s2_bf16x3": [_p, _i, _i, _i, _p, _p, _p, _p],
     "egtr_decoder_scratch_bytes": [_i, _i],
     "egtr_decoder_fault": [],
     "egtr_decoder_debug_profile": [_p],
@@ -111,8 +115,9 @@ _RESTYPES = {
     "egtr_groupnorm_scratch_doubles": _ll,
     "egtr_triplets_scratch_bytes": _ll,
     "egtr_decoder_scratch_bytes": _ll,
+    "egtr_stem_planes_bytes": _ll,
 }
-_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version", "egtr_decoder_fault"}
+_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version", "egtr_decoder_fault", "egtr_stem_krow"}
 
 _lib = None
 

@@ -190,6 +190,15 @@ class Engine:
         # stem weights for the NHWC4 gather: k = (ky*7 + kx)*4 + c, 49 taps x 4 -> 196, padded to K = 256
         w4 = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1)
         self.stem = L(_conv_mat(w4, 256), b)
+        # TMA-fed stem (stem.cu): weights as [64][ky][4 * kx + c] rows of `krow` elements (28 real), bf16 hi/lo planes
+        self.stem_mode = os.environ.get("EGTR_STEM", "tma")
+        krow = int(call("egtr_stem_krow"))
+        wt = torch.zeros(w.shape[0], 7, krow, dtype=torch.float32, device=dev)
+        wt[:, :, :28] = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1).permute(0, 2, 3, 1).reshape(w.shape[0], 7, 28)
+        wt = wt.reshape(w.shape[0], 7 * krow).contiguous()
+        self.stem_w_planes = torch.empty(2 * wt.shape[0] * wt.shape[1], dtype=torch.bfloat16, device=dev)
+        call("egtr_split_weight_bf16", _ptr(wt), wt.shape[0], wt.shape[1], wt.shape[0], _ptr(self.stem_w_planes), _stream())
+        self.stem_bias = b.detach().to(device=dev, dtype=torch.float32).contiguous()
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS, start=1):
             for bi in range(nblk):
@@ -521,7 +530,8 @@ class Engine:
         ws = dict(shapes=shapes, S=S, stem_hw=(h1, w1), c2_hw=(h2, w2))
         ws["shapes_c"] = (C.c_int * (2 * len(shapes)))(*[v for hw in shapes for v in hw])
         ws["starts"] = [sum(h * w for h, w in shapes[:l]) for l in range(len(shapes))]
-        ws["px4"] = torch.empty(B * (H + 6) * (W + 6) * 4, **f32)
+        ws["px4"] = torch.empty(B * (H + 6) * (W + 6) * 4, **f32) if self.stem_mode != "tma" else None
+        ws["px_planes"] = torch.zeros(int(call("egtr_stem_planes_bytes", B, H, W)), dtype=torch.uint8, device=dev) if self.stem_mode == "tma" else None
         ws["stem"] = torch.empty(B * h1 * w1, 64, **f32)
         # backbone ping-pong buffers sized for the largest stage output (layer1: h2*w2 x 256)
         big = B * h2 * w2 * 256
@@ -630,9 +640,16 @@ class Engine:
         # ---- backbone (deformable_detr.py:778): stem 7x7/2 as a gather-GEMM over the NCHW image, max-pool, bottlenecks
         h1, w1 = ws["stem_hw"]
         _sp_bb = self.span("stage_backbone"); _sp_bb.__enter__()
-        call("egtr_pad_nchw3_to_nhwc4_f32", _ptr(px), B, H, W, 3, _ptr(ws["px4"]), st)
-        self.gemm(self.stem, B * h1 * w1, ws["stem"], relu=True,
-                  conv=dict(x=ws["px4"], mode=3, H=H + 6, W=W + 6, C=4, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=0))
+        if self.stem_mode == "tma" and gemm_backend() != "simt":
+            # two bf16 planes of the zero-bordered NHWC4 image; a filter row of 128 output pixels' windows is one TMA box (stem.cu)
+            call("egtr_stem_pad_split_bf16", _ptr(px), B, H, W, _ptr(ws["px_planes"]), st)
+            call("egtr_stem_conv7x7s2_bf16x3", _ptr(ws["px_planes"]), B, H, W, _ptr(self.stem_w_planes), _ptr(self.stem_bias), _ptr(ws["stem"]), st)
+        else:
+            if ws["px4"] is None:
+                ws["px4"] = torch.empty(B * (H + 6) * (W + 6) * 4, **f32)
+            call("egtr_pad_nchw3_to_nhwc4_f32", _ptr(px), B, H, W, 3, _ptr(ws["px4"]), st)
+            self.gemm(self.stem, B * h1 * w1, ws["stem"], relu=True,
+                      conv=dict(x=ws["px4"], mode=3, H=H + 6, W=W + 6, C=4, OH=h1, OW=w1, KH=7, KW=7, stride=2, pad=0))
         h, w = ws["c2_hw"]
         bufs = ws["bb"]
         x = bufs[0]

@@ -87,7 +87,8 @@ def call(name, *args):
         drop = True
     if "bb_gemm" in sk and stage == "stage_backbone" and name == "egtr_gemm_sbf16" and "gemm_p32" in sp:
         drop = True
-    if "stem" in sk and stage == "stage_backbone" and (name in ("egtr_pad_nchw3_to_nhwc4_f32", "egtr_maxpool3x3s2_nhwc_ex") or
+    if "stem" in sk and stage == "stage_backbone" and (name in ("egtr_pad_nchw3_to_nhwc4_f32", "egtr_maxpool3x3s2_nhwc_ex", "egtr_stem_pad_split_bf16",
+                                                                "egtr_stem_conv7x7s2_bf16x3") or
                                                         (name == "egtr_gemm_sbf16" and "gemm_p32" not in sp)):
         drop = True
     if "groupnorm" in sk and name == "egtr_groupnorm_ex":
