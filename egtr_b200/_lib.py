@@ -100,6 +100,7 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p, _p],
     "egtr_stem_planes_bytes": [_i, _i, _i],
     "egtr_stem_krow": [],
+    "egtr_stem_layout": [],
     "egtr_stem_pad_split_bf16": [_p, _i, _i, _i, _p, _p],
     "egtr_stem_conv7x7s2_bf16x3": [_p, _i, _i, _i, _p, _p, _p, _p],
     "egtr_decoder_scratch_bytes": [_i, _i],
@@ -117,7 +118,7 @@ _RESTYPES = {
     "egtr_decoder_scratch_bytes": _ll,
     "egtr_stem_planes_bytes": _ll,
 }
-_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version", "egtr_decoder_fault", "egtr_stem_krow"}
+_NO_STATUS = set(_RESTYPES) | {"egtr_abi_version", "egtr_decoder_fault", "egtr_stem_krow", "egtr_stem_layout"}
 
 _lib = None
 

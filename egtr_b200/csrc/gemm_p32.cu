@@ -1044,6 +1044,17 @@ int tmap_weight_planes(const void* planes, int K, long long rows, int box_rows, 
   return cached_map(desc2(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, rows, 2ull * K, BLOCK_K, box_rows), out);
 }
 
+// Any tiled map (rank <= 4, unit element strides) through the same mutex-protected cache: stem.cu's overlapping-row image map.
+int tmap_tiled(const void* ptr, int dtype, int rank, const unsigned long long* dims, const unsigned long long* strides, const unsigned* box,
+               int swizzle64, CUtensorMap* out) {
+  MapDesc d;
+  memset(&d, 0, sizeof(d));
+  d.ptr = ptr; d.dtype = dtype; d.rank = rank; d.swizzle64 = swizzle64;
+  for (int i = 0; i < rank; ++i) { d.dim[i] = dims[i]; d.box[i] = box[i]; d.estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) d.stride[i] = strides[i];
+  return cached_map(d, out);
+}
+
 // Entry used by egtr_gemm_sbf16 when the operand source is P32 (a.fmt == 1): mode 0 rows or mode 1 NHWC convolution.
 int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                       cudaStream_t st) {

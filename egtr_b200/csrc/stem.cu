@@ -15,25 +15,37 @@
 #include <cuda.h>
 
 #include <cuda_bf16.h>
-#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace egtr {
 void count_launch();
+int tmap_tiled(const void* ptr, int dtype, int rank, const unsigned long long* dims, const unsigned long long* strides, const unsigned* box,
+               int swizzle64, CUtensorMap* out);  // gemm_p32.cu: the library's tensor-map cache
 namespace {
 
-#ifndef EGTR_STEM_KROW      // elements of a filter row per operand row: 64 = 128-byte rows (SWIZZLE_128B), 32 = 64-byte rows (SWIZZLE_64B)
-#define EGTR_STEM_KROW 32
+// Image layouts (EGTR_STEM_LAYOUT):
+//   1  two planes (hi, lo) of NHWC4 bf16, 64-byte operand rows (SWIZZLE_64B): two boxes per filter row, 6 MMAs (lo*hi, hi*lo, hi*hi)
+//   2  ONE plane, hi and lo interleaved per pixel (h0 h1 h2 0 l0 l1 l2 0 = 16 bytes): the 8-pixel window is one 128-byte operand row,
+//      ONE box per filter row (half the TMA requests of layout 1).
+//      The split moves into two zero-padded weight sets over the same 64-element row: B13 = w_hi at the hi AND the lo positions
+//      (A . B13 = hi*w_hi + lo*w_hi), B2 = w_lo at the hi positions (A . B2 = hi*w_lo): 8 MMAs per filter row, half of whose
+//      multiplies meet zeros.  Measured 64.4 us against layout 1's 57.4 us (six 16 KB stages in flight instead of nine next to the
+//      112 KB of resident weight sets): the kernel is bound by bytes in flight, not by the request rate.  Kept as an A/B variant.
+#ifndef EGTR_STEM_LAYOUT
+#define EGTR_STEM_LAYOUT 1
 #endif
-constexpr int KROW = EGTR_STEM_KROW;
+constexpr int LAYOUT = EGTR_STEM_LAYOUT;
+constexpr int KROW = LAYOUT == 2 ? 64 : 32;      // elements of an operand row
 constexpr int ROW_BYTES = KROW * 2;
+constexpr int PIX_BYTES = LAYOUT == 2 ? 16 : 8;  // bytes per pixel of a plane
+constexpr int NPLANES = LAYOUT == 2 ? 1 : 2;
 constexpr int KH = 7, NOUT = 64, TILE = 128;
 constexpr int A_BYTES = TILE * ROW_BYTES;        // one plane's box of one filter row
-constexpr int W_BYTES = NOUT * ROW_BYTES;        // one plane's weight tile of one filter row
-constexpr int STAGES = KROW == 64 ? 3 : 9;
-constexpr int STAGE_BYTES = 2 * A_BYTES;
+constexpr int W_BYTES = NOUT * ROW_BYTES;        // one weight tile (hi / lo plane, or set B13 / B2) of one filter row
+constexpr int STAGES = LAYOUT == 2 ? 6 : 9;
+constexpr int STAGE_BYTES = NPLANES * A_BYTES;
 constexpr int W_RES_BYTES = KH * 2 * W_BYTES;
 constexpr int STG_BYTES = 4 * 4096;
 constexpr int SMEM_BYTES = W_RES_BYTES + STAGES * STAGE_BYTES + STG_BYTES + 256 + 1024;
@@ -118,7 +130,7 @@ stem_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
           const uint32_t st = ptx::smem_u32(ring + stage * STAGE_BYTES);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_4d(st, &map_hi, &full_bar[stage], 0, ox0, 2 * oy + ky, b);
-          tma_load_4d(st + A_BYTES, &map_lo, &full_bar[stage], 0, ox0, 2 * oy + ky, b);
+          if (NPLANES == 2) tma_load_4d(st + A_BYTES, &map_lo, &full_bar[stage], 0, ox0, 2 * oy + ky, b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,13 +150,22 @@ stem_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t a_hi = ptx::smem_u32(ring + stage * STAGE_BYTES), a_lo = a_hi + A_BYTES;
           const uint32_t b_hi = ptx::smem_u32(wres + ky * 2 * W_BYTES), b_lo = b_hi + W_BYTES;
+          if (LAYOUT == 2) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {  // the filter row's 32 elements (28 real): two 16-wide k-steps
-            const uint64_t dah = umma_desc(a_hi + ks * 32), dal = umma_desc(a_lo + ks * 32);
-            const uint64_t dbh = umma_desc(b_hi + ks * 32), dbl = umma_desc(b_lo + ks * 32);
-            ptx::umma_bf16(d_tmem, dal, dbh, idesc, (ky != 0) || (ks != 0));  // small terms first
-            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
-            ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) {  // the interleaved row's 64 elements (8 pixels x (4 hi | 4 lo)): four 16-wide k-steps
+              const uint64_t da = umma_desc(a_hi + ks * 32);
+              ptx::umma_bf16(d_tmem, da, umma_desc(b_lo + ks * 32), idesc, (ky != 0) || (ks != 0));  // set B2: hi * w_lo (small term first)
+              ptx::umma_bf16(d_tmem, da, umma_desc(b_hi + ks * 32), idesc, 1);                        // set B13: hi * w_hi + lo * w_hi
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {  // the filter row's 32 elements (28 real): two 16-wide k-steps
+              const uint64_t dah = umma_desc(a_hi + ks * 32), dal = umma_desc(a_lo + ks * 32);
+              const uint64_t dbh = umma_desc(b_hi + ks * 32), dbl = umma_desc(b_lo + ks * 32);
+              ptx::umma_bf16(d_tmem, dal, dbh, idesc, (ky != 0) || (ks != 0));  // small terms first
+              ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1);
+              ptx::umma_bf16(d_tmem, dah, dbh, idesc, 1);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (ky == KH - 1) ptx::umma_commit(&acc_full[acc]);
@@ -210,7 +231,8 @@ stem_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ 
   }
 }
 
-// NCHW fp32 image -> two zero-bordered NHWC4 bf16 planes [2][B][Hp][Wp][4] (hi, then lo), Hp = H + 6, Wp = W + 6 rounded up to even
+// NCHW fp32 image -> zero-bordered NHWC4 bf16, Hp = H + 6, Wp = W + 6 rounded up to even: two planes [2][B][Hp][Wp][4] (hi, then lo:
+// layout 1) or one plane [B][Hp][Wp][8] with hi and lo interleaved per pixel (layout 2)
 __global__ void pad_split_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp, uint2* __restrict__ out) {
   pdl_entry();
   const long long n = (long long)B * Hp * Wp;
@@ -229,22 +251,15 @@ __global__ void pad_split_kernel(const float* __restrict__ img, int B, int H, in
 #pragma unroll
   for (int c = 0; c < 3; ++c) split_bf16(v[c], h[c], l[c]);
   auto pk = [](__nv_bfloat16 a0, __nv_bfloat16 a1) { return (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16); };
-  out[i] = make_uint2(pk(h[0], h[1]), pk(h[2], __float2bfloat16_rn(0.f)));
-  out[n + i] = make_uint2(pk(l[0], l[1]), pk(l[2], __float2bfloat16_rn(0.f)));
+  const uint2 hi = make_uint2(pk(h[0], h[1]), pk(h[2], __float2bfloat16_rn(0.f))), lo = make_uint2(pk(l[0], l[1]), pk(l[2], __float2bfloat16_rn(0.f)));
+  if (LAYOUT == 2) {
+    ((uint4*)out)[i] = make_uint4(hi.x, hi.y, lo.x, lo.y);
+  } else {
+    out[i] = hi;
+    out[n + i] = lo;
+  }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn stem_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
 int* stem_error_flag() {
   static int* flag = nullptr;
   if (!flag) {
@@ -264,9 +279,11 @@ extern "C" long long egtr_stem_planes_bytes(int B, int H, int W) {
   return 2 * B * Hp * Wp * 8 + 4096;  // + slack: the last windows of the last row read past it (into zero weights)
 }
 extern "C" int egtr_stem_krow(void) { return KROW; }
+extern "C" int egtr_stem_layout(void) { return LAYOUT; }
 
 extern "C" int egtr_stem_pad_split_bf16(const float* img, int B, int H, int W, void* planes, egtr_stream_t s) {
   EGTR_CHECK(img && planes && B > 0 && H > 0 && W > 0, EGTR_ERR_ARG, "egtr_stem_pad_split_bf16: bad arguments");
+  EGTR_CHECK(((uintptr_t)planes & 15) == 0, EGTR_ERR_ARG, "egtr_stem_pad_split_bf16: planes must be 16-byte aligned");
   const int Hp = H + 6, Wp = (W + 6 + 1) & ~1;
   const long long total = (long long)B * Hp * Wp;
   launch_pdl(pad_split_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)0, (cudaStream_t)s, img, B, H, W, Hp, Wp, (uint2*)planes);
@@ -282,35 +299,22 @@ extern "C" int egtr_stem_conv7x7s2_bf16x3(const void* planes, int B, int H, int 
              "egtr_stem_conv7x7s2_bf16x3: alignment");
   const int Hp = H + 6, Wp = (W + 6 + 1) & ~1;
   const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
-  EncodeTiledFn enc = stem_encode_fn();
-  EGTR_CHECK(enc != nullptr, EGTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  const CUtensorMapSwizzle swz = ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  // {element in window, output pixel (stride 2 pixels = 16 B: the windows overlap), padded row, image}
-  struct Key { const void* p; int B, H, W; } key = {planes, B, H, W};
-  static Key last = {};
-  static CUtensorMap m_hi, m_lo, m_w;
-  static const void* last_w = nullptr;
-  if (memcmp(&key, &last, sizeof(key)) != 0) {
-    const unsigned long long row_pitch = (unsigned long long)Wp * 8, img_pitch = row_pitch * Hp;
-    for (int pl = 0; pl < 2; ++pl) {
-      cuuint64_t dims[4] = {(cuuint64_t)KROW, (cuuint64_t)OW, (cuuint64_t)Hp, (cuuint64_t)B};
-      cuuint64_t strides[3] = {16, row_pitch, img_pitch};
-      cuuint32_t box[4] = {(cuuint32_t)KROW, TILE, 1, 1}, estr[4] = {1, 1, 1, 1};
-      void* base = (uint8_t*)planes + (size_t)pl * img_pitch * B;
-      CUresult r = enc(pl ? &m_lo : &m_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA, "stem: cuTensorMapEncodeTiled (image plane, overlapping windows) failed with CUresult %d", (int)r);
-    }
-    last = key;
-  }
-  if (w_planes != last_w) {  // [2][64][KH * KROW] bf16: hi rows then lo rows
-    cuuint64_t dims[2] = {(cuuint64_t)KH * KROW, 2 * NOUT}, strides[1] = {(cuuint64_t)KH * KROW * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KROW, NOUT}, estr[2] = {1, 1};
-    CUresult r = enc(&m_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    EGTR_CHECK(r == CUDA_SUCCESS, EGTR_ERR_CUDA, "stem: cuTensorMapEncodeTiled (weights) failed with CUresult %d", (int)r);
-    last_w = w_planes;
-  }
+  const int swz64 = ROW_BYTES == 128 ? 0 : 1;
+  // {element in window, output pixel (stride 2 pixels: the windows overlap), padded row, image}
+  const unsigned long long row_pitch = (unsigned long long)Wp * PIX_BYTES, img_pitch = row_pitch * Hp;
+  const unsigned long long dims[4] = {(unsigned long long)KROW, (unsigned long long)OW, (unsigned long long)Hp, (unsigned long long)B};
+  const unsigned long long strides[3] = {2ull * PIX_BYTES, row_pitch, img_pitch};
+  const unsigned box[4] = {(unsigned)KROW, TILE, 1, 1};
+  CUtensorMap m_hi, m_lo, m_w;
+  int rc;
+  if ((rc = tmap_tiled(planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, swz64, &m_hi)) != EGTR_OK) return rc;
+  m_lo = m_hi;
+  if (NPLANES == 2 && (rc = tmap_tiled((const uint8_t*)planes + img_pitch * B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, swz64, &m_lo)) != EGTR_OK)
+    return rc;
+  // weights [2][64][KH * KROW] bf16: rows 0-63 = hi plane (layout 2: set B13), rows 64-127 = lo plane (set B2)
+  const unsigned long long wdims[2] = {(unsigned long long)KH * KROW, 2 * NOUT}, wstrides[1] = {(unsigned long long)KH * KROW * 2};
+  const unsigned wbox[2] = {(unsigned)KROW, NOUT};
+  if ((rc = tmap_tiled(w_planes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wdims, wstrides, wbox, swz64, &m_w)) != EGTR_OK) return rc;
   StemArgs a = {};
   a.bias = bias; a.out = out; a.B = B; a.OH = OH; a.OW = OW; a.tiles_x = cdiv(OW, TILE);
   a.err = stem_error_flag();

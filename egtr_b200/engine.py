@@ -190,14 +190,25 @@ class Engine:
         # stem weights for the NHWC4 gather: k = (ky*7 + kx)*4 + c, 49 taps x 4 -> 196, padded to K = 256
         w4 = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1)
         self.stem = L(_conv_mat(w4, 256), b)
-        # TMA-fed stem (stem.cu): weights as [64][ky][4 * kx + c] rows of `krow` elements (28 real), bf16 hi/lo planes
+        # TMA-fed stem (stem.cu): weights laid out like the operand rows its tensor map delivers (include/egtr_b200.h)
         self.stem_mode = os.environ.get("EGTR_STEM", "tma")
         krow = int(call("egtr_stem_krow"))
-        wt = torch.zeros(w.shape[0], 7, krow, dtype=torch.float32, device=dev)
-        wt[:, :, :28] = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1).permute(0, 2, 3, 1).reshape(w.shape[0], 7, 28)
-        wt = wt.reshape(w.shape[0], 7 * krow).contiguous()
-        self.stem_w_planes = torch.empty(2 * wt.shape[0] * wt.shape[1], dtype=torch.bfloat16, device=dev)
-        call("egtr_split_weight_bf16", _ptr(wt), wt.shape[0], wt.shape[1], wt.shape[0], _ptr(self.stem_w_planes), _stream())
+        w7 = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1).permute(0, 2, 3, 1).contiguous().float()  # [64, ky, kx, 4]
+        if int(call("egtr_stem_layout")) == 2:
+            # one image plane with hi | lo interleaved per pixel: set B13 = w_hi at the hi and the lo positions, set B2 = w_lo at the hi ones
+            hi = w7.to(torch.bfloat16)
+            lo = (w7 - hi.float()).to(torch.bfloat16)
+            sets = torch.zeros(2, w.shape[0], 7, 8, 8, dtype=torch.bfloat16, device=dev)
+            sets[0, :, :, :7, 0:4] = hi
+            sets[0, :, :, :7, 4:8] = hi
+            sets[1, :, :, :7, 0:4] = lo
+            self.stem_w_planes = sets.reshape(-1).contiguous()
+        else:
+            wt = torch.zeros(w.shape[0], 7, krow, dtype=torch.float32, device=dev)
+            wt[:, :, :28] = w7.reshape(w.shape[0], 7, 28)
+            wt = wt.reshape(w.shape[0], 7 * krow).contiguous()
+            self.stem_w_planes = torch.empty(2 * wt.shape[0] * wt.shape[1], dtype=torch.bfloat16, device=dev)
+            call("egtr_split_weight_bf16", _ptr(wt), wt.shape[0], wt.shape[1], wt.shape[0], _ptr(self.stem_w_planes), _stream())
         self.stem_bias = b.detach().to(device=dev, dtype=torch.float32).contiguous()
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS, start=1):

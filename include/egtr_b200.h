@@ -317,13 +317,17 @@ int egtr_relation_head_fwd_f32(const float* const* q_ptrs, const float* const* k
 
 /* ---------------------------------------------------------------- ResNet stem on TMA (stem.cu) */
 /* conv1 7x7 / stride 2 / pad 3 + folded FrozenBN + ReLU (timm resnet50 stem, model/deformable_detr.py:772-787) without a gather:
- * the image is stored as two zero-bordered NHWC4 bf16 planes (hi, lo) and a filter row of an output pixel's window is a contiguous
- * run, so 128 windows are one TMA box over a tensor map with overlapping rows.  planes: egtr_stem_planes_bytes(B, H, W) bytes,
- * ZERO-INITIALISED once by the caller (the slack behind the last row is read against zero weights), 128-byte aligned.
- * w_planes: bf16 [2][64][7 * krow] (egtr_split_weight_bf16 of the [64, 7 * krow] matrix w[o][ky][4 * kx + c], krow =
- * egtr_stem_krow(), zeros elsewhere); out: fp32 NHWC [B, OH, OW, 64]. */
+ * the image is stored as zero-bordered NHWC4 bf16 (hi, lo) in which a filter row of an output pixel's window is a contiguous run,
+ * so 128 windows are one TMA box over a tensor map with overlapping rows.  planes: egtr_stem_planes_bytes(B, H, W) bytes,
+ * ZERO-INITIALISED once by the caller (the slack behind the last row is read against zero weights), 128-byte aligned, filled by
+ * egtr_stem_pad_split_bf16.  Weights, bf16 [2][64][7 * krow], krow = egtr_stem_krow(), by egtr_stem_layout():
+ *   1 (two image planes, krow 32; the default): row o of plane 0 / 1 = hi / lo of w[o][ky][4 * kx + c] (egtr_split_weight_bf16 of that matrix);
+ *   2 (one plane, hi and lo interleaved per pixel, krow 64; build-time A/B variant, -DEGTR_STEM_LAYOUT=2): element ky*64 + 8*kx + j of row o of set 0 =
+ *     hi(w[o][c][ky][kx]) for j = c and for j = 4 + c, of set 1 = lo(w[o][c][ky][kx]) for j = c; zeros elsewhere (c < 3, kx < 7).
+ * out: fp32 NHWC [B, OH, OW, 64]. */
 long long egtr_stem_planes_bytes(int B, int H, int W);
 int egtr_stem_krow(void);
+int egtr_stem_layout(void);
 int egtr_stem_pad_split_bf16(const float* img_nchw, int B, int H, int W, void* planes, egtr_stream_t s);
 int egtr_stem_conv7x7s2_bf16x3(const void* planes, int B, int H, int W, const void* w_planes, const float* bias, float* out, egtr_stream_t s);
 
