@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call R: grid divisor x forwards in flight (throughput configuration), workload B
+# grid divisor x forwards in flight (throughput configuration), workload B
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 out=gpurun_out/${1:-r02r_grid_div}.txt
