@@ -48,12 +48,10 @@ constexpr int STG_BYTES = 32 * 128;           // one epilogue box: 32 rows x 32 
 // CTAS == 2: a cluster of two CTAs computes a 256-row tile with one cta_group::2 MMA — each CTA stages its own 128 activation
 // rows and only HALF of the weight tile, so a k-block costs 64 KB instead of 96 KB of L2->SM traffic per SM at BLOCK_N = 256
 // and a third pipeline stage fits.
-// WS == 1: weight-stationary mode of the CTA-pair kernel for short K (K * B_ROWS * 4 bytes <= 128 KB: K <= 256 at 256-wide
-// tiles).  Profiling showed the MMA warp waiting on operand loads, not the epilogue waiting on the MMAs: the L2->SM path
-// delivers ~20-25 B/clk/SM in practice, and half of a streamed k-block's 64 KB is the weight tile that every m-tile re-reads.
-// Here a CTA keeps its half of the n-tile's weights resident in shared memory across all the m-tiles it processes (work is
-// dealt in contiguous n-major ranges), so steady-state traffic is the activation rows only, in 16 KB single-group stages.
-template <int BLOCK_N, int CTAS, int WS = 0>
+// (A weight-stationary variant — this CTA's half of an n-tile's weights resident across its m-tiles, activations alone streamed —
+// was built and measured in round 1: 8-15 % slower than streaming both operands, because the resident region leaves 64 KB instead
+// of 192 KB of loads in flight on a latency-bound operand path.  Removed in round 2.)
+template <int BLOCK_N, int CTAS>
 struct PCfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
@@ -61,17 +59,14 @@ struct PCfg {
   static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
   static constexpr int B_ROWS = BLOCK_N / CTAS;  // weight rows staged by one CTA
   static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
-  static constexpr int B_RES_BYTES = WS ? 128 * 1024 : 0;                  // resident weights: k_blocks * (hi + lo tile)
-  static constexpr int MAX_RES_KBLOCKS = WS ? B_RES_BYTES / (2 * B_TILE_BYTES) : 0;
-  static constexpr int STAGE_BYTES = WS ? A_GROUP_BYTES : 2 * A_GROUP_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGE_BUDGET = WS ? 64 * 1024 : 192 * 1024;
+  static constexpr int STAGE_BYTES = 2 * A_GROUP_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGE_BUDGET = 192 * 1024;
   static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 4 ? 4 : STAGE_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int CTRL_BYTES = 512;
-  static constexpr int SMEM_BYTES = B_RES_BYTES + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + 1024 /*align slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + CTRL_BYTES + 1024 /*align slack*/;
   static constexpr int CHUNKS = COLS_PER_WARP / 32;  // 32-column chunks per epilogue warp
   static_assert(STAGES >= 2, "operand ring needs at least two stages");
-  static_assert(!WS || CTAS == 2, "weight-stationary mode is built for CTA pairs");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -139,18 +134,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int CTAS, int WS>
-__global__ void __launch_bounds__((PCfg<BLOCK_N, CTAS, WS>::NUM_THREADS), 1)
+template <int BLOCK_N, int CTAS>
+__global__ void __launch_bounds__((PCfg<BLOCK_N, CTAS>::NUM_THREADS), 1)
 gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                 const __grid_constant__ CUtensorMap tmap_out2, const PArgs p, int* __restrict__ err) {
   if (!(p.dbg & 4)) pdl_launch_dependents();  // the next kernel may take SMs as this grid's CTAs retire
   if (threadIdx.x == 0) P32_STAMP(0);
-  using C = PCfg<BLOCK_N, CTAS, WS>;
+  using C = PCfg<BLOCK_N, CTAS>;
   constexpr int EPI_WARPS = C::EPI_WARPS, TMA_WARP = C::TMA_WARP, MMA_WARP = C::MMA_WARP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem_res = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // WS: resident weight tiles first
-  uint8_t* smem = smem_res + C::B_RES_BYTES;                                        // operand stage ring
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // operand stage ring
   uint8_t* stg_all = smem + C::STAGES * C::STAGE_BYTES;         // [EPI_WARPS][4096], 1024-aligned
   uint8_t* ctrl = stg_all + EPI_WARPS * STG_BYTES;
   uint64_t* full_bar = (uint64_t*)ctrl;          // [STAGES]
@@ -158,9 +152,7 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_full = empty_bar + 4;           // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* res_bar = tmem_empty + 2;            // [EPI_WARPS]
-  uint64_t* b_full = res_bar + MAX_EPI_WARPS;    // WS: resident weights loaded
-  uint64_t* b_free = b_full + 1;                 // WS: every MMA that reads the resident weights has completed
-  uint32_t* tmem_holder = (uint32_t*)(b_free + 1);
+  uint32_t* tmem_holder = (uint32_t*)(res_bar + MAX_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,26 +164,16 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // phantom odd tile decodes to batch index nb: its loads are out of bounds (zero fill) and it stores nothing.
   const int m_tiles2 = (m_tiles + CTAS - 1) / CTAS;
   const int total_all = m_tiles2 * n_tiles * p.splits;
-  // streaming: items dealt round-robin, n fastest (neighbouring CTAs share activation rows in L2); WS: each CTA (pair) takes a
-  // contiguous n-major range, so its n-tile — and with it the resident weights — changes at most once or twice
+  // items dealt round-robin, n fastest (neighbouring CTAs share activation rows in L2)
   const int slots = gridDim.x / CTAS, me = blockIdx.x / CTAS;
-  const int w_first = WS ? (int)((long long)me * total_all / slots) : me;
-  const int total = WS ? (int)((long long)(me + 1) * total_all / slots) : total_all;
-  const int w_step = WS ? 1 : slots;
+  const int w_first = me, total = total_all, w_step = slots;
   const int k_blocks_all = p.K / BLOCK_K;
   auto decode = [&](int w) {
     TileCoord t;
     const int tg = w / p.splits;
     t.sp = w - tg * p.splits;
-    int mt2;
-    if (WS) {
-      const int nt = tg / m_tiles2;
-      mt2 = tg - nt * m_tiles2;
-      t.n0 = nt * BLOCK_N;
-    } else {
-      mt2 = tg / n_tiles;
-      t.n0 = (tg - mt2 * n_tiles) * BLOCK_N;
-    }
+    const int mt2 = tg / n_tiles;
+    t.n0 = (tg - mt2 * n_tiles) * BLOCK_N;
     const int mt = mt2 * CTAS + rank;
     t.b = mt / mtiles_per_b;
     const int r = mt - t.b * mtiles_per_b;
@@ -215,8 +197,6 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       ptx::mbar_init(&tmem_empty[i], EPI_WARPS * CTAS);  // lane 0 of every epilogue warp of the pair
     }
     for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
-    ptx::mbar_init(b_full, 1);
-    ptx::mbar_init(b_free, 1);
     ptx::fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -236,36 +216,11 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ------------------------------------------------------------------ TMA: activation groups + weight tiles
     if (lane == 0) {
       int stage = 0, phase = 0;
-      int cur_n0 = -1;
-      uint32_t bfree_phase = 0;
       for (int w = w_first; w < total; w += w_step) {
         const TileCoord t = decode(w);
         const int n0 = t.n0;
         const int kb_lo = t.sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
         const int ax = t.w0 * p.stride - p.pad, ay = t.h0 * p.stride - p.pad;
-        if constexpr (WS) {
-          if (n0 != cur_n0) {  // (re)load this CTA's half of the n-tile's weights: k_blocks x (hi, lo) tiles, resident from here on
-            if (cur_n0 >= 0) { ptx::mbar_wait(b_free, bfree_phase, err, 207); bfree_phase ^= 1; }
-            cur_n0 = n0;
-            if (rank == 0) ptx::mbar_arrive_expect_tx(b_full, 2 * k_blocks_all * 2 * C::B_TILE_BYTES);
-            const int nr = n0 + rank * C::B_ROWS;
-            const uint32_t rs = ptx::smem_u32(smem_res);
-            for (int kb = 0; kb < k_blocks_all; ++kb) {
-              ptx::tma_load_2d_2cta(rs + kb * 2 * C::B_TILE_BYTES, &tmap_w, b_full, kb * BLOCK_K, nr);
-              ptx::tma_load_2d_2cta(rs + kb * 2 * C::B_TILE_BYTES + C::B_TILE_BYTES, &tmap_w, b_full, kb * BLOCK_K, p.plane_rows + nr);
-            }
-          }
-          for (int kg = 2 * kb_lo; kg < 2 * kb_hi; ++kg) {  // one 32-channel P32 group (16 KB) per stage
-            const int kb = kg >> 1;
-            const int tap = kb / p.slabs, slab = kb - tap * p.slabs;
-            const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 201);
-            const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            ptx::tma_load_4d_2cta(st, &tmap_a, &full_bar[stage], slab * 128 + (kg & 1) * 64, ax + kx, ay + ky, t.b);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-          }
-        } else {
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int tap = kb / p.slabs, slab = kb - tap * p.slabs;
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -289,56 +244,19 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        }
       }
     }
   } else if (warp == MMA_WARP && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M * CTAS, BLOCK_N);
     int stage = 0, phase = 0, it = 0;
-    int cur_n0 = -1;
-    uint32_t bfull_phase = 0;
     for (int w = w_first; w < total; w += w_step, ++it) {
       const int sp = w % p.splits;
       const int kb_lo = sp * p.kb_per_split, kb_hi = min(k_blocks_all, kb_lo + p.kb_per_split);
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
-      if constexpr (WS) {
-        const int n0 = decode(w).n0;
-        if (n0 != cur_n0) { ptx::mbar_wait(b_full, bfull_phase, err, 208); bfull_phase ^= 1; cur_n0 = n0; }
-      }
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, err, 202);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      if constexpr (WS) {
-        const bool last_of_ntile = (w + 1 < total) && (decode(w + 1).n0 != cur_n0);  // the TMA warp reloads the weights after this tile
-        const uint32_t rs = ptx::smem_u32(smem_res);
-        for (int kg = 2 * kb_lo; kg < 2 * kb_hi; ++kg) {
-          ptx::mbar_wait(&full_bar[stage], phase, err, 203);
-          if (lane == 0 && it == 0 && kg == 2 * kb_lo) P32_STAMP(2);
-          ptx::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a0 = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-            const uint32_t b_hi = rs + (kg >> 1) * 2 * C::B_TILE_BYTES;
-            const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {  // the group's two 16-wide k-steps; weight k-step = 2 * (kg & 1) + j inside the k-block
-              const int ks = 2 * (kg & 1) + j;
-              const uint64_t dah = ptx::umma_desc_sw128(a0 + j * 32), dal = ptx::umma_desc_sw128(a0 + j * 32 + 64);
-              const uint64_t dbh = ptx::umma_desc_sw128(b_hi + ks * 32), dbl = ptx::umma_desc_sw128(b_lo + ks * 32);
-              ptx::umma_bf16_2cta(d_tmem, dal, dbh, idesc, (kg != 2 * kb_lo) || (j != 0));
-              ptx::umma_bf16_2cta(d_tmem, dah, dbl, idesc, 1);
-              ptx::umma_bf16_2cta(d_tmem, dah, dbh, idesc, 1);
-            }
-            ptx::umma_commit_2cta(&empty_bar[stage]);
-            if (kg == 2 * kb_hi - 1) {
-              ptx::umma_commit_2cta(&tmem_full[acc]);
-              if (last_of_ntile) ptx::umma_commit_2cta(b_free);
-            }
-          }
-          __syncwarp();
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-      } else {
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase, err, 203);
         if (lane == 0 && it == 0 && kb == kb_lo) P32_STAMP(2);
@@ -372,7 +290,6 @@ gemm_p32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-      }
       }
     }
   } else if (warp < EPI_WARPS) {
@@ -886,10 +803,10 @@ int pick_bw_log2(int OW, int OH) {
   return best;
 }
 
-template <int BLOCK_N, int CTAS, int WS = 0>
+template <int BLOCK_N, int CTAS>
 int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, int Npad, int K, const Epilogue& ep,
                cudaStream_t st) {
-  using C = PCfg<BLOCK_N, CTAS, WS>;
+  using C = PCfg<BLOCK_N, CTAS>;
   const bool conv = a.mode == 1;
   PArgs p = {};
   p.M = M; p.N = N; p.K = K;
@@ -924,7 +841,7 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
     if (splits > splitk_cap) splits = splitk_cap;
     if (splits < 1) splits = 1;
   }
-  if (WS || ep.ln_gamma != nullptr || ep.out_fmt == EGTR_FMT_H16PAIR) splits = 1;  // (the LayerNorm epilogue needs the complete row sums in one tile)
+  if (ep.ln_gamma != nullptr || ep.out_fmt == EGTR_FMT_H16PAIR) splits = 1;  // (the LayerNorm epilogue needs the complete row sums in one tile)
   const int kbps = cdiv(k_blocks, splits);
   splits = cdiv(k_blocks, kbps);
   p.splits = splits; p.kb_per_split = kbps;
@@ -1006,14 +923,14 @@ int launch_p32(const ASrc& a, const void* planes, int plane_rows, int M, int N, 
   }
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
-    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N, CTAS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EGTR_CUDA(cudaFuncSetAttribute(gemm_p32_kernel<BLOCK_N, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int work = cdiv(m_tiles, CTAS) * cdiv(p.ncols, BLOCK_N) * splits;  // per CTA (CTAS == 1) or per CTA pair
   // throughput mode (egtr_set_grid_div): the persistent grid takes 1/div of the GPU, so that GEMMs of the other forwards in
   // flight run beside it on disjoint SMs instead of time-slicing the whole machine
   const int grid = balanced_grid(work, num_sms() / CTAS / grid_div()) * CTAS;
-  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS, WS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, to2, p,
+  EGTR_CUDA(launch_cluster_pdl(gemm_p32_kernel<BLOCK_N, CTAS>, dim3(grid), dim3(C::NUM_THREADS), (size_t)(C::SMEM_BYTES), st, CTAS, ta, tw, to, tr, to2, p,
                        device_error_flag_p32()));
   if (splits > 1) {
     ReduceArgs r = {};
@@ -1101,17 +1018,8 @@ int gemm_p32_dispatch(const ASrc& a, const void* planes, int plane_rows, int M, 
   if (forced_ctas == 1) pair = false;
   if (forced_ctas == 2 && bn >= 128) pair = true;
   if (pair) {
-    // weight-stationary variant (this CTA's half of an n-tile's weights resident in a 128 KB region, K <= 256 at 256 columns,
-    // K <= 512 at 128): OFF by default — measured 8-15 % slower than streaming (fc1 43.9 vs 38.9 us, 334 vs 345 images/s): the
-    // operand path is latency-bound, and the resident region leaves only 64 KB of loads in flight instead of 192 KB
-    static const int ws_mode = [] { const char* e = getenv("EGTR_GEMM_WS"); return e ? atoi(e) : 0; }();  // 0 off, 1 auto, 2 whenever it fits (dev)
-    const long long items = (long long)cdiv(cdiv(M, BLOCK_M), 2) * cdiv(N, bn);
-    const bool fits = (long long)K * (bn / 2) * 4 <= 128 * 1024;
-    const bool ws = fits && (ws_mode == 2 || (ws_mode == 1 && items >= 2 * (num_sms() / 2)));
-    if (bn == 256) return ws ? launch_p32<256, 2, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st)
-                             : launch_p32<256, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
-    return ws ? launch_p32<128, 2, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st)
-              : launch_p32<128, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+    if (bn == 256) return launch_p32<256, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
+    return launch_p32<128, 2>(a, planes, plane_rows, M, N, Npad, K, ep, st);
   }
   if (bn == 256) return launch_p32<256, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st);
   if (bn == 128) return launch_p32<128, 1>(a, planes, plane_rows, M, N, Npad, K, ep, st);
