@@ -18,6 +18,20 @@ import numpy as np
 MODES = ["sgdet"]
 
 
+def rows_equal(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """bool [len(a), len(b)]: row i of `a` equals row j of `b` (role of `lib/pytorch_misc.py::intersect_2d`)."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"row width mismatch: {a.shape[1]} vs {b.shape[1]}")
+    return (a[:, None, :] == b[None, :, :]).all(-1)
+
+
+def descending_indices(scores: np.ndarray) -> np.ndarray:
+    """[scores.size, scores.ndim] multi-indices of `scores` from the largest value down (role of `lib/pytorch_misc.py::argsort_desc`)."""
+    scores = np.asarray(scores)
+    return np.stack(np.unravel_index(np.argsort(-scores, axis=None), scores.shape), 1)
+
+
 def bbox_overlaps(boxes: np.ndarray, query_boxes: np.ndarray) -> np.ndarray:
     """IoU [N, K] of xyxy boxes with pixel-inclusive extents (w = x2 - x1 + 1), zero when the intersection is empty."""
     b = np.asarray(boxes, dtype=np.float64)[:, None, :]
