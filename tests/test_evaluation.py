@@ -137,3 +137,26 @@ def test_coco_evaluator_interface():
     ev.accumulate()
     ev.summarize()
     assert abs(ev.coco_eval["bbox"].stats[1] - 1.0) < 1e-9  # AP50, the number evaluate_egtr.py:103 reports
+
+
+def test_oi_evaluator_edge_cases():
+    """Images without ground-truth relations (the reference's evaluator raises KeyError there), without predictions, and a perfect
+    prediction: recall and both mAPs are 1 for the latter, the former two only dilute them."""
+    import numpy as np
+    from egtr_b200.oi_evaluation import OIEvaluator
+    ev = OIEvaluator(["on", "under"], ["a", "b", "c"])
+    boxes = np.array([[0, 0, 50, 50], [60, 60, 120, 120]], np.float32)
+    gt = dict(gt_boxes=boxes, gt_classes=np.array([0, 1]), gt_relations=np.array([[0, 1, 1]]))
+    pairs = np.array([(s, o) for s in range(2) for o in range(2)])
+    scores = np.zeros((4, 2), np.float32)
+    scores[1, 1] = 0.9  # pair (0, 1), predicate 1
+    ev(gt, dict(pred_boxes=boxes.copy(), pred_classes=np.array([0, 1]), obj_scores=np.array([0.9, 0.8], np.float32), sbj_obj_inds=pairs, pred_scores=scores))
+    m = ev.aggregate_metrics()
+    assert abs(m["microR@50"] - 1.0) < 1e-9 and abs(m["w_rel_mAP"] - 1.0) < 1e-9 and abs(m["w_phr_mAP"] - 1.0) < 1e-9 and abs(m["score"] - 1.0) < 1e-9
+    # an image with no ground-truth relation and one with all-zero predicate scores
+    ev(dict(gt_boxes=boxes, gt_classes=np.array([0, 1]), gt_relations=np.zeros((0, 3), np.int64)),
+       dict(pred_boxes=boxes.copy(), pred_classes=np.array([0, 1]), obj_scores=np.array([0.9, 0.8], np.float32), sbj_obj_inds=pairs, pred_scores=scores))
+    ev(gt, dict(pred_boxes=boxes.copy(), pred_classes=np.array([0, 1]), obj_scores=np.array([0.9, 0.8], np.float32), sbj_obj_inds=pairs,
+                pred_scores=np.zeros((4, 2), np.float32)))
+    m2 = ev.aggregate_metrics()
+    assert abs(m2["microR@50"] - 0.5) < 1e-9 and 0.0 < m2["w_rel_mAP"] <= 1.0
