@@ -115,6 +115,66 @@ def level_shapes(H: int, W: int, num_levels: int = 4) -> List[Tuple[int, int]]:
     return shapes[:num_levels]
 
 
+def fused_decoder_matrices(sd: Dict[str, torch.Tensor], layers: int, query_pos: torch.Tensor, heads: int = 8) -> Dict[str, torch.Tensor]:
+    """fp32 operands of the one-kernel decoder stack (decoder.cu, `egtr_decoder_weights_t`) from the reference's state-dict keys —
+    pure torch, any device.  Every projection is stacked over the layers; the q | k | v rows are head-major (CTA r of the cluster
+    owns head r: q_r | k_r | v_r, q pre-scaled by head_dim^-0.5 as `deformable_detr.py:1166` does after the projection); the
+    offsets / logits rows likewise (head r: its 32 sampling-offset rows | its 16 attention-logit rows); the `query_pos` halves of
+    `(h + query_pos) . W` (deformable_detr.py:1404-1409, 1040) are weight-only terms composed in fp64 into per-layer row biases in
+    the STANDARD column order (`qkv_pos` [L, N, 3d]: q | k | v incl. biases, `off_pos` [L, N, 384])."""
+    d = query_pos.shape[1]
+    hd = d // heads
+    scaling = hd ** -0.5
+    qpos = query_pos.double()
+    N = qpos.shape[0]
+    wq, wo, woff, wout, w1, w2, vec, qkv_pos, off_pos = [], [], [], [], [], [], [], [], []
+    for i in range(layers):
+        p = f"model.decoder.layers.{i}."
+        q_w, q_b = sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.q_proj.bias"] * scaling
+        k_w, k_b = sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"]
+        v_w, v_b = sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"]
+        wq.append(torch.stack([q_w.view(heads, hd, d), k_w.view(heads, hd, d), v_w.view(heads, hd, d)], 1).reshape(3 * d, d))
+        qkv_pos.append(torch.cat([qpos @ q_w.double().t() + q_b.double(), qpos @ k_w.double().t() + k_b.double(),
+                                  v_b.double().expand(N, -1)], 1).float())
+        wo.append(sd[p + "self_attn.out_proj.weight"])
+        ow = torch.cat([sd[p + "encoder_attn.sampling_offsets.weight"], sd[p + "encoder_attn.attention_weights.weight"]], 0)
+        ob = torch.cat([sd[p + "encoder_attn.sampling_offsets.bias"], sd[p + "encoder_attn.attention_weights.bias"]], 0)
+        n_off = sd[p + "encoder_attn.sampling_offsets.weight"].shape[0]  # heads * levels * points * 2
+        po, pl = n_off // heads, (ow.shape[0] - n_off) // heads
+        woff.append(torch.cat([torch.cat([ow[po * r: po * (r + 1)], ow[n_off + pl * r: n_off + pl * (r + 1)]], 0) for r in range(heads)], 0))
+        off_pos.append((qpos @ ow.double().t() + ob.double()).float())
+        wout.append(sd[p + "encoder_attn.output_proj.weight"])
+        w1.append(sd[p + "fc1.weight"])
+        w2.append(sd[p + "fc2.weight"])
+        vec.append(torch.cat([sd[p + "self_attn.out_proj.bias"], sd[p + "encoder_attn.output_proj.bias"], sd[p + "fc2.bias"],
+                              sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"],
+                              sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"],
+                              sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], sd[p + "fc1.bias"]]))
+    cat = lambda ws: torch.cat(ws, 0).float().contiguous()  # noqa: E731
+    return dict(w_qkv=cat(wq), w_o=cat(wo), w_offaw=cat(woff), w_out=cat(wout), w_fc1=cat(w1), w_fc2=cat(w2), vec=torch.stack(vec).float().contiguous(),
+                qkv_pos=torch.stack(qkv_pos).contiguous(), off_pos=torch.stack(off_pos).contiguous())
+
+
+def stem_weight_rows(w: torch.Tensor, layout: int, krow: int) -> torch.Tensor:
+    """The stem's weights laid out like the operand rows its tensor map delivers (stem.cu, include/egtr_b200.h).  `w`: the BN-folded
+    conv1 weight [64, 3, 7, 7] (fp32).  layout 1 -> fp32 [64, 7 * krow] with w[o][ky][4 * kx + c] (to be split into hi / lo planes);
+    layout 2 (one image plane, hi | lo interleaved per pixel) -> bf16 [2, 64, 7 * 64]: set 0 = hi(w) at elements 8 * kx + c AND
+    8 * kx + 4 + c, set 1 = lo(w) at 8 * kx + c; zeros elsewhere."""
+    o = w.shape[0]
+    w7 = torch.cat([w, w.new_zeros(o, 1, 7, 7)], 1).permute(0, 2, 3, 1).contiguous().float()  # [64, ky, kx, 4]
+    if layout == 2:
+        hi = w7.to(torch.bfloat16)
+        lo = (w7 - hi.float()).to(torch.bfloat16)
+        sets = torch.zeros(2, o, 7, 8, 8, dtype=torch.bfloat16, device=w.device)
+        sets[0, :, :, :7, 0:4] = hi
+        sets[0, :, :, :7, 4:8] = hi
+        sets[1, :, :, :7, 0:4] = lo
+        return sets.reshape(2, o, 7 * 64).contiguous()
+    wt = torch.zeros(o, 7, krow, dtype=torch.float32, device=w.device)
+    wt[:, :, :28] = w7.reshape(o, 7, 28)
+    return wt.reshape(o, 7 * krow).contiguous()
+
+
 class Engine:
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], device, model_only: bool = False):
         """`model_only`: the bare `DeformableDetrModel` (backbone -> encoder -> decoder; `state_dict` holds the `model.*` keys
@@ -193,22 +253,13 @@ class Engine:
         # TMA-fed stem (stem.cu): weights laid out like the operand rows its tensor map delivers (include/egtr_b200.h)
         self.stem_mode = os.environ.get("EGTR_STEM", "tma")
         krow = int(call("egtr_stem_krow"))
-        w7 = torch.cat([w, w.new_zeros(w.shape[0], 1, 7, 7)], 1).permute(0, 2, 3, 1).contiguous().float()  # [64, ky, kx, 4]
-        if int(call("egtr_stem_layout")) == 2:
-            # one image plane with hi | lo interleaved per pixel: set B13 = w_hi at the hi and the lo positions, set B2 = w_lo at the hi ones
-            hi = w7.to(torch.bfloat16)
-            lo = (w7 - hi.float()).to(torch.bfloat16)
-            sets = torch.zeros(2, w.shape[0], 7, 8, 8, dtype=torch.bfloat16, device=dev)
-            sets[0, :, :, :7, 0:4] = hi
-            sets[0, :, :, :7, 4:8] = hi
-            sets[1, :, :, :7, 0:4] = lo
-            self.stem_w_planes = sets.reshape(-1).contiguous()
+        layout = int(call("egtr_stem_layout"))
+        rows = stem_weight_rows(w, layout, krow)
+        if layout == 2:
+            self.stem_w_planes = rows.reshape(-1).contiguous()
         else:
-            wt = torch.zeros(w.shape[0], 7, krow, dtype=torch.float32, device=dev)
-            wt[:, :, :28] = w7.reshape(w.shape[0], 7, 28)
-            wt = wt.reshape(w.shape[0], 7 * krow).contiguous()
-            self.stem_w_planes = torch.empty(2 * wt.shape[0] * wt.shape[1], dtype=torch.bfloat16, device=dev)
-            call("egtr_split_weight_bf16", _ptr(wt), wt.shape[0], wt.shape[1], wt.shape[0], _ptr(self.stem_w_planes), _stream())
+            self.stem_w_planes = torch.empty(2 * rows.shape[0] * rows.shape[1], dtype=torch.bfloat16, device=dev)
+            call("egtr_split_weight_bf16", _ptr(rows), rows.shape[0], rows.shape[1], rows.shape[0], _ptr(self.stem_w_planes), _stream())
         self.stem_bias = b.detach().to(device=dev, dtype=torch.float32).contiguous()
         self.blocks = []
         for li, nblk in enumerate(RESNET_BLOCKS, start=1):
@@ -275,7 +326,7 @@ class Engine:
         self.refpt_w = sd["model.reference_points.weight"].contiguous()
         self.refpt_b = sd["model.reference_points.bias"].contiguous()
 
-        self._prepare_fused_decoder(sd, scaling)
+        self._prepare_fused_decoder(sd)
 
         if self.model_only:
             torch.cuda.current_stream().synchronize()
@@ -290,7 +341,7 @@ class Engine:
         self._prepare_relation_head(sd)
         torch.cuda.current_stream().synchronize()
 
-    def _prepare_fused_decoder(self, sd, scaling: float):
+    def _prepare_fused_decoder(self, sd):
         """Weights of the one-kernel decoder stack (decoder.cu, `egtr_decoder_weights_t`): every projection stacked over the
         layers as bf16 hi/lo planes; q|k|v rows head-major (CTA r of the cluster owns head r); the `query_pos` halves of
         `(h + query_pos) . W` (deformable_detr.py:1404-1409, 1040) are weight-only terms, composed here in fp64."""
@@ -299,40 +350,17 @@ class Engine:
         self.dec_fused_ok = N <= 256 and cfg.decoder_ffn_dim == 1024 and d == 256
         if not self.dec_fused_ok:
             return
-        qpos = self.query_pos.double()
-        wq, wo, woff, wout, w1, w2, vec, qkv_pos, off_pos = [], [], [], [], [], [], [], [], []
-        for i in range(nl):
-            p = f"model.decoder.layers.{i}."
-            q_w, q_b = sd[p + "self_attn.q_proj.weight"] * scaling, sd[p + "self_attn.q_proj.bias"] * scaling
-            k_w, k_b = sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"]
-            v_w, v_b = sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"]
-            wq.append(torch.stack([q_w.view(8, 32, d), k_w.view(8, 32, d), v_w.view(8, 32, d)], 1).reshape(768, d))
-            qkv_pos.append(torch.cat([qpos @ q_w.double().t() + q_b.double(), qpos @ k_w.double().t() + k_b.double(),
-                                      v_b.double().expand(N, -1)], 1).float())
-            wo.append(sd[p + "self_attn.out_proj.weight"])
-            ow = torch.cat([sd[p + "encoder_attn.sampling_offsets.weight"], sd[p + "encoder_attn.attention_weights.weight"]], 0)
-            ob = torch.cat([sd[p + "encoder_attn.sampling_offsets.bias"], sd[p + "encoder_attn.attention_weights.bias"]], 0)
-            # kernel weight rows head-major: head r = its 32 offset rows (columns 32r..) | its 16 logit rows (columns 256 + 16r..)
-            woff.append(torch.cat([torch.cat([ow[32 * r: 32 * r + 32], ow[256 + 16 * r: 256 + 16 * r + 16]], 0) for r in range(8)], 0))
-            off_pos.append((qpos @ ow.double().t() + ob.double()).float())
-            wout.append(sd[p + "encoder_attn.output_proj.weight"])
-            w1.append(sd[p + "fc1.weight"])
-            w2.append(sd[p + "fc2.weight"])
-            vec.append(torch.cat([sd[p + "self_attn.out_proj.bias"], sd[p + "encoder_attn.output_proj.bias"], sd[p + "fc2.bias"],
-                                  sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"],
-                                  sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"],
-                                  sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], sd[p + "fc1.bias"]]))
+        mats = fused_decoder_matrices(sd, nl, self.query_pos, cfg.decoder_attention_heads)
 
-        def planes(ws):
-            w = torch.cat(ws, 0).to(device=dev, dtype=torch.float32).contiguous()
+        def planes(w):
+            w = w.to(device=dev, dtype=torch.float32).contiguous()
             out = torch.empty(2 * w.shape[0] * w.shape[1], dtype=torch.bfloat16, device=dev)
             call("egtr_split_weight_bf16", _ptr(w), w.shape[0], w.shape[1], w.shape[0], _ptr(out), _stream())
             return out
 
-        keep = dict(w_qkv=planes(wq), w_o=planes(wo), w_offaw=planes(woff), w_out=planes(wout), w_fc1=planes(w1), w_fc2=planes(w2),
-                    vec=torch.stack(vec).to(dev, torch.float32).contiguous(), qkv_pos=torch.stack(qkv_pos).to(dev).contiguous(),
-                    off_pos=torch.stack(off_pos).to(dev).contiguous(), tgt=self.query_tgt.to(dev, torch.float32).contiguous(),
-                    ref_points=torch.empty(N, 2, dtype=torch.float32, device=dev))
+        keep = {k: planes(mats[k]) for k in ("w_qkv", "w_o", "w_offaw", "w_out", "w_fc1", "w_fc2")}
+        keep.update(vec=mats["vec"].to(dev), qkv_pos=mats["qkv_pos"].to(dev), off_pos=mats["off_pos"].to(dev),
+                    tgt=self.query_tgt.to(dev, torch.float32).contiguous(), ref_points=torch.empty(N, 2, dtype=torch.float32, device=dev))
         call("egtr_small_linear_f32", _ptr(self.query_pos), 256, _ptr(self.refpt_w), _ptr(self.refpt_b), N, 256, 2, 1,
              None, 0, 0, _ptr(keep["ref_points"]), 2, _stream())
         self._dec_fused_tensors = keep  # the struct holds raw pointers
