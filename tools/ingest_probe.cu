@@ -1,5 +1,5 @@
-// L2 -> SM operand ingest probe (sm_100a): how many bytes per clock can ONE SM pull from L2, by TMA, by the load/store unit
-// (cp.async 16 B), and by both at once — and does it depend on how many SMs pull?  The GEMM kernels' operand traffic (64 KB per
+// L2 -> SM operand ingest probe (sm_100a): how many bytes per clock can ONE SM pull from L2 by TMA — and does it depend on how many
+// SMs pull, or on the pitch of the box rows?  The GEMM kernels' operand traffic (64 KB per
 // k-block per SM against 1536 tensor-pipe cycles) needs 42 B/clk/SM at full rate; the fused decoder's 8-SM cluster measured ~24.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o ingest_probe ingest_probe.cu -lcuda
@@ -110,7 +110,7 @@ int main() {
     printf("L2 -> SM ingest per SM (B/clk): rows of 128 B at a pitch of %d B, %d rounds of 32 KB per stream, buffer 64 MB (L2-resident)\n", pitch, iters);
     for (int grid : {1, 8, 74, 148}) {
       if (rows_total / grid < 4 * 2 * BOX_ROWS + 8) continue;
-      for (int mode = 1; mode <= 3; ++mode) {
+      for (int mode = 1; mode <= 1; ++mode) {  // (a cp.async stream, mode bit 1, is built but its timing was never validated: not run)
         for (int rep = 0; rep < 2; ++rep) {  // first pass warms L2
           probe<<<grid, THREADS, smem>>>(map, buf, rows_total, iters, mode, pitch, out);
           CK(cudaDeviceSynchronize());
